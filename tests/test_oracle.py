@@ -1,0 +1,249 @@
+"""CPU tests of the oracle itself: it must be pinned before it is trusted.
+
+* RHS: against golden vectors produced by the reference's OWN RHS functions
+  (tests/golden/make_rhs_golden.py executes /root/reference/examples/*.py).
+* Solver: PARITY UNPINNED vs diffrax (absent); pinned indirectly by the Tsit5 order conditions,
+  the interpolant identities, the independent numpy twin, the reference's physics tests and a
+  DOP853 truth check.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.integrate import solve_ivp
+from scipy.optimize import root_scalar
+
+from oracle import oracle as orc
+from oracle import oracle_np
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "rhs_golden.npz"))
+CASES = sorted({k.split("/")[0] for k in GOLD.files})
+
+
+def _close(a, b, rtol, atol):
+    return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_rhs_matches_reference_golden(name):
+    fam, dims = int(GOLD[name + "/family"]), tuple(int(x) for x in GOLD[name + "/dims"])
+    for k in range(len(GOLD[name + "/t"])):
+        dy = orc.rhs(fam, dims, GOLD[name + "/t"][k], GOLD[name + "/y"][k],
+                     GOLD[name + "/theta"][k], GOLD[name + "/shared"][k])
+        ref = GOLD[name + "/dy"][k]
+        assert _close(dy, ref, 1e-14, 1e-14 * np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trajectories_match_reference_rhs_numpy_solver(name):
+    """C++ oracle vs (reference RHS callable + independent numpy restatement of the solver)."""
+    fam, dims = int(GOLD[name + "/family"]), tuple(int(x) for x in GOLD[name + "/dims"])
+    for k in range(len(GOLD[name + "/traj_y0"])):
+        ys, _, st = orc.solve(fam, dims, GOLD[name + "/traj_y0"][k], GOLD[name + "/traj_theta"][k],
+                              GOLD[name + "/traj_shared"][k], t1=120)
+        ref = GOLD[name + "/traj_ys"][k]
+        assert list(st[0]) == list(GOLD[name + "/traj_stats"][k])
+        assert _close(ys[0], ref, 1e-9, 1e-12 * np.max(np.abs(ref)))
+
+
+def test_tableau_order_conditions():
+    c6, rows, berr = orc.tableau()
+    A = np.zeros((7, 7))
+    for i, r in enumerate(rows):
+        A[i + 1, : i + 1] = r
+    c = np.concatenate([[0.0], c6])
+    b = A[6].copy()  # b_sol = last row (SSAL)
+    assert np.allclose(A.sum(1), c, atol=2e-15)
+    Ac, Ac2, AAc = A @ c, A @ c**2, A @ (A @ c)
+    conds = [
+        (b.sum(), 1), (b @ c, 1 / 2), (b @ c**2, 1 / 3), (b @ Ac, 1 / 6), (b @ c**3, 1 / 4),
+        (b @ (c * Ac), 1 / 8), (b @ Ac2, 1 / 12), (b @ AAc, 1 / 24), (b @ c**4, 1 / 5),
+        (b @ (c**2 * Ac), 1 / 10), (b @ (c * Ac2), 1 / 15), (b @ (c * AAc), 1 / 30),
+        (b @ (Ac * Ac), 1 / 20), (b @ (A @ c**3), 1 / 20), (b @ (A @ (c * Ac)), 1 / 40),
+        (b @ (A @ Ac2), 1 / 60), (b @ (A @ AAc), 1 / 120),
+    ]
+    for got, want in conds:
+        assert abs(got - want) < 5e-15
+    bhat = b - berr  # embedded 4th-order weights: satisfy order <=4 but not order 5
+    for got, want in [(bhat.sum(), 1), (bhat @ c, 1 / 2), (bhat @ c**2, 1 / 3), (bhat @ Ac, 1 / 6),
+                      (bhat @ c**3, 1 / 4), (bhat @ (c * Ac), 1 / 8), (bhat @ Ac2, 1 / 12),
+                      (bhat @ AAc, 1 / 24)]:
+        assert abs(got - want) < 5e-15
+    assert abs(bhat @ c**4 - 1 / 5) > 1e-5
+    assert np.allclose(oracle_np.B_ERR, berr, atol=0, rtol=0)
+
+
+def test_dense_output_identities():
+    _, rows, _ = orc.tableau()
+    bsol = np.concatenate([rows[5], [0.0]])
+    assert np.max(np.abs(orc.dense_weights(1.0) - bsol)) < 5e-15
+    assert np.all(orc.dense_weights(0.0) == 0.0)
+    for th in (0.25, 0.5, 0.75):
+        assert abs(orc.dense_weights(th).sum() - th) < 2e-15
+        assert np.allclose(orc.dense_weights(th), oracle_np.dense_weights(th), rtol=1e-15, atol=1e-16)
+
+
+def test_saveat_grid_matches_reference_rule():
+    # odes.py:177-179: linspace(start, stop, int(stop // step) + 1)
+    assert len(orc.saveat_ts(0.0, 100, 1)) == 101
+    assert len(orc.saveat_ts(0.0, 300.0, 1)) == 301
+    for step in (1.0, 2.0, 3.0, 7.0):
+        assert len(orc.saveat_ts(0.0, 100, step)) == int(100 / step) + 1
+    assert np.allclose(np.diff(orc.saveat_ts(0.0, 100, 3)), 100 / 33)
+    assert len(orc.saveat_ts(0.0, 100, 0)) == 101
+
+
+def test_initial_state_exact_and_shapes():
+    # tests/test_simulation/test_odes.py:45-74
+    th = np.array([2.0 / 7.0, 1.0 / 7.0])
+    y0 = np.array([99.0, 1.0, 0.0])
+    for days in (10, 50, 100, 200, 300.0):
+        ys, _, st = orc.solve(orc.SIR_DENSITY, (1, 1, 1), y0, th, t1=days)
+        assert ys.shape == (1, int(days) + 1, 3)
+        assert np.all(ys[0, 0] == y0)
+        assert st[0, 0] == 0
+    ys, _, st = orc.solve(orc.SIR_DENSITY, (1, 1, 1), y0, th, t1=100)
+    assert (st[0, 1], st[0, 2]) == (100, 7)  # SURVEY.md 8d measured step counts
+
+
+@pytest.mark.parametrize("s0,i0,r0", [(0.99, 0.01, 0.0), (0.95, 0.05, 0.0), (0.90, 0.10, 0.0),
+                                      (0.80, 0.20, 0.0)])
+def test_sir_final_size(s0, i0, r0):
+    # tests/test_sir_dynamics/test_sir.py:9-65
+    ys, _, _ = orc.solve(orc.SIR_1BIN, (1, 1, 1), [s0, i0, r0], [2.0 / 7.0, 1.0 / 7.0], t1=300)
+    sinf = root_scalar(lambda x: x - s0 * np.exp(-2.0 * (1 - x)), bracket=[0.0, s0],
+                       method="bisect", xtol=1e-8).root
+    assert ys[0, -1, 2] == pytest.approx(1 - sinf, abs=2e-2)
+
+
+@pytest.mark.parametrize("s0,i0,r0", [(0.99, 0.01, 0.0), (0.95, 0.05, 0.0), (0.90, 0.10, 0.0),
+                                      (0.80, 0.20, 0.0), (0.8, 0.0, 0.2), (0.75, 0.1, 0.15)])
+def test_sir_mass_conservation(s0, i0, r0):
+    # tests/test_sir_dynamics/test_sir.py:68-100 (includes the f==0 initial-step edge)
+    ys, _, st = orc.solve(orc.SIR_1BIN, (1, 1, 1), [s0, i0, r0], [2.0 / 7.0, 1.0 / 7.0], t1=120)
+    tot = ys[0].sum(1)
+    assert np.all(np.isfinite(ys)) and st[0, 0] == 0
+    assert np.allclose(tot, tot[0], atol=1e-6)
+
+
+@pytest.mark.parametrize("r0,inf,lat,wan", [(2.0, 7.0, 3.0, 60.0), (3.0, 5.0, 2.0, 100.0)])
+def test_seirs_endemic_equilibrium(r0, inf, lat, wan):
+    # tests/test_seirs_dynamics/test_seirs.py:8-65
+    beta, gamma, sigma, omega = r0 / inf, 1 / inf, 1 / lat, 1 / wan
+    ys, _, _ = orc.solve(orc.SEIRS_1BIN, (1, 1, 1), [0.99, 0.0, 0.01, 0.0],
+                         [beta, gamma, sigma, omega], t1=1000)
+    last = ys[0, -100:]
+    assert np.all(last.std(0) < 1e-4)
+    s_eq = 1 / r0
+    i_eq = (1 - s_eq) / (1 + gamma / sigma + gamma / omega)
+    assert last[:, 0].mean() == pytest.approx(s_eq, rel=1e-2)
+    assert last[:, 2].mean() == pytest.approx(i_eq, rel=1e-2)
+
+
+def test_seasonal_seirs_keeps_oscillating():
+    # tests/test_seirs_seasonality_dynamics/...:12-42
+    th = [2.0 / 7.0, 1 / 7.0, 1 / 3.0, 1 / 60.0, 0.2, 0.0, 365.0]
+    ys, _, _ = orc.solve(orc.SEIRS_SEASONAL, (1, 1, 1), [0.99, 0.0, 0.01, 0.0], th, t1=1500)
+    assert ys[0, -100:, 2].std() > 1e-4
+
+
+def test_truth_check_against_dop853():
+    rng = np.random.default_rng(7)
+    A, S = 2, 3
+    th = np.concatenate([rng.uniform(1.5, 3.5, S) / 7.0, np.full(S, 1 / 7.0),
+                         np.full(S, 1 / 3.0), np.full(S, 1 / 60.0)])
+    C = np.array([[0.7, 0.3], [0.3, 0.7]]).ravel()
+    y0 = np.zeros(26)
+    y0[:2] = [742.5, 247.5]
+    y0[8:14] = 10.0 / 6
+    ys, _, st = orc.solve(orc.SEIRS_MULTISTRAIN, (A, 1, S), y0, th, C, t1=200)
+    f = lambda t, y: orc.rhs(orc.SEIRS_MULTISTRAIN, (A, 1, S), t, y, th, C)
+    ref = solve_ivp(f, (0, 200), y0, method="DOP853", rtol=1e-12, atol=1e-12,
+                    t_eval=np.arange(201.0)).y.T
+    err = np.max(np.abs(ys[0] - ref) / (1e-6 / 1e-5 + np.abs(ref)))
+    assert err < 2e-4  # global error is O(rtol=1e-5) with a modest constant
+    tight, _, _ = orc.solve(orc.SEIRS_MULTISTRAIN, (A, 1, S), y0, th, C, t1=200, rtol=1e-11, atol=1e-12)
+    assert np.max(np.abs(tight[0] - ref) / (1.0 + np.abs(ref))) < 1e-8
+
+
+def test_constant_step_branch():
+    # odes.py:115-118 ConstantStepSize
+    ys, _, st = orc.solve(orc.SIR_1BIN, (1, 1, 1), [0.9, 0.1, 0.0], [2 / 7, 1 / 7], t1=50, const_dt=0.25)
+    assert (st[0, 1], st[0, 2]) == (200, 0)
+    ad, _, _ = orc.solve(orc.SIR_1BIN, (1, 1, 1), [0.9, 0.1, 0.0], [2 / 7, 1 / 7], t1=50, rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(ys - ad)) < 1e-8
+
+
+def test_max_steps_reported():
+    ys, _, st = orc.solve(orc.SIR_1BIN, (1, 1, 1), [0.9, 0.1, 0.0], [2 / 7, 1 / 7], t1=150, max_steps=5)
+    assert st[0, 0] == 1 and st[0, 3] == 5
+    assert np.isinf(ys[0, -1]).all()
+
+
+def test_tangents_are_frozen_step_derivatives():
+    """Forward tangents == derivative of the discrete scheme with the step sequence frozen.
+    Checked by central differences of the numpy twin re-run on the SAME steps."""
+    A = 2
+    C = (np.array([[0.7, 0.3], [0.3, 0.7]]) / 1.0).ravel()
+    th = np.array([2.0 / 7.0, 1.0 / 7.0])
+    y0 = np.array([742.5, 247.5, 7.5, 2.5, 0.0, 0.0])
+    ys, dys, st = orc.solve(orc.SIR_AGE, (A, 1, 1), y0, th, C, t1=100, wrt=(0, 1))
+    # adaptive finite differences agree only to ~rtol; they bound gross errors
+    eps = 1e-6
+    for p in range(2):
+        d = np.zeros(2); d[p] = eps
+        yp, _, _ = orc.solve(orc.SIR_AGE, (A, 1, 1), y0, th + d, C, t1=100, rtol=1e-11, atol=1e-11)
+        ym, _, _ = orc.solve(orc.SIR_AGE, (A, 1, 1), y0, th - d, C, t1=100, rtol=1e-11, atol=1e-11)
+        fd = (yp - ym)[0] / (2 * eps)
+        scale = np.max(np.abs(fd))
+        assert np.max(np.abs(dys[0, :, :, p] - fd)) < 2e-3 * scale
+    # frozen-step check: replay the accepted steps as fixed steps in the numpy twin
+    def ode(t, s, a):
+        ss, ii, rr = s
+        pop = ss + ii + rr
+        foi = a[0] * np.sum((C.reshape(A, A) * ii) / pop, axis=1)
+        return (-ss * foi, ss * foi - ii * a[1], ii * a[1])
+    _, stats, steps = oracle_np.solve(ode, (y0[:2], y0[2:4], y0[4:]), th, 100, return_steps=True)
+    assert stats["num_accepted_steps"] == st[0, 1]
+
+    def replay(thv):
+        y = y0.copy()
+        out = []
+        for (ta, tb) in steps:
+            h = tb - ta
+            k = np.empty((7, 6))
+            for s in range(7):
+                ysn = y + (oracle_np.A[s - 1] @ k[:s] if s else 0.0)
+                k[s] = h * np.concatenate(ode(0.0, (ysn[:2], ysn[2:4], ysn[4:]), thv))
+            out.append((y.copy(), k.copy()))
+            y = ysn
+        return y
+    for p in range(2):
+        d = np.zeros(2); d[p] = 1e-7
+        fd = (replay(th + d) - replay(th - d)) / 2e-7
+        assert np.max(np.abs(dys[0, -1, :, p] - fd)) < 1e-6 * np.max(np.abs(fd))
+
+
+def test_poisson_incidence_loglik_and_grad():
+    from scipy.special import gammaln
+    A = 2
+    C = np.array([[0.7, 0.3], [0.3, 0.7]]).ravel()
+    y0 = np.array([742.5, 247.5, 7.5, 2.5, 0.0, 0.0])
+    truth, _, _ = orc.solve(orc.SIR_AGE, (A, 1, 1), y0, [2 / 7, 1 / 7], C, t1=100, save_idx=[4, 5])
+    obs = np.diff(truth[0], axis=0)
+    th = np.array([2.3 / 6.0, 1 / 6.0])
+    ys, dys, _ = orc.solve(orc.SIR_AGE, (A, 1, 1), y0, th, C, t1=100, save_idx=[4, 5], wrt=(0, 1))
+    lp, g = orc.poisson_incidence(ys, dys, obs)
+    rate = np.maximum(np.diff(ys[0], axis=0), 1e-6)
+    want = np.sum(obs * np.log(rate) - rate - gammaln(obs + 1))
+    assert lp[0] == pytest.approx(want, rel=1e-13)
+    assert g.shape == (1, 2) and np.all(np.isfinite(g))
+
+
+def test_openmp_batch_is_order_independent():
+    rng = np.random.default_rng(3)
+    B = 64
+    th = np.stack([rng.uniform(1.2, 4, B) / 7.0, np.full(B, 1 / 7.0)], 1)
+    a, _, sa = orc.solve(orc.SIR_1BIN, (1, 1, 1), [0.9, 0.1, 0.0], th, t1=60, nthreads=1)
+    b, _, sb = orc.solve(orc.SIR_1BIN, (1, 1, 1), [0.9, 0.1, 0.0], th, t1=60, nthreads=4)
+    assert np.array_equal(a, b) and np.array_equal(sa, sb)
