@@ -1,0 +1,86 @@
+"""In-tree build of libdynode_b200.so (hand-written sm_100a CUDA + the C ABI).
+
+nvcc cross-compiles without a GPU; one translation unit per flow-family instance
+(csrc/instances.def) so the instances build in parallel.  The .so is git-ignored but travels to
+the GPU box with the repo snapshot.
+"""
+
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libdynode_b200.so")
+INCLUDE = os.path.join(HERE, "..", "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def instance_ids():
+    txt = open(os.path.join(CSRC, "instances.def")).read()
+    return [int(m) for m in re.findall(r"^X\((\d+),", txt, flags=re.M)]
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "dynode_b200.h")]
+    return deps
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _sources())
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = []
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_v else [])
+    for k in instance_ids():
+        obj = os.path.join(BUILD, f"inst_{k}.o")
+        jobs.append((obj, [nvcc, *flags, f"-DDYN_INST={k}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]))
+    obj = os.path.join(BUILD, "capi.o")
+    jobs.append((obj, [nvcc, *flags, "-c", os.path.join(CSRC, "capi.cu"), "-o", obj]))
+
+    def run(job):
+        obj, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(run, jobs))
+    if verbose or ptxas_v:
+        for obj, log in results:
+            if log.strip():
+                print(f"--- {os.path.basename(obj)}\n{log}", file=sys.stderr)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _ in results]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True, ptxas_v="--ptxas-v" in sys.argv))

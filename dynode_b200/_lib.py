@@ -1,0 +1,121 @@
+"""ctypes binding of libdynode_b200.so (the C ABI in include/dynode_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or no CUDA device is present,
+every compute entry point raises.  torch is used only for device memory and streams.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdynode_b200.so")
+
+FLOW_SIR, FLOW_SEIRS, FLOW_SEIRS_C = 0, 1, 2
+FLAG_SEASONAL, FLAG_DENSITY_DEP = 1, 2
+P_BETA, P_GAMMA, P_SIGMA, P_OMEGA, P_SEASON_AMP, P_SEASON_PHASE = range(6)
+STAT_RESULT, STAT_ACCEPTED, STAT_REJECTED, STAT_STEPS = range(4)
+
+EXPORTED_SYMBOLS = (
+    "dynode_version", "dynode_last_error", "dynode_state_size", "dynode_num_compartments",
+    "dynode_saved_size", "dynode_is_supported", "dynode_solve_f64", "dynode_solve_sens_f64",
+    "dynode_poisson_loglik_grad_f64", "dynode_probe_dfma", "dynode_probe_hbm_write",
+)
+
+
+def wrt_id(kind: int, strain: int = 0) -> int:
+    return kind * 16 + strain
+
+
+class DynodeError(RuntimeError):
+    """Raised when the native library rejects a call (invalid argument / unsupported ODE)."""
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("flow", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("n_groups", ctypes.c_int32), ("n_strains", ctypes.c_int32)]
+
+
+class SolverDesc(ctypes.Structure):
+    _fields_ = [("t0", ctypes.c_double), ("t1", ctypes.c_double), ("rtol", ctypes.c_double),
+                ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64)]
+
+
+class Array(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("beta", Array), ("gamma", Array), ("sigma", Array), ("omega", Array),
+                ("season_amp", Array), ("season_phase", Array), ("season_period", Array),
+                ("contact", ctypes.c_void_p)]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load the native library (building it in-tree with nvcc if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise DynodeError(f"{LIB_PATH} is missing; run `python -m dynode_b200._build`")
+        from . import _build
+        _build.build()
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_uint32
+    MP, SP, PP = ctypes.POINTER(ModelDesc), ctypes.POINTER(SolverDesc), ctypes.POINTER(Params)
+    L.dynode_version.restype = ctypes.c_int
+    L.dynode_last_error.restype = ctypes.c_char_p
+    for f in (L.dynode_state_size, L.dynode_num_compartments, L.dynode_is_supported):
+        f.restype = ctypes.c_int
+        f.argtypes = [MP]
+    L.dynode_saved_size.restype = ctypes.c_int
+    L.dynode_saved_size.argtypes = [MP, u32]
+    L.dynode_solve_f64.restype = ctypes.c_int
+    L.dynode_solve_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, u32, vp, vp, vp]
+    L.dynode_solve_sens_f64.restype = ctypes.c_int
+    L.dynode_solve_sens_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, u32, i32,
+                                        ctypes.POINTER(i32), vp, vp, vp, vp, vp]
+    L.dynode_poisson_loglik_grad_f64.restype = ctypes.c_int
+    L.dynode_poisson_loglik_grad_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, i32, vp, dbl, i32,
+                                                 ctypes.POINTER(i32), vp, vp, vp, vp, vp]
+    L.dynode_probe_dfma.restype = i64
+    L.dynode_probe_dfma.argtypes = [vp, i32, vp]
+    L.dynode_probe_hbm_write.restype = ctypes.c_int
+    L.dynode_probe_hbm_write.argtypes = [vp, i64, vp]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return load().dynode_last_error().decode()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DynodeError(last_error())
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise DynodeError(
+            "dynode_b200 needs a CUDA device (B200, sm_100a): the engine has no CPU fallback")
+    return torch
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def i32_array(vals: Sequence[int]):
+    arr = (ctypes.c_int32 * max(1, len(vals)))(*vals)
+    return arr

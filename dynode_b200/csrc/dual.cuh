@@ -1,0 +1,98 @@
+// dual.cuh -- forward-mode dual numbers held in registers: value + P tangents.
+// Carrying tangents through the accepted Tsit5 steps differentiates the discrete scheme with the
+// step sequence frozen, which is what the reference's reverse-mode pass through diffrax computes
+// (stop_gradient on the controller factor and on the automatic dt0).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dynode {
+
+template <int P>
+struct Dual {
+  double v;
+  double d[P];
+};
+template <>
+struct Dual<0> {
+  double v;
+};
+
+#define DYN_DI __device__ __forceinline__
+
+template <int P> DYN_DI Dual<P> make_dual(double x) {
+  Dual<P> r; r.v = x;
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = 0.0;
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> operator+(const Dual<P>& a, const Dual<P>& b) {
+  Dual<P> r; r.v = a.v + b.v;
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = a.d[p] + b.d[p];
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> operator-(const Dual<P>& a, const Dual<P>& b) {
+  Dual<P> r; r.v = a.v - b.v;
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = a.d[p] - b.d[p];
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> operator*(const Dual<P>& a, const Dual<P>& b) {
+  Dual<P> r; r.v = a.v * b.v;
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = fma(a.d[p], b.v, a.v * b.d[p]);
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> operator*(double a, const Dual<P>& b) {
+  Dual<P> r; r.v = a * b.v;
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = a * b.d[p];
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> operator/(const Dual<P>& a, const Dual<P>& b) {
+  Dual<P> r; r.v = a.v / b.v;
+  if constexpr (P > 0) {
+    const double inv = 1.0 / b.v;
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = fma(-r.v, b.d[p], a.d[p]) * inv;
+  }
+  return r;
+}
+// r = a*b + c
+template <int P> DYN_DI Dual<P> dfma(double a, const Dual<P>& b, const Dual<P>& c) {
+  Dual<P> r; r.v = fma(a, b.v, c.v);
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = fma(a, b.d[p], c.d[p]);
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> dual_shfl(const Dual<P>& a, int src) {
+  Dual<P> r; r.v = __shfl_sync(0xffffffffu, a.v, src);
+  if constexpr (P > 0) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = __shfl_sync(0xffffffffu, a.d[p], src);
+  }
+  return r;
+}
+template <int P> DYN_DI Dual<P> dual_log(const Dual<P>& a) {
+  Dual<P> r; r.v = log(a.v);
+  if constexpr (P > 0) {
+    const double inv = 1.0 / a.v;
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = a.d[p] * inv;
+  }
+  return r;
+}
+
+}  // namespace dynode

@@ -1,0 +1,22 @@
+// inst.cu -- explicit instantiation of the kernels of ONE flow-family instance (-DDYN_INST=k).
+#include "lane_solver.cuh"
+
+#ifndef DYN_INST
+#error "compile with -DDYN_INST=<index from instances.def>"
+#endif
+
+namespace dynode {
+
+template <int IDX> struct Inst;
+#define X(IDX, FLOW, FLAGS, G, S) \
+  template <> struct Inst<IDX> { static constexpr int flow = FLOW, flags = FLAGS, g = G, s = S; };
+#include "instances.def"
+#undef X
+
+using I = Inst<DYN_INST>;
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_SAVE>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_SAVE>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
+
+}  // namespace dynode

@@ -1,0 +1,465 @@
+// lane_solver.cuh -- the ensemble Tsit5 kernel: one trajectory per group of L = G*S lanes,
+// every lane owning the compartments of one (population group g, strain s) cell in REGISTERS.
+//
+// Replaces, for a whole ensemble in one launch, what the reference runs per trajectory through
+// diffrax.diffeqsolve (reference src/dynode/simulation/odes.py:133-144): the while-loop of
+// adaptive Tsit5 steps, the I-controller, and the SaveAt(ts) dense-output writes
+// (SURVEY.md 8a rows a3-a9), on the compartmental right-hand sides of a11.
+//
+// Layout (DESIGN.md "Kernel K1"):
+//   lane (g, s) holds  S_g (replicated across the S lanes of a group, kept bit-identical by
+//   order-fixed segmented sums), and E/I/R/C[g, s]: NE <= 5 state elements, 8*NE doubles with the
+//   7 stage derivatives, all in registers -> no shared/local memory traffic in the step loop.
+//   32/L trajectories share a warp (SIR/SEIRS 1-bin: 32, age SIR: 16, multi-strain 2x3: 5).
+//   Cross-lane terms (N_g, the contact contraction, dS_g, the RMS error norm) are warp shuffles.
+//   FP64 FMA on the CUDA cores; no tensor cores (contractions are <= 6x6).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/dynode_b200.h"
+#include "dual.cuh"
+#include "solve_args.h"
+#include "tsit5.cuh"
+
+namespace dynode {
+
+template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
+struct LaneSolver {
+  static constexpr bool HAS_E = FLOW != DYNODE_FLOW_SIR;
+  static constexpr bool HAS_C = FLOW == DYNODE_FLOW_SEIRS_C;
+  static constexpr bool WANING = FLOW != DYNODE_FLOW_SIR;
+  static constexpr bool SEASONAL = (FLAGS & DYNODE_FLAG_SEASONAL) != 0;
+  static constexpr bool DENSITY = (FLAGS & DYNODE_FLAG_DENSITY_DEP) != 0;
+  static constexpr int NE = 3 + (HAS_E ? 1 : 0) + (HAS_C ? 1 : 0);  // elements per lane
+  static constexpr int IE = 1;
+  static constexpr int II = HAS_E ? 2 : 1;
+  static constexpr int IR = II + 1;
+  static constexpr int IC = IR + 1;
+  static constexpr int L = G * S;
+  static constexpr int TPW = 32 / L;  // trajectories per warp
+  static constexpr int N = G + (NE - 1) * G * S;
+  static_assert(L >= 1 && L <= 32, "a trajectory must fit one warp");
+  using D = Dual<P>;
+
+  struct Ctx {
+    int base;   // lane of cell (0,0) of my trajectory
+    int sbase;  // lane of cell (g,0)
+    int g, s;
+    D beta, gamma, sigma, omega, amp, phase;
+    double period;
+    double K[G];  // contact[g][:]
+  };
+
+  // sum over the S strain lanes of my group, in fixed order (identical in every lane of the group)
+  static DYN_DI D sum_strains(const D& x, const Ctx& c) {
+    if constexpr (S == 1) {
+      return x;
+    } else {
+      D r = dual_shfl(x, c.sbase);
+#pragma unroll
+      for (int k = 1; k < S; ++k) r = r + dual_shfl(x, c.sbase + k);
+      return r;
+    }
+  }
+  static DYN_DI double sum_strains(double x, const Ctx& c) {
+    if constexpr (S == 1) {
+      return x;
+    } else {
+      double r = __shfl_sync(0xffffffffu, x, c.sbase);
+#pragma unroll
+      for (int k = 1; k < S; ++k) r += __shfl_sync(0xffffffffu, x, c.sbase + k);
+      return r;
+    }
+  }
+  // sum over groups of a value that is already identical across the strain lanes of each group
+  static DYN_DI double sum_groups(double x, const Ctx& c) {
+    if constexpr (G == 1) {
+      return x;
+    } else {
+      double r = __shfl_sync(0xffffffffu, x, c.base + c.s);
+#pragma unroll
+      for (int b = 1; b < G; ++b) r += __shfl_sync(0xffffffffu, x, c.base + b * S + c.s);
+      return r;
+    }
+  }
+  // sum of a per-lane partial over the whole trajectory; identical in all of its lanes
+  static DYN_DI double traj_sum(double x, const Ctx& c) { return sum_groups(sum_strains(x, c), c); }
+
+  // ---- right-hand side of the flow family in lane layout -------------
+  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Ctx& c) {
+    D prop;
+    if constexpr (DENSITY) {
+      prop = y[II];  // tests/test_simulation/test_odes.py:23  s_to_i = beta*s*i
+    } else {
+      D part = y[II] + y[IR];
+      if constexpr (HAS_E) part = part + y[IE];
+      const D Ng = y[0] + sum_strains(part, c);  // N_g = s_g + sum_s (e+i+r)[g,s]   (c excluded)
+      prop = y[II] / Ng;
+    }
+    // contact contraction: sum_b K[g][b] * prop[b, s]
+    D acc;
+    if constexpr (G == 1) {
+      acc = c.K[0] * prop;
+    } else {
+      acc = c.K[0] * dual_shfl(prop, c.base + c.s);
+#pragma unroll
+      for (int b = 1; b < G; ++b) acc = dfma(c.K[b], dual_shfl(prop, c.base + b * S + c.s), acc);
+    }
+    D beta_t = c.beta;
+    if constexpr (SEASONAL) {
+      // beta*(1 + amp*sin(2*pi*t/period + phase))   (seirs_seasonal_forcing.py:34-37)
+      const double w = ((2.0 * CUDART_PI) * t) / c.period;
+      D arg = c.phase;
+      arg.v += w;
+      double sn, cs;
+      sincos(arg.v, &sn, &cs);
+      D seas;
+      seas.v = fma(c.amp.v, sn, 1.0);
+      if constexpr (P > 0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) seas.d[p] = fma(c.amp.d[p], sn, c.amp.v * cs * arg.d[p]);
+      }
+      beta_t = c.beta * seas;
+    }
+    const D foi = beta_t * acc;
+    const D newinf = foi * y[0];
+    D net = make_dual<P>(0.0) - newinf;
+    D wan;
+    if constexpr (WANING) {
+      wan = c.omega * y[IR];
+      net = wan - newinf;
+    }
+    dy[0] = sum_strains(net, c);  // ds_g = -sum_s newinf + sum_s omega_s r
+    const D rec = c.gamma * y[II];
+    if constexpr (HAS_E) {
+      const D prog = c.sigma * y[IE];
+      dy[IE] = newinf - prog;
+      dy[II] = prog - rec;
+    } else {
+      dy[II] = newinf - rec;
+    }
+    if constexpr (WANING) dy[IR] = rec - wan; else dy[IR] = rec;
+    if constexpr (HAS_C) dy[IC] = newinf;
+  }
+
+  static DYN_DI double sq(double x) { return x * x; }
+
+  // ---- the kernel body ------------------------------------------------------------------
+  static __device__ void run(const SolveArgs& a) {
+    using namespace tsit5;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tw = lane / L;
+    const int q = lane - tw * L;
+    Ctx c;
+    c.g = q / S;
+    c.s = q - c.g * S;
+    c.base = tw * L;
+    c.sbase = c.base + c.g * S;
+    const int64_t traj = warp_global * TPW + tw;
+    const bool valid = (tw < TPW) && (traj < a.B);
+    const int64_t tr = valid ? traj : 0;  // invalid lanes shadow trajectory 0, never write
+    const bool lead = (c.s == 0);         // owner of the replicated S_g for norms and stores
+
+    // ---- parameters -> registers (coalesced: a warp reads a contiguous run of draws)
+    auto ld = [&](const DynodeArray& arr, int k, double dflt) -> double {
+      return arr.ptr ? __ldg(arr.ptr + tr * arr.batch_stride + k) : dflt;
+    };
+    c.beta = make_dual<P>(ld(a.prm.beta, c.s, 0.0));
+    c.gamma = make_dual<P>(ld(a.prm.gamma, c.s, 0.0));
+    c.sigma = make_dual<P>(HAS_E ? ld(a.prm.sigma, c.s, 0.0) : 0.0);
+    c.omega = make_dual<P>(WANING ? ld(a.prm.omega, c.s, 0.0) : 0.0);
+    c.amp = make_dual<P>(SEASONAL ? ld(a.prm.season_amp, 0, 0.0) : 0.0);
+    c.phase = make_dual<P>(SEASONAL ? ld(a.prm.season_phase, 0, 0.0) : 0.0);
+    c.period = SEASONAL ? ld(a.prm.season_period, 0, 1.0) : 1.0;
+#pragma unroll
+    for (int b = 0; b < G; ++b)
+      c.K[b] = a.prm.contact ? __ldg(a.prm.contact + c.g * G + b) : (b == c.g ? 1.0 : 0.0);
+    if constexpr (P > 0) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int w = a.wrt[p];
+        if (w >= 0 && (w & 15) == c.s) {
+          const int kind = w >> 4;
+          if (kind == DYNODE_P_BETA) c.beta.d[p] = 1.0;
+          if (kind == DYNODE_P_GAMMA) c.gamma.d[p] = 1.0;
+          if (kind == DYNODE_P_SIGMA) c.sigma.d[p] = 1.0;
+          if (kind == DYNODE_P_OMEGA) c.omega.d[p] = 1.0;
+        }
+        if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_AMP) c.amp.d[p] = 1.0;
+        if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_PHASE) c.phase.d[p] = 1.0;
+      }
+    }
+
+    // ---- element offsets inside a full state row and inside a saved row
+    int off_full[NE], off_save[NE];
+    off_full[0] = c.g;
+#pragma unroll
+    for (int e = 1; e < NE; ++e) off_full[e] = G + (e - 1) * G * S + c.g * S + c.s;
+    int n_saved = 0;
+    {
+      int run_off = 0;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int sz = (e == 0) ? G : G * S;
+        const bool on = (a.save_mask >> e) & 1u;
+        off_save[e] = on ? run_off + (e == 0 ? c.g : c.g * S + c.s) : -1;
+        if (on) run_off += sz;
+      }
+      n_saved = run_off;
+    }
+    if (!lead) off_save[0] = -1;  // S_g is stored once, by the strain-0 lane
+
+    // ---- initial state
+    D y[NE], f[7][NE], ys[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      y[e] = make_dual<P>(__ldg(a.y0.ptr + tr * a.y0.batch_stride + off_full[e]));
+      if constexpr (P > 0) {
+        if (a.dy0) {
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            if (a.p0 + p < a.P_total)
+              y[e].d[p] = __ldg(a.dy0 + ((tr * a.P_total + a.p0 + p) * (int64_t)N) + off_full[e]);
+        }
+      }
+    }
+
+    const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
+    const double inv_n = 1.0 / (double)N;
+    double tprev = a.t0, tnext;
+    rhs(a.t0, y, f[0], c);  // FSAL f0 (solver.init)
+
+    if (a.const_dt > 0.0) {
+      tnext = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
+    } else {
+      // Hairer-Wanner initial step (PIDController._select_initial_step)
+      double p0 = 0.0, p1 = 0.0;
+      double scale[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        scale[e] = fma(fabs(y[e].v), rtol, atol);
+        const double w = (e == 0 && !lead) ? 0.0 : 1.0;
+        p0 += w * sq(y[e].v / scale[e]);
+        p1 += w * sq(f[0][e].v / scale[e]);
+      }
+      const double d0 = sqrt(traj_sum(p0, c) * inv_n);
+      const double d1 = sqrt(traj_sum(p1, c) * inv_n);
+      const bool small = (d0 < 1e-5) || (d1 < 1e-5);
+      const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, f[0][e], y[e]);
+      rhs(a.t0 + h0, ys, f[1], c);
+      double p2 = 0.0;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const double w = (e == 0 && !lead) ? 0.0 : 1.0;
+        p2 += w * sq((f[1][e].v - f[0][e].v) / scale[e]);
+      }
+      const double d2 = sqrt(traj_sum(p2, c) * inv_n) / h0;
+      const double md = fmax(d1, d2);
+      const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
+      tnext = a.t0 + fmin(100.0 * h0, h1);
+    }
+    tnext = fmin(tnext, t1);
+
+    int32_t n_acc = 0, n_rej = 0, n_steps = 0;
+    int32_t save_i = 0;
+    bool active = valid && (tprev < t1) && (n_steps < a.max_steps);
+
+    // fused log-likelihood state
+    D lp_acc = make_dual<P>(0.0), obs_prev = make_dual<P>(0.0);
+    const int obs_m = (a.obs_comp == 0) ? G : G * S;
+    const int obs_q = (a.obs_comp == 0) ? c.g : c.g * S + c.s;
+    const bool obs_owner = (a.obs_comp != 0) || lead;
+
+    while (__any_sync(0xffffffffu, active)) {
+      const double h = tnext - tprev;
+      // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, a21 * f[0][e], y[e]);
+      rhs(fma(c2, h, tprev), ys, f[1], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(a32, f[1][e], a31 * f[0][e]), y[e]);
+      rhs(fma(c3, h, tprev), ys, f[2], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        ys[e] = dfma(h, dfma(a43, f[2][e], dfma(a42, f[1][e], a41 * f[0][e])), y[e]);
+      rhs(fma(c4, h, tprev), ys, f[3], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        ys[e] = dfma(h, dfma(a54, f[3][e], dfma(a53, f[2][e], dfma(a52, f[1][e], a51 * f[0][e]))), y[e]);
+      rhs(fma(c5, h, tprev), ys, f[4], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        ys[e] = dfma(h, dfma(a65, f[4][e], dfma(a64, f[3][e], dfma(a63, f[2][e],
+                     dfma(a62, f[1][e], a61 * f[0][e])))), y[e]);
+      rhs(tnext, ys, f[5], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        ys[e] = dfma(h, dfma(a76, f[5][e], dfma(a75, f[4][e], dfma(a74, f[3][e], dfma(a73, f[2][e],
+                     dfma(a72, f[1][e], a71 * f[0][e]))))), y[e]);
+      rhs(tnext, ys, f[6], c);  // ys is y1
+
+      // ---- embedded error, scaled RMS norm over the whole state (PIDController.adapt_step_size)
+      bool keep;
+      double dt_next;
+      if (a.const_dt > 0.0) {
+        keep = true;
+        dt_next = a.const_dt;
+      } else {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          double er = e7 * f[6][e].v;
+          er = fma(e6, f[5][e].v, er);
+          er = fma(e5, f[4][e].v, er);
+          er = fma(e4, f[3][e].v, er);
+          er = fma(e3, f[2][e].v, er);
+          er = fma(e2, f[1][e].v, er);
+          er = fma(e1, f[0][e].v, er);
+          er *= h;
+          if (er != er) er = CUDART_INF;  // NaN -> inf (diffeqsolve body)
+          const double y1v = (ys[e].v != ys[e].v) ? y[e].v : ys[e].v;
+          const double sc = fma(fmax(fabs(y[e].v), fabs(y1v)), rtol, atol);
+          const double w = (e == 0 && !lead) ? 0.0 : 1.0;
+          part += w * sq(er / sc);
+        }
+        const double err = sqrt(traj_sum(part, c) * inv_n);
+        keep = err < 1.0;
+        dt_next = h * controller_factor(err, keep);
+      }
+      double ntprev = keep ? tnext : tprev;
+      double ntnext = ntprev + dt_next;
+      ntprev = fmin(ntprev, t1);
+      if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);  // _clip_to_end
+
+      // ---- SaveAt(ts): dense output over [tprev, tnext] for every ts[k] <= tnext
+      const bool do_save = active && keep;
+      const double inv_h = 1.0 / ((tnext == tprev) ? 1.0 : h);
+      while (true) {
+        bool pend = do_save && (save_i < a.T);
+        double tsv = 0.0;
+        if (pend) {
+          tsv = __ldg(a.save_ts + save_i);
+          pend = tsv <= tnext;
+        }
+        if (!__any_sync(0xffffffffu, pend)) break;
+        if (pend) {
+          double b[7];
+          dense_weights((tsv - tprev) * inv_h, b);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) b[j] *= h;
+          if constexpr (MODE == MODE_SAVE) {
+            const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              if (off_save[e] >= 0) {
+                D v = dfma(b[0], f[0][e], y[e]);
+#pragma unroll
+                for (int j = 1; j < 7; ++j) v = dfma(b[j], f[j][e], v);
+                if (a.write_primal) a.ys[row + off_save[e]] = v.v;
+                if constexpr (P > 0) {
+#pragma unroll
+                  for (int p = 0; p < P; ++p)
+                    if (a.p0 + p < a.P_total)
+                      a.dys[(row + off_save[e]) * a.P_total + a.p0 + p] = v.d[p];
+                }
+              }
+            }
+          } else {
+            // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
+            // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
+            D v = make_dual<P>(0.0);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              if (e == a.obs_comp) {
+                v = dfma(b[0], f[0][e], y[e]);
+#pragma unroll
+                for (int j = 1; j < 7; ++j) v = dfma(b[j], f[j][e], v);
+              }
+            }
+            if (save_i > 0 && obs_owner) {
+              D inc = v - obs_prev;
+              const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
+              if (inc.v > 1e-6) {
+                const D lg = dual_log(inc);
+                lp_acc = lp_acc + (o * lg - inc);
+              } else {
+                lp_acc.v += o * log(1e-6) - 1e-6;  // clamped: zero gradient (jnp.maximum)
+              }
+            }
+            obs_prev = v;
+          }
+          ++save_i;
+        }
+      }
+
+      // ---- commit
+      if (active) {
+        ++n_steps;
+        if (keep) {
+          ++n_acc;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) { y[e] = ys[e]; f[0][e] = f[6][e]; }
+        } else {
+          ++n_rej;
+        }
+        tprev = ntprev;
+        tnext = ntnext;
+        active = (tprev < t1) && (n_steps < a.max_steps);
+      }
+    }
+
+    // ---- epilogue
+    if constexpr (MODE == MODE_SAVE) {
+      if (valid && a.write_primal) {
+        // slots never reached keep diffrax's +inf fill
+        for (int k = save_i; k < a.T; ++k) {
+          const int64_t row = (traj * a.T + k) * (int64_t)n_saved;
+#pragma unroll
+          for (int e = 0; e < NE; ++e)
+            if (off_save[e] >= 0) a.ys[row + off_save[e]] = CUDART_INF;
+        }
+      }
+    } else {
+      if (!obs_owner) lp_acc = make_dual<P>(0.0);
+      const double tot = traj_sum(lp_acc.v, c);
+      if (valid && q == 0 && a.write_primal) a.lp[traj] = tot + a.lp_const;
+      if constexpr (P > 0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const double gp = traj_sum(lp_acc.d[p], c);
+          if (valid && q == 0 && a.p0 + p < a.P_total) a.grad[traj * a.P_total + a.p0 + p] = gp;
+        }
+      }
+    }
+    if (valid && q == 0 && a.write_primal) {
+      int32_t* st = a.stats + traj * 4;
+      st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
+      st[DYNODE_STAT_ACCEPTED] = n_acc;
+      st[DYNODE_STAT_REJECTED] = n_rej;
+      st[DYNODE_STAT_STEPS] = n_steps;
+    }
+  }
+};
+
+template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
+__global__ void __launch_bounds__(kThreads) lane_solver_kernel(const SolveArgs a) {
+  LaneSolver<FLOW, FLAGS, G, S, P, MODE>::run(a);
+}
+
+// Host launcher: one warp integrates 32/(G*S) trajectories; the grid covers the ensemble.
+template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
+cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream) {
+  constexpr int TPW = LaneSolver<FLOW, FLAGS, G, S, P, MODE>::TPW;
+  constexpr int per_cta = TPW * (kThreads / 32);
+  const int64_t grid = (a.B + per_cta - 1) / per_cta;
+  if (grid <= 0) return cudaSuccess;
+  lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace dynode

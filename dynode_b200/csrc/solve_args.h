@@ -1,0 +1,47 @@
+// solve_args.h -- launch arguments shared by the kernels (lane_solver.cuh) and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dynode_b200.h"
+
+namespace dynode {
+
+constexpr int kPMax = 2;            // max tangent directions carried per pass (more -> several passes)
+// Directions per pass chosen so that (1+P) * 8 * NE doubles stay in registers without spilling:
+// SIR lanes hold 3 elements (P=2 -> 72 doubles), SEIRS/SEIRS_C lanes 4-5 elements (P=1 -> 80).
+constexpr int tangent_chunk(int flow) { return flow == DYNODE_FLOW_SIR ? 2 : 1; }
+constexpr int kThreads = 128;       // 4 warps per CTA
+constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
+constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
+
+struct SolveArgs {
+  int64_t B;
+  DynodeArray y0;
+  DynodeParams prm;
+  const double* save_ts;
+  int32_t T;
+  uint32_t save_mask;
+  double t0, t1, rtol, atol, const_dt;
+  int32_t max_steps;
+  double* ys;      // [B][T][n_saved]   (written when write_primal)
+  int32_t* stats;  // [B][4]            (written when write_primal)
+  int32_t write_primal;
+  // sensitivities: this pass carries directions p0 .. p0+P-1 of P_total
+  int32_t P_total, p0;
+  int32_t wrt[kPMax];
+  const double* dy0;  // [B][P_total][n]
+  double* dys;        // [B][T][n_saved][P_total]
+  // fused log-likelihood
+  int32_t obs_comp;
+  const double* obs;  // [T-1][m]
+  double lp_const;
+  double* lp;    // [B]
+  double* grad;  // [B][P_total]
+};
+
+// Defined in lane_solver.cuh, explicitly instantiated per model in inst.cu (see instances.def).
+template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
+cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream);
+
+}  // namespace dynode

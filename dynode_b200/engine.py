@@ -1,0 +1,184 @@
+"""Low-level ensemble engine: torch CUDA tensors in, one native launch, torch CUDA tensors out.
+
+This is the device-resident layer under `dynode_b200.simulation.simulate`: it only validates
+shapes, allocates outputs and forwards raw device pointers to the C ABI
+(include/dynode_b200.h).  All arithmetic happens in the sm_100a kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+from . import _lib
+from ._lib import DynodeError
+
+_PARAM_FIELDS = ("beta", "gamma", "sigma", "omega", "season_amp", "season_phase", "season_period")
+
+
+@dataclass(frozen=True)
+class FlowModel:
+    """A member of the compiled flow family (csrc/instances.def)."""
+
+    flow: int
+    flags: int
+    n_groups: int
+    n_strains: int
+
+    def desc(self) -> _lib.ModelDesc:
+        return _lib.ModelDesc(self.flow, self.flags, self.n_groups, self.n_strains)
+
+    @property
+    def n_compartments(self) -> int:
+        return {0: 3, 1: 4, 2: 5}[self.flow]
+
+    @property
+    def state_size(self) -> int:
+        return self.n_groups + (self.n_compartments - 1) * self.n_groups * self.n_strains
+
+    def compartment_sizes(self) -> Tuple[int, ...]:
+        gs = self.n_groups * self.n_strains
+        return (self.n_groups,) + (gs,) * (self.n_compartments - 1)
+
+    def saved_size(self, mask: int) -> int:
+        return sum(sz for c, sz in enumerate(self.compartment_sizes()) if (mask >> c) & 1)
+
+    def full_mask(self) -> int:
+        return (1 << self.n_compartments) - 1
+
+    def check_supported(self) -> None:
+        d = self.desc()
+        if not _lib.load().dynode_is_supported(ctypes.byref(d)):
+            raise DynodeError("unsupported ODE: " + _lib.last_error())
+
+
+@dataclass
+class SolverOptions:
+    """diffeqsolve arguments fixed by reference odes.py:107-144 / config/params.py:24-67."""
+
+    t1: float
+    t0: float = 0.0
+    rtol: float = 1e-5
+    atol: float = 1e-6
+    const_dt: float = 0.0
+    max_steps: int = 10**6
+
+    def desc(self) -> _lib.SolverDesc:
+        return _lib.SolverDesc(float(self.t0), float(self.t1), float(self.rtol), float(self.atol),
+                               float(self.const_dt), int(self.max_steps))
+
+
+def _dev_f64(torch, x, device):
+    t = torch.as_tensor(x, dtype=torch.float64, device=device)
+    return t.contiguous()
+
+
+def _as_array(t, row: int, B: int, name: str) -> _lib.Array:
+    """(B,row) / (row,) / scalar tensor -> DynodeArray (shared rows get batch_stride 0)."""
+    if t is None:
+        return _lib.Array(None, 0)
+    if t.numel() == row:
+        return _lib.Array(t.data_ptr(), 0)
+    if t.numel() == B * row:
+        return _lib.Array(t.data_ptr(), row)
+    raise ValueError(f"{name}: expected {row} or {B}x{row} values, got shape {tuple(t.shape)}")
+
+
+class _Bound:
+    """Validated device-side view of one ensemble call (keeps tensors alive across the launch)."""
+
+    def __init__(self, model: FlowModel, y0, params: Dict[str, object], contact, save_ts, B=None):
+        torch = _lib.require_cuda()
+        model.check_supported()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.torch, self.dev, self.model = torch, dev, model
+        n, S, G = model.state_size, model.n_strains, model.n_groups
+        self.y0 = _dev_f64(torch, y0, dev)
+        if self.y0.shape[-1] != n and self.y0.numel() % n != 0:
+            raise ValueError(f"y0 must have {n} values per trajectory, got {tuple(self.y0.shape)}")
+        self.p = {k: (_dev_f64(torch, params[k], dev) if params.get(k) is not None else None)
+                  for k in _PARAM_FIELDS}
+        # ensemble size = the largest leading dimension among batched inputs
+        if B is None:
+            B = max(1, self.y0.numel() // n)
+            for k, t in self.p.items():
+                if t is None:
+                    continue
+                row = S if k in ("beta", "gamma", "sigma", "omega") else 1
+                B = max(B, t.numel() // row)
+        self.B = int(B)
+        self.contact = None
+        if contact is not None:
+            self.contact = _dev_f64(torch, contact, dev)
+            if self.contact.numel() != G * G:
+                raise ValueError(f"contact must be {G}x{G}, got {tuple(self.contact.shape)}")
+        self.save_ts = _dev_f64(torch, save_ts, dev)
+        self.T = int(self.save_ts.numel())
+        self.c_params = _lib.Params()
+        for k in _PARAM_FIELDS:
+            row = S if k in ("beta", "gamma", "sigma", "omega") else 1
+            setattr(self.c_params, k, _as_array(self.p[k], row, self.B, k))
+        self.c_params.contact = self.contact.data_ptr() if self.contact is not None else None
+        self.c_y0 = _as_array(self.y0, n, self.B, "y0")
+
+
+def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions,
+                   save_ts, save_mask: Optional[int] = None, wrt: Sequence[int] = (), dy0=None,
+                   out=None, stats_out=None, B: Optional[int] = None):
+    """One launch for the whole ensemble.  Returns (ys[B,T,n_saved], dys or None, stats[B,4]).
+
+    Everything stays on the current CUDA device and stream; nothing synchronises.
+    """
+    b = _Bound(model, y0, params, contact, save_ts, B)
+    torch = b.torch
+    mask = model.full_mask() if save_mask is None else int(save_mask)
+    ns = model.saved_size(mask)
+    ys = out if out is not None else torch.empty((b.B, b.T, ns), dtype=torch.float64, device=b.dev)
+    stats = stats_out if stats_out is not None else torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
+    L = _lib.load()
+    md, sd = model.desc(), opts.desc()
+    stream = ctypes.c_void_p(_lib.current_stream_ptr())
+    P = len(wrt)
+    if P == 0:
+        _lib.check(L.dynode_solve_f64(ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0,
+                                      ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T, mask,
+                                      ys.data_ptr(), stats.data_ptr(), stream))
+        return ys, None, stats
+    dys = torch.empty((b.B, b.T, ns, P), dtype=torch.float64, device=b.dev)
+    d0 = None
+    if dy0 is not None:
+        d0 = _dev_f64(torch, dy0, b.dev)
+        if d0.numel() != b.B * P * model.state_size:
+            raise ValueError("dy0 must be [B][n_wrt][n]")
+    _lib.check(L.dynode_solve_sens_f64(ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0,
+                                       ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T, mask, P,
+                                       _lib.i32_array(list(wrt)), d0.data_ptr() if d0 is not None else None,
+                                       ys.data_ptr(), dys.data_ptr(), stats.data_ptr(), stream))
+    return ys, dys, stats
+
+
+def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions,
+                        save_ts, obs_comp: int, obs, lp_const: float = 0.0, wrt: Sequence[int] = (),
+                        dy0=None, B: Optional[int] = None):
+    """Fused solve + Poisson-incidence log-likelihood + gradient: returns (lp[B], grad[B,P], stats)."""
+    b = _Bound(model, y0, params, contact, save_ts, B)
+    torch = b.torch
+    m = model.compartment_sizes()[obs_comp]
+    obs_t = _dev_f64(torch, obs, b.dev)
+    if obs_t.numel() != (b.T - 1) * m:
+        raise ValueError(f"obs must be [{b.T - 1}][{m}], got {tuple(obs_t.shape)}")
+    P = len(wrt)
+    lp = torch.empty((b.B,), dtype=torch.float64, device=b.dev)
+    grad = torch.empty((b.B, max(P, 1)), dtype=torch.float64, device=b.dev)
+    stats = torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
+    d0 = None
+    if dy0 is not None:
+        d0 = _dev_f64(torch, dy0, b.dev)
+    md, sd = model.desc(), opts.desc()
+    _lib.check(_lib.load().dynode_poisson_loglik_grad_f64(
+        ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(),
+        b.T, int(obs_comp), obs_t.data_ptr(), float(lp_const), P, _lib.i32_array(list(wrt)),
+        d0.data_ptr() if d0 is not None else None, lp.data_ptr(), grad.data_ptr(), stats.data_ptr(),
+        ctypes.c_void_p(_lib.current_stream_ptr())))
+    return lp, (grad[:, :P] if P else None), stats
