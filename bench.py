@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ensemble ODE engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3]
+
+A "step" is one pass of the hot path over one batch of synthetic draws: the whole ensemble solved
+from t=0 to 365 d with Tsit5 + PID controller and written out daily (diffeqsolve + SaveAt).
+Workload at N=1 = BASELINE.json configs[3]: multi-strain age-stratified SEIRS, 100k draws per GPU
+(weak scaling: every rank solves its own 100k draws, no data-path collective).
+
+  value      trajectories/s, inputs resident in HBM, device-timed with CUDA events (max over ranks)
+  e2e        same metric through the public API (simulate_ensemble) with HOST buffers:
+             H2D of the draws and D2H of every saved trajectory inside the timed region
+  roofline   dominant kernel (lane_solver_kernel): algorithmic bytes / measured duration vs the
+             measured HBM peak; the FP64-FMA view of the same kernel is in roofline_fp64
+  cpu_baseline   the CPU oracle (restatement of the reference's diffrax path, OpenMP) on a bounded
+             sample of the same workload, timed on this box's host cores
+
+--impl reference times that CPU oracle as the reference arm (the reference's own JAX/diffrax stack
+cannot be installed in this image: no jax/diffrax wheels, no network -- see DESIGN.md).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (case name in tests/cases.py, draws per GPU, description)
+    "c4": ("seirs_multi_a2s3", 100_000,
+           "C4 multi-strain age-stratified SEIRS+C (A=2,S=3,n=26), 365 d, daily SaveAt T=366"),
+    "c3": ("seirs_seasonal", 1_000_000, "C3 seasonally forced SEIRS (n=4), 365 d, daily SaveAt T=366"),
+}
+F_RHS = {"seirs_multi_a2s3": 130, "seirs_seasonal": 18}  # flops per RHS evaluation
+
+
+def algorithmic_work(n, p_in, T, n_saved, f_rhs, n_att_total, B):
+    """flops = (6*N_att+3)*F_rhs + N_att*(70n+50) + T*(14*n_s+45);
+    bytes = 8*(n+P_in) + 8*T*n_s + 16 per trajectory."""
+    flops = (6 * n_att_total + 3 * B) * f_rhs + n_att_total * (70 * n + 50) + B * T * (14 * n_saved + 45)
+    byts = B * (8 * (n + p_in) + 8 * T * n_saved + 16)
+    return flops, byts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc, self.thr = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.thr = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(workload: str, B: int, seed: int):
+    from tests.cases import make_case
+    return make_case(WORKLOADS[workload][0], B, seed=seed)
+
+
+def cpu_oracle_leg(workload: str, sample_chunks: int, chunk: int, seed: int):
+    """Time the CPU oracle (all host threads) on sample_chunks x chunk draws of the workload."""
+    from oracle import oracle as orc
+    case = make_inputs(workload, chunk, seed)
+    fam, dims, theta, shared = case["oracle"]
+    orc.solve(fam, dims, case["y0"][:256] if np.ndim(case["y0"]) == 2 else case["y0"], theta[:256], shared,
+              t1=case["t1"])  # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    for _ in range(sample_chunks):
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+    dt = time.perf_counter() - t0
+    return sample_chunks * chunk / dt, orc.num_threads(), dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path = the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, B, desc = WORKLOADS[args.workload]
+    chunk = 8192
+    from oracle import oracle as orc
+    case = make_inputs(args.workload, chunk, 20260101)
+    fam, dims, theta, shared = case["oracle"]
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+    dt = time.perf_counter() - t0
+    v = args.steps * chunk / dt
+    cores = orc.num_threads()
+    sample = f"{chunk} draws of the same workload per step, {args.steps} steps, OpenMP over {cores} threads"
+    line = {
+        "impl": "reference", "metric": "solved trajectories/s", "value": v, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "draws_per_step": chunk, "rtol": 1e-5, "atol": 1e-6, "solver": "Tsit5"},
+        "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference JAX/diffrax stack not installable here; CPU oracle (C++ restatement, OpenMP) timed instead",
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dynode_b200 import _lib, engine
+    from dynode_b200.config import SolverParams
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate_ensemble
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name, B, desc = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    case = make_inputs(args.workload, B, 20260101 + rank)
+    model = case["model"]
+    t1 = case["t1"]
+    opts = engine.SolverOptions(t1=t1)
+    save_ts_h = np.linspace(0.0, t1, int(t1 // 1) + 1)
+    T, n = len(save_ts_h), model.state_size
+    ns = n
+    # ---- device-resident inputs
+    params_d = {k: torch.as_tensor(v, dtype=torch.float64, device=dev) for k, v in case["params"].items()}
+    y0_d = torch.as_tensor(case["y0"], dtype=torch.float64, device=dev)
+    contact_d = None if case["contact"] is None else torch.as_tensor(case["contact"], dtype=torch.float64, device=dev)
+    ts_d = torch.as_tensor(save_ts_h, device=dev)
+    ys = torch.empty((B, T, ns), dtype=torch.float64, device=dev)
+    stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
+
+    def step():
+        engine.solve_ensemble(model, y0_d, params_d, contact_d, opts, ts_d, out=ys, stats_out=stats, B=B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- roofline probes (measured FP64 FMA and HBM write peaks on this GPU)
+    L = _lib.load()
+    import ctypes
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.dynode_probe_dfma(sink.data_ptr(), 2000, stream)
+    torch.cuda.synchronize()
+    e0.record(); flops = L.dynode_probe_dfma(sink.data_ptr(), 40000, stream); e1.record()
+    torch.cuda.synchronize()
+    fp64_peak_tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    nw = ys.numel()
+    L.dynode_probe_hbm_write(ys.data_ptr(), nw, stream)
+    torch.cuda.synchronize()
+    e0.record(); L.dynode_probe_hbm_write(ys.data_ptr(), nw, stream); e1.record()
+    torch.cuda.synchronize()
+    hbm_write_gbs = nw * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    # ---- warm-up, then K timed steps
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        a.record(); step(); b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    per_step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    st = stats.cpu().numpy()
+    assert (st[:, 0] == 0).all(), "some trajectories hit max_steps"
+    n_att = int(st[:, 3].sum())
+    p_in = sum(int(np.size(v)) // B for v in case["params"].values() if np.size(v) >= B)
+    flops_alg, bytes_alg = algorithmic_work(n, p_in, T, ns, F_RHS[name], n_att, B)
+    kern_ms = statistics.mean(per_step_ms)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    ach_gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
+    ach_tf = flops_alg / (kern_ms * 1e-3) / 1e12
+
+    # ---- end-to-end through the public API with HOST buffers (pinned): H2D + solve + D2H
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).pin_memory()
+        hp = {k: pin(v) for k, v in case["params"].items()}
+        G, S = model.n_groups, model.n_strains
+        y0h = pin(np.broadcast_to(case["y0"], (B, n)))
+        if name == "seirs_multi_a2s3":
+            ode = ex.seirs_multi_strain_ode
+            p = ex.SEIRS_MultiStrain_ODEParams(beta=hp["beta"], gamma=hp["gamma"], sigma=hp["sigma"], omega=hp["omega"],
+                                               contact_matrix=torch.as_tensor(case["contact"]))
+            sizes = [G, G * S, G * S, G * S, G * S]
+            shp = [(B, G)] + [(B, G, S)] * 4
+        else:
+            ode = ex.seirs_ode_seasonal
+            p = ex.SeasonalSEIRS_ODEParams(beta=hp["beta"], gamma=hp["gamma"], sigma=hp["sigma"], omega=hp["omega"],
+                                           seasonality_params=ex.SeasonalityParams(
+                                               forcing_amp=hp["season_amp"], forcing_phase=hp["season_phase"],
+                                               forcing_period=hp["season_period"]))
+            sizes = [1, 1, 1, 1]
+            shp = [(B, 1)] * 4
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        state = tuple(y0h[:, offs[i]:offs[i + 1]].reshape(shp[i]) for i in range(len(sizes)))
+        out_h = torch.empty((B, T, ns), dtype=torch.float64).pin_memory()
+        sp = SolverParams()
+        k_e2e = max(1, min(args.steps, args.e2e_steps))
+
+        def e2e_step():
+            return simulate_ensemble(ode, t1, state, p, sp, batch_size=B, state_batched=True, out=out_h,
+                                     host_chunk=args.host_chunk)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            sol = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # the result the user reads: check it equals the device-resident run
+        chk = float((sol.ys[4 if name == "seirs_multi_a2s3" else 3][:64].to(dev).reshape(64, T, -1)
+                     - ys[:64, :, -(sizes[-1]):]).abs().max())
+        h2d = int(sum(v.numel() for v in hp.values()) * 8 + y0h.numel() * 8)
+        d2h = int(out_h.numel() * 8 + B * 16)
+        e2e = {"value": world * B * k_e2e / dt, "unit": "trajectories/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
+               "api": "dynode_b200.simulation.simulate_ensemble (pinned host in/out, chunked H2D/solve/D2H overlap)",
+               "max_abs_diff_vs_device_run": chk}
+
+    # ---- CPU baseline on rank 0, N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        chunks = args.cpu_chunks
+        v, cores, dt = cpu_oracle_leg(args.workload, chunks, 8192, 20260101)
+        cpu = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
+               "sample": f"{chunks}x8192 draws of the same workload ({dt:.1f} s wall), C++ oracle + OpenMP"}
+
+    if rank == 0:
+        line = {
+            "metric": "solved trajectories/s", "value": value, "unit": "trajectories/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "draws_per_gpu": B, "rtol": 1e-5, "atol": 1e-6, "solver": "Tsit5+PID",
+                       "mean_accepted": float(st[:, 1].mean()), "mean_rejected": float(st[:, 2].mean()),
+                       "l2": f"each step streams {bytes_alg / 1e9:.2f} GB of output through the 126 MB L2, "
+                             "evicting the inputs between steps (inputs+outputs >> L2)"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "dynode::lane_solver_kernel", "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": bytes_alg, "hbm_write_probe_gbs": hbm_write_gbs},
+            "roofline_fp64": {"bound": "fp64_fma", "achieved": ach_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+                              "frac": ach_tf / fp64_peak_tf, "peak_source": "dynode_probe_dfma measured in this run",
+                              "algorithmic_flops_per_launch": flops_alg, "attempted_steps_total": n_att},
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override draws per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--host-chunk", type=int, default=8192)
+    ap.add_argument("--cpu-chunks", type=int, default=12)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

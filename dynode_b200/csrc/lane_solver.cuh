@@ -96,7 +96,7 @@ struct LaneSolver {
       D part = y[II] + y[IR];
       if constexpr (HAS_E) part = part + y[IE];
       const D Ng = y[0] + sum_strains(part, c);  // N_g = s_g + sum_s (e+i+r)[g,s]   (c excluded)
-      prop = y[II] / Ng;
+      prop = ddiv_fast(y[II], Ng);
     }
     // contact contraction: sum_b K[g][b] * prop[b, s]
     D acc;
@@ -125,22 +125,20 @@ struct LaneSolver {
     }
     const D foi = beta_t * acc;
     const D newinf = foi * y[0];
-    D net = make_dual<P>(0.0) - newinf;
-    D wan;
-    if constexpr (WANING) {
-      wan = c.omega * y[IR];
-      net = wan - newinf;
-    }
-    dy[0] = sum_strains(net, c);  // ds_g = -sum_s newinf + sum_s omega_s r
     const D rec = c.gamma * y[II];
+    if constexpr (WANING) {
+      dy[0] = sum_strains(dmsub(c.omega, y[IR], newinf), c);  // ds_g = sum_s (omega_s r - newinf)
+      dy[IR] = dnmadd(c.omega, y[IR], rec);                   // gamma i - omega r
+    } else {
+      dy[0] = sum_strains(dneg(newinf), c);
+      dy[IR] = rec;
+    }
     if constexpr (HAS_E) {
-      const D prog = c.sigma * y[IE];
-      dy[IE] = newinf - prog;
-      dy[II] = prog - rec;
+      dy[IE] = dnmadd(c.sigma, y[IE], newinf);  // newinf - sigma e
+      dy[II] = dmsub(c.sigma, y[IE], rec);      // sigma e - gamma i
     } else {
       dy[II] = newinf - rec;
     }
-    if constexpr (WANING) dy[IR] = rec - wan; else dy[IR] = rec;
     if constexpr (HAS_C) dy[IC] = newinf;
   }
 
@@ -211,6 +209,7 @@ struct LaneSolver {
       n_saved = run_off;
     }
     if (!lead) off_save[0] = -1;  // S_g is stored once, by the strain-0 lane
+    double* out_row = a.ys + traj * (int64_t)a.T * n_saved;  // advanced by n_saved per saved time
 
     // ---- initial state
     D y[NE], f[7][NE], ys[NE];
@@ -279,31 +278,33 @@ struct LaneSolver {
       const double h = tnext - tprev;
       // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
 #pragma unroll
-      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, a21 * f[0][e], y[e]);
-      rhs(fma(c2, h, tprev), ys, f[1], c);
+      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, T5_a21 * f[0][e], y[e]);
+      rhs(fma(T5_c2, h, tprev), ys, f[1], c);
 #pragma unroll
-      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(a32, f[1][e], a31 * f[0][e]), y[e]);
-      rhs(fma(c3, h, tprev), ys, f[2], c);
-#pragma unroll
-      for (int e = 0; e < NE; ++e)
-        ys[e] = dfma(h, dfma(a43, f[2][e], dfma(a42, f[1][e], a41 * f[0][e])), y[e]);
-      rhs(fma(c4, h, tprev), ys, f[3], c);
+      for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(T5_a32, f[1][e], T5_a31 * f[0][e]), y[e]);
+      rhs(fma(T5_c3, h, tprev), ys, f[2], c);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
-        ys[e] = dfma(h, dfma(a54, f[3][e], dfma(a53, f[2][e], dfma(a52, f[1][e], a51 * f[0][e]))), y[e]);
-      rhs(fma(c5, h, tprev), ys, f[4], c);
+        ys[e] = dfma(h, dfma(T5_a43, f[2][e], dfma(T5_a42, f[1][e], T5_a41 * f[0][e])), y[e]);
+      rhs(fma(T5_c4, h, tprev), ys, f[3], c);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
-        ys[e] = dfma(h, dfma(a65, f[4][e], dfma(a64, f[3][e], dfma(a63, f[2][e],
-                     dfma(a62, f[1][e], a61 * f[0][e])))), y[e]);
+        ys[e] = dfma(h, dfma(T5_a54, f[3][e], dfma(T5_a53, f[2][e], dfma(T5_a52, f[1][e], T5_a51 * f[0][e]))), y[e]);
+      rhs(fma(T5_c5, h, tprev), ys, f[4], c);
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        ys[e] = dfma(h, dfma(T5_a65, f[4][e], dfma(T5_a64, f[3][e], dfma(T5_a63, f[2][e],
+                     dfma(T5_a62, f[1][e], T5_a61 * f[0][e])))), y[e]);
       rhs(tnext, ys, f[5], c);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
-        ys[e] = dfma(h, dfma(a76, f[5][e], dfma(a75, f[4][e], dfma(a74, f[3][e], dfma(a73, f[2][e],
-                     dfma(a72, f[1][e], a71 * f[0][e]))))), y[e]);
+        ys[e] = dfma(h, dfma(T5_a76, f[5][e], dfma(T5_a75, f[4][e], dfma(T5_a74, f[3][e], dfma(T5_a73, f[2][e],
+                     dfma(T5_a72, f[1][e], T5_a71 * f[0][e]))))), y[e]);
       rhs(tnext, ys, f[6], c);  // ys is y1
 
-      // ---- embedded error, scaled RMS norm over the whole state (PIDController.adapt_step_size)
+      // ---- embedded error, scaled RMS norm over the whole state (PIDController.adapt_step_size).
+      // A NaN error estimate propagates to err and is rejected with factor 0.2, which is what
+      // diffrax's NaN->inf substitution yields.
       bool keep;
       double dt_next;
       if (a.const_dt > 0.0) {
@@ -313,19 +314,17 @@ struct LaneSolver {
         double part = 0.0;
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-          double er = e7 * f[6][e].v;
-          er = fma(e6, f[5][e].v, er);
-          er = fma(e5, f[4][e].v, er);
-          er = fma(e4, f[3][e].v, er);
-          er = fma(e3, f[2][e].v, er);
-          er = fma(e2, f[1][e].v, er);
-          er = fma(e1, f[0][e].v, er);
+          double er = T5_e7 * f[6][e].v;
+          er = fma(T5_e6, f[5][e].v, er);
+          er = fma(T5_e5, f[4][e].v, er);
+          er = fma(T5_e4, f[3][e].v, er);
+          er = fma(T5_e3, f[2][e].v, er);
+          er = fma(T5_e2, f[1][e].v, er);
+          er = fma(T5_e1, f[0][e].v, er);
           er *= h;
-          if (er != er) er = CUDART_INF;  // NaN -> inf (diffeqsolve body)
-          const double y1v = (ys[e].v != ys[e].v) ? y[e].v : ys[e].v;
-          const double sc = fma(fmax(fabs(y[e].v), fabs(y1v)), rtol, atol);
-          const double w = (e == 0 && !lead) ? 0.0 : 1.0;
-          part += w * sq(er / sc);
+          const double sc = fma(fmax(fabs(y[e].v), fabs(ys[e].v)), rtol, atol);
+          const double r = div_fast(er, sc);
+          if (e == 0) part = lead ? r * r : 0.0; else part = fma(r, r, part);
         }
         const double err = sqrt(traj_sum(part, c) * inv_n);
         keep = err < 1.0;
@@ -338,62 +337,74 @@ struct LaneSolver {
 
       // ---- SaveAt(ts): dense output over [tprev, tnext] for every ts[k] <= tnext
       const bool do_save = active && keep;
-      const double inv_h = 1.0 / ((tnext == tprev) ? 1.0 : h);
-      while (true) {
-        bool pend = do_save && (save_i < a.T);
-        double tsv = 0.0;
-        if (pend) {
-          tsv = __ldg(a.save_ts + save_i);
-          pend = tsv <= tnext;
+      double ts_next = (do_save && save_i < a.T) ? __ldg(a.save_ts + save_i) : CUDART_INF;
+      if (__any_sync(0xffffffffu, ts_next <= tnext)) {
+        // monomial form of the Tsit5 interpolant (tsit5.cuh kDense): Q_m = sum_i w_im f_i
+        D Q[4][NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          Q[0][e] = kDense[0][0] * f[0][e];
+#pragma unroll
+          for (int m = 1; m < 4; ++m) {
+            D acc = kDense[0][m] * f[0][e];
+#pragma unroll
+            for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m], f[i][e], acc);
+            Q[m][e] = acc;
+          }
         }
-        if (!__any_sync(0xffffffffu, pend)) break;
-        if (pend) {
-          double b[7];
-          dense_weights((tsv - tprev) * inv_h, b);
+        const double inv_h = rcp_fast((tnext == tprev) ? 1.0 : h);
+        while (true) {
+          const bool pend = ts_next <= tnext;
+          if (!__any_sync(0xffffffffu, pend)) break;
+          if (pend) {
+            const double th = (ts_next - tprev) * inv_h;
+            const double hth = h * th;
+            if constexpr (MODE == MODE_SAVE) {
 #pragma unroll
-          for (int j = 0; j < 7; ++j) b[j] *= h;
-          if constexpr (MODE == MODE_SAVE) {
-            const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
+              for (int e = 0; e < NE; ++e) {
+                if (off_save[e] >= 0) {
+                  D v = dfma(th, Q[3][e], Q[2][e]);
+                  v = dfma(th, v, Q[1][e]);
+                  v = dfma(th, v, Q[0][e]);
+                  v = dfma(hth, v, y[e]);
+                  if (a.write_primal) out_row[off_save[e]] = v.v;
+                  if constexpr (P > 0) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-              if (off_save[e] >= 0) {
-                D v = dfma(b[0], f[0][e], y[e]);
-#pragma unroll
-                for (int j = 1; j < 7; ++j) v = dfma(b[j], f[j][e], v);
-                if (a.write_primal) a.ys[row + off_save[e]] = v.v;
-                if constexpr (P > 0) {
-#pragma unroll
-                  for (int p = 0; p < P; ++p)
-                    if (a.p0 + p < a.P_total)
-                      a.dys[(row + off_save[e]) * a.P_total + a.p0 + p] = v.d[p];
+                    for (int p = 0; p < P; ++p)
+                      if (a.p0 + p < a.P_total)
+                        a.dys[((traj * a.T + save_i) * (int64_t)n_saved + off_save[e]) * a.P_total + a.p0 + p] = v.d[p];
+                  }
                 }
               }
-            }
-          } else {
-            // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
-            // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
-            D v = make_dual<P>(0.0);
+              out_row += n_saved;
+            } else {
+              // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
+              // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
+              D v = make_dual<P>(0.0);
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-              if (e == a.obs_comp) {
-                v = dfma(b[0], f[0][e], y[e]);
-#pragma unroll
-                for (int j = 1; j < 7; ++j) v = dfma(b[j], f[j][e], v);
+              for (int e = 0; e < NE; ++e) {
+                if (e == a.obs_comp) {
+                  D u = dfma(th, Q[3][e], Q[2][e]);
+                  u = dfma(th, u, Q[1][e]);
+                  u = dfma(th, u, Q[0][e]);
+                  v = dfma(hth, u, y[e]);
+                }
               }
-            }
-            if (save_i > 0 && obs_owner) {
-              D inc = v - obs_prev;
-              const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
-              if (inc.v > 1e-6) {
-                const D lg = dual_log(inc);
-                lp_acc = lp_acc + (o * lg - inc);
-              } else {
-                lp_acc.v += o * log(1e-6) - 1e-6;  // clamped: zero gradient (jnp.maximum)
+              if (save_i > 0 && obs_owner) {
+                D inc = v - obs_prev;
+                const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
+                if (inc.v > 1e-6) {
+                  const D lg = dual_log(inc);
+                  lp_acc = lp_acc + (o * lg - inc);
+                } else {
+                  lp_acc.v += o * log(1e-6) - 1e-6;  // clamped: zero gradient (jnp.maximum)
+                }
               }
+              obs_prev = v;
             }
-            obs_prev = v;
+            ++save_i;
+            ts_next = (save_i < a.T) ? __ldg(a.save_ts + save_i) : CUDART_INF;
           }
-          ++save_i;
         }
       }
 

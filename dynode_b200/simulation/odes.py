@@ -1,0 +1,327 @@
+"""`simulate`: the drop-in boundary (reference src/dynode/simulation/odes.py:35-198).
+
+Same signature, validations and return conventions as the reference, but instead of tracing the
+RHS through diffrax the call resolves the (registered) RHS to a compiled flow-family instance and
+makes ONE launch of the sm_100a ensemble kernel.  `simulate_ensemble` is the batched entry the
+reference would reach through jax.vmap(simulate) / numpyro Predictive (infer/inference.py:225-235).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from inspect import getfullargspec
+from typing import Any, Dict, Optional, Sequence, Tuple, get_type_hints
+
+import numpy as np
+import torch
+
+from .. import _lib, engine
+from ..flows import FlowSpec, UnsupportedODEError, flow_spec_of, get_path
+from ..typing import CompartmentState, ODE_Eqns
+
+MAX_STEPS_MESSAGE = "The maximum number of solver steps was reached. Try increasing `max_steps`."
+
+
+@dataclasses.dataclass
+class AbstractODEParams:
+    """Base class of the parameter containers passed to the ODEs (reference odes.py:25-32).
+
+    Subclass it as a plain `@dataclasses.dataclass`; fields are floats or torch tensors.
+    """
+
+
+@dataclasses.dataclass
+class SubSaveAt:
+    ts: np.ndarray
+    indices: Optional[Tuple[int, ...]] = None
+
+
+@dataclasses.dataclass
+class SaveAt:
+    """Which times / compartments are saved (stands in for diffrax.SaveAt)."""
+
+    ts: Optional[np.ndarray] = None
+    subs: Optional[SubSaveAt] = None
+
+    @property
+    def times(self) -> np.ndarray:
+        return self.subs.ts if self.subs is not None else self.ts
+
+    @property
+    def indices(self) -> Optional[Tuple[int, ...]]:
+        return self.subs.indices if self.subs is not None else None
+
+
+@dataclasses.dataclass
+class Solution:
+    """What `simulate` returns (the fields DynODE reads off diffrax.Solution).
+
+    ts:    (T,) save times
+    ys:    tuple, one tensor per compartment, leading time axis: (T, *shape); compartments left out
+           by `sub_save_indices` come back with shape (T, 0) (reference odes.py:182-193).
+           Ensemble solves carry a leading batch axis: (B, T, *shape).
+    stats: num_steps, num_accepted_steps, num_rejected_steps, max_steps
+    result: 0 = successful, 1 = max_steps reached (per trajectory for ensembles)
+    """
+
+    t0: float
+    t1: float
+    ts: torch.Tensor
+    ys: Tuple[torch.Tensor, ...]
+    stats: Dict[str, Any]
+    result: Any
+
+
+def build_saveat(start: float, stop, step=1, sub_save_indices: Optional[Tuple[int, ...]] = None) -> SaveAt:
+    """The save grid of the reference (odes.py:148-198): linspace(start, stop, int(stop // step) + 1)."""
+    if step <= 0:
+        step = 1
+    save_times = np.linspace(start, stop, int(stop // step) + 1)
+    if sub_save_indices is not None:
+        return SaveAt(subs=SubSaveAt(ts=save_times, indices=tuple(int(i) for i in sub_save_indices)))
+    return SaveAt(ts=save_times)
+
+
+def _solver_options(solver_parameters, duration_days) -> engine.SolverOptions:
+    from ..config.params import Tsit5
+
+    if not isinstance(solver_parameters.solver_method, Tsit5):
+        raise UnsupportedODEError(
+            f"solver {type(solver_parameters.solver_method).__name__} is not implemented on the device; "
+            "only Tsit5 is (reference default, config/params.py:28-34)")
+    if len(solver_parameters.discontinuity_points) > 0:
+        raise UnsupportedODEError(
+            "discontinuity_points (ClipStepSizeController jump_ts) are not implemented on the device yet")
+    return engine.SolverOptions(
+        t0=0.0, t1=float(duration_days), rtol=solver_parameters.ode_solver_rel_tolerance,
+        atol=solver_parameters.ode_solver_abs_tolerance,
+        const_dt=float(solver_parameters.constant_step_size), max_steps=int(solver_parameters.max_steps))
+
+
+def _numel_per_traj(t: torch.Tensor, batched: bool) -> int:
+    shape = t.shape[1:] if batched else t.shape
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+def _resolve(ode, initial_state, ode_parameters, batch_size: Optional[int], state_batched: bool):
+    """(FlowSpec, FlowModel, kernel parameter dict, contact[target][source]) for this call."""
+    spec: FlowSpec = flow_spec_of(ode)
+    comps = spec.compartments
+    if len(initial_state) != len(comps):
+        raise UnsupportedODEError(
+            f"flow '{spec.flow}' integrates compartments {comps}, got {len(initial_state)} compartments")
+    G = _numel_per_traj(initial_state[0], state_batched)
+    gs = _numel_per_traj(initial_state[1], state_batched)
+    if G == 0 or gs % G != 0:
+        raise UnsupportedODEError("compartment shapes are not (groups) / (groups, strains)")
+    S = gs // G
+    for c in initial_state[2:]:
+        if _numel_per_traj(c, state_batched) != gs:
+            raise UnsupportedODEError("all strain-stratified compartments must share one shape")
+    model = engine.FlowModel(spec.flow_id, spec.flags, G, S)
+    try:
+        model.check_supported()
+    except _lib.DynodeError as e:
+        raise UnsupportedODEError(str(e)) from None
+    params = {}
+    for kname, path in spec.fields.items():
+        params[kname] = torch.as_tensor(get_path(ode_parameters, path), dtype=torch.float64)
+    contact = None
+    if spec.contact is not None:
+        cm = torch.as_tensor(get_path(ode_parameters, spec.contact), dtype=torch.float64)
+        if cm.numel() != G * G:
+            raise UnsupportedODEError(f"contact matrix must have {G}x{G} entries, got {tuple(cm.shape)}")
+        cm = cm.reshape(G, G)
+        contact = cm.t().contiguous() if spec.contact_layout == "source_target" else cm
+    return spec, model, params, contact
+
+
+def _validate_call(ode, initial_state, ode_parameters, duration_days) -> None:
+    # reference odes.py:93-112
+    if any(not isinstance(compartment, torch.Tensor) for compartment in initial_state):
+        raise TypeError("Please pass torch.Tensor compartments (the engine's array type) instead of np.array to ODEs")
+    expected = get_type_hints(getattr(ode, "__wrapped__", ode))[getfullargspec(getattr(ode, "__wrapped__", ode)).args[2]]
+    assert type(ode_parameters) is expected, (
+        f"passed {type(ode_parameters)} ode parameters, but your ODE model expects {expected}")
+    assert isinstance(duration_days, (int, float)), "tf must be of type int or float"
+
+
+def _split_ys(ys_flat: torch.Tensor, model: engine.FlowModel, mask: int, shapes, lead: Tuple[int, ...]):
+    """[..., T, n_saved] -> per-compartment views (..., T, *shape); unsaved -> (..., T, 0)."""
+    out, off = [], 0
+    for c, sz in enumerate(model.compartment_sizes()):
+        if (mask >> c) & 1:
+            out.append(ys_flat[..., off:off + sz].reshape(*lead, *shapes[c]))
+            off += sz
+        else:
+            out.append(ys_flat.new_empty((*lead, 0)))
+    return tuple(out)
+
+
+def _mask_from(indices: Optional[Sequence[int]], ncomp: int) -> int:
+    if indices is None:
+        return (1 << ncomp) - 1
+    mask = 0
+    for i in indices:
+        if not -ncomp <= int(i) < ncomp:
+            print(f"An index passed to sub_save_indices was out of range for initial_state values: {i}")
+            continue
+        mask |= 1 << (int(i) % ncomp)
+    return mask
+
+
+def simulate(
+    ode: ODE_Eqns,
+    duration_days,
+    initial_state: CompartmentState,
+    ode_parameters: AbstractODEParams,
+    solver_parameters,
+    sub_save_indices: Optional[Tuple[int, ...]] = None,
+    save_step: int = 1,
+) -> Solution:
+    """Solve `ode` for `duration_days` days from `initial_state` (reference odes.py:35-145).
+
+    Returns a `Solution` whose `ys` holds, per compartment, the state at every saved day including
+    t=0 and t=duration_days.  Raises TypeError for non-tensor compartments, AssertionError when
+    `ode_parameters` is not of the type the ODE annotates, UnsupportedODEError for an ODE outside the
+    compiled flow family, RuntimeError when `max_steps` is exceeded (diffrax throw=True).
+    """
+    _validate_call(ode, initial_state, ode_parameters, duration_days)
+    sol = _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,
+               save_step, batch_size=None, state_batched=False, throw=True)
+    return sol
+
+
+def simulate_ensemble(
+    ode: ODE_Eqns,
+    duration_days,
+    initial_state: CompartmentState,
+    ode_parameters: AbstractODEParams,
+    solver_parameters,
+    sub_save_indices: Optional[Tuple[int, ...]] = None,
+    save_step: int = 1,
+    *,
+    batch_size: int,
+    state_batched: Optional[bool] = None,
+    throw: bool = True,
+    out: Optional[torch.Tensor] = None,
+    host_chunk: int = 8192,
+) -> Solution:
+    """`simulate` over an ensemble of `batch_size` parameter draws in one launch per device chunk.
+
+    Parameter fields with `batch_size` rows are per-draw, others are shared.  `initial_state`
+    compartments carry a leading batch axis when `state_batched` (default: inferred from the leading
+    dimension).  Outputs carry a leading batch axis and live on the device of `initial_state[0]`;
+    host-resident inputs are streamed (H2D / solve / D2H overlapped in `host_chunk`-sized pieces,
+    `out` = optional pinned [B, T, n_saved] host buffer to reuse).
+    """
+    _validate_call(ode, initial_state, ode_parameters, duration_days)
+    if state_batched is None:
+        state_batched = all(c.ndim >= 1 and c.shape[0] == batch_size for c in initial_state) and (
+            initial_state[0].ndim >= 2 or batch_size != initial_state[0].numel() or batch_size == 1)
+    return _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,
+                save_step, batch_size=int(batch_size), state_batched=bool(state_batched), throw=throw,
+                out=out, host_chunk=host_chunk)
+
+
+def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices, save_step,
+         *, batch_size, state_batched, throw, out=None, host_chunk=8192) -> Solution:
+    _lib.require_cuda()
+    spec, model, params, contact = _resolve(ode, initial_state, ode_parameters, batch_size, state_batched)
+    opts = _solver_options(solver_parameters, duration_days)
+    saveat = build_saveat(opts.t0, duration_days, save_step, sub_save_indices)
+    mask = _mask_from(saveat.indices, model.n_compartments)
+    B = 1 if batch_size is None else batch_size
+    ensemble = batch_size is not None
+    out_dev = initial_state[0].device
+    shapes = [tuple(c.shape[1:] if state_batched else c.shape) for c in initial_state]
+    n = model.state_size
+    if state_batched:
+        y0 = torch.cat([c.reshape(B, -1).to(torch.float64) for c in initial_state], dim=1)
+    else:
+        y0 = torch.cat([c.reshape(-1).to(torch.float64) for c in initial_state])
+    assert y0.shape[-1] == n
+    T = len(saveat.times)
+    ns = model.saved_size(mask)
+    cuda = torch.device("cuda", torch.cuda.current_device())
+
+    if out_dev.type == "cuda" or not ensemble or B <= host_chunk:
+        ys, _, stats = engine.solve_ensemble(model, y0, params, contact, opts, saveat.times, mask, B=B)
+        if out_dev.type != "cuda":
+            if out is not None:
+                out.copy_(ys)
+                ys = out
+            else:
+                ys = ys.cpu()
+            stats_h = stats.cpu()
+        else:
+            stats_h = stats.cpu() if throw else None
+    else:
+        ys, stats_h = _host_pipeline(model, y0, params, contact, opts, saveat.times, mask, B, T, ns, out,
+                                     host_chunk, cuda)
+        stats = stats_h
+
+    if throw and bool((stats_h[:, _lib.STAT_RESULT] != 0).any()):
+        raise RuntimeError(MAX_STEPS_MESSAGE)
+    st = stats if (out_dev.type == "cuda") else stats_h
+    lead = (B, T) if ensemble else (T,)
+    ys_view = ys if ensemble else ys[0]
+    stats_d = {
+        "num_steps": st[:, _lib.STAT_STEPS] if ensemble else st[0, _lib.STAT_STEPS],
+        "num_accepted_steps": st[:, _lib.STAT_ACCEPTED] if ensemble else st[0, _lib.STAT_ACCEPTED],
+        "num_rejected_steps": st[:, _lib.STAT_REJECTED] if ensemble else st[0, _lib.STAT_REJECTED],
+        "max_steps": int(solver_parameters.max_steps),
+    }
+    result = st[:, _lib.STAT_RESULT] if ensemble else st[0, _lib.STAT_RESULT]
+    ts = torch.as_tensor(saveat.times, dtype=torch.float64, device=out_dev)
+    return Solution(t0=opts.t0, t1=opts.t1, ts=ts, ys=_split_ys(ys_view, model, mask, shapes, lead),
+                    stats=stats_d, result=result)
+
+
+def _host_pipeline(model, y0, params, contact, opts, save_ts, mask, B, T, ns, out, chunk, cuda):
+    """Host-resident ensemble: per chunk H2D(params) -> kernel -> D2H(ys), double-buffered on two
+    streams so the PCIe copy of chunk k overlaps the solve of chunk k+1."""
+    S = model.n_strains
+    n = model.state_size
+    if out is None:
+        out = torch.empty((B, T, ns), dtype=torch.float64, pin_memory=True)
+    stats_h = torch.empty((B, 4), dtype=torch.int32, pin_memory=True)
+    compute = torch.cuda.current_stream()
+    copy = torch.cuda.Stream()
+    bufs = [torch.empty((chunk, T, ns), dtype=torch.float64, device=cuda) for _ in range(2)]
+    sbufs = [torch.empty((chunk, 4), dtype=torch.int32, device=cuda) for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    ts_dev = torch.as_tensor(save_ts, dtype=torch.float64, device=cuda)
+    contact_dev = None if contact is None else contact.to(cuda)
+
+    def rows(t, row, lo, hi):
+        if t is None:
+            return None
+        if t.numel() == row:
+            return t.to(cuda, non_blocking=True)
+        return t.reshape(B, row)[lo:hi].to(cuda, non_blocking=True)
+
+    k = 0
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        j = k % 2
+        if k >= 2:
+            compute.wait_event(free[j])  # D2H of the chunk that used this buffer has finished
+        p = {name: rows(t, S if name in ("beta", "gamma", "sigma", "omega") else 1, lo, hi)
+             for name, t in params.items()}
+        y = rows(y0, n, lo, hi)
+        engine.solve_ensemble(model, y, p, contact_dev, opts, ts_dev, mask, out=bufs[j][: hi - lo],
+                              stats_out=sbufs[j][: hi - lo], B=hi - lo)
+        done[j].record(compute)
+        copy.wait_event(done[j])
+        with torch.cuda.stream(copy):
+            out[lo:hi].copy_(bufs[j][: hi - lo], non_blocking=True)
+            stats_h[lo:hi].copy_(sbufs[j][: hi - lo], non_blocking=True)
+            free[j].record(copy)
+        k += 1
+    copy.synchronize()
+    return out, stats_h
