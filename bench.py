@@ -184,7 +184,7 @@ def run_ours(args):
     stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
 
     def step():
-        engine.solve_ensemble(model, y0_d, params_d, contact_d, opts, ts_d, out=ys, stats_out=stats, B=B)
+        engine.solve_ensemble(model, y0_d, params_d, contact_d, opts, save_ts_h, out=ys, stats_out=stats, B=B)
 
     def barrier():
         if world > 1:

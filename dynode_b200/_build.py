@@ -49,17 +49,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in _sources())
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, extra_flags=(),
+          out: str = LIB, build_dir: str = BUILD) -> str:
+    """Compile and link.  `extra_flags`/`out`/`build_dir` exist for tuning experiments (variant
+    libraries selected at run time with DYNODE_B200_LIB)."""
+    if not force and out == LIB and not needs_build():
         return LIB
-    os.makedirs(BUILD, exist_ok=True)
+    BUILD_ = build_dir
+    os.makedirs(BUILD_, exist_ok=True)
     nvcc = _nvcc()
     jobs = []
-    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_v else [])
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if ptxas_v else [])
     for k in instance_ids():
-        obj = os.path.join(BUILD, f"inst_{k}.o")
+        obj = os.path.join(BUILD_, f"inst_{k}.o")
         jobs.append((obj, [nvcc, *flags, f"-DDYN_INST={k}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]))
-    obj = os.path.join(BUILD, "capi.o")
+    obj = os.path.join(BUILD_, "capi.o")
     jobs.append((obj, [nvcc, *flags, "-c", os.path.join(CSRC, "capi.cu"), "-o", obj]))
 
     def run(job):
@@ -75,11 +79,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         for obj, log in results:
             if log.strip():
                 print(f"--- {os.path.basename(obj)}\n{log}", file=sys.stderr)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _ in results]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [o for o, _ in results]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import os
 from typing import Optional, Sequence
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdynode_b200.so")
+LIB_PATH = os.environ.get("DYNODE_B200_LIB") or os.path.join(HERE, "libdynode_b200.so")
 
 FLOW_SIR, FLOW_SEIRS, FLOW_SEIRS_C = 0, 1, 2
 FLAG_SEASONAL, FLAG_DENSITY_DEP = 1, 2
@@ -40,7 +40,8 @@ class ModelDesc(ctypes.Structure):
 
 class SolverDesc(ctypes.Structure):
     _fields_ = [("t0", ctypes.c_double), ("t1", ctypes.c_double), ("rtol", ctypes.c_double),
-                ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64)]
+                ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64),
+                ("save_dt", ctypes.c_double)]
 
 
 class Array(ctypes.Structure):

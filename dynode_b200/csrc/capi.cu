@@ -88,6 +88,7 @@ static void fill_common(SolveArgs& a, const DynodeSolverDesc* sv, int64_t B, Dyn
   a.save_ts = save_ts;
   a.T = T;
   a.t0 = sv->t0; a.t1 = sv->t1; a.rtol = sv->rtol; a.atol = sv->atol; a.const_dt = sv->const_dt;
+  a.save_dt = sv->save_dt > 0.0 ? sv->save_dt : 0.0;
   a.max_steps = (int32_t)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.write_primal = 1;
   a.wrt[0] = a.wrt[1] = -1;

@@ -81,6 +81,12 @@ DYN_DI double rcp_fast(double b) {
   r = fma(r, e, r);
   return r;
 }
+// one Newton step: ~2^-46 relative error, for quantities that only enter a norm
+DYN_DI double rcp_fast1(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  return fma(r, fma(-b, r, 1.0), r);
+}
 DYN_DI double div_fast(double a, double b) {
   const double r = rcp_fast(b);
   const double q = a * r;

@@ -23,6 +23,7 @@ struct SolveArgs {
   int32_t T;
   uint32_t save_mask;
   double t0, t1, rtol, atol, const_dt;
+  double save_dt;  // > 0: save_ts is the uniform grid t0 + k*save_dt (k < T-1), ts[T-1] = t1
   int32_t max_steps;
   double* ys;      // [B][T][n_saved]   (written when write_primal)
   int32_t* stats;  // [B][4]            (written when write_primal)

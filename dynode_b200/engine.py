@@ -64,9 +64,27 @@ class SolverOptions:
     const_dt: float = 0.0
     max_steps: int = 10**6
 
-    def desc(self) -> _lib.SolverDesc:
+    def desc(self, save_dt: float = 0.0) -> _lib.SolverDesc:
         return _lib.SolverDesc(float(self.t0), float(self.t1), float(self.rtol), float(self.atol),
-                               float(self.const_dt), int(self.max_steps))
+                               float(self.const_dt), int(self.max_steps), float(save_dt))
+
+
+def uniform_save_dt(save_ts, t0: float, t1: float) -> float:
+    """save_dt hint for the C ABI: > 0 only if `save_ts` (host array) is bit-for-bit the grid
+    t0 + k*dt (k < T-1), ts[T-1] = t1 that build_saveat's linspace produces; else 0."""
+    import numpy as np
+
+    if not isinstance(save_ts, np.ndarray) or save_ts.ndim != 1 or save_ts.size < 2:
+        return 0.0
+    ts = save_ts.astype(np.float64, copy=False)
+    dt = float(ts[1] - ts[0])
+    if not dt > 0.0 or ts[0] != t0 or ts[-1] != t1:
+        return 0.0
+    k = np.arange(ts.size - 1, dtype=np.float64)
+    return dt if np.array_equal(ts[:-1], k * dt + t0) else 0.0
+
+
+_GRID_CACHE: Dict[tuple, object] = {}
 
 
 def _dev_f64(torch, x, device):
@@ -88,7 +106,8 @@ def _as_array(t, row: int, B: int, name: str) -> _lib.Array:
 class _Bound:
     """Validated device-side view of one ensemble call (keeps tensors alive across the launch)."""
 
-    def __init__(self, model: FlowModel, y0, params: Dict[str, object], contact, save_ts, B=None):
+    def __init__(self, model: FlowModel, y0, params: Dict[str, object], contact, save_ts, B=None,
+                 opts: "SolverOptions" = None):
         torch = _lib.require_cuda()
         model.check_supported()
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -113,7 +132,20 @@ class _Bound:
             self.contact = _dev_f64(torch, contact, dev)
             if self.contact.numel() != G * G:
                 raise ValueError(f"contact must be {G}x{G}, got {tuple(self.contact.shape)}")
-        self.save_ts = _dev_f64(torch, save_ts, dev)
+        # host grids are checked for build_saveat's uniform pattern (lets the kernel skip the loads);
+        # device-resident grids carry the hint from the caller (attribute `dynode_save_dt`)
+        self.save_dt = getattr(save_ts, "dynode_save_dt", 0.0)
+        if opts is not None and not hasattr(save_ts, "dynode_save_dt"):
+            self.save_dt = uniform_save_dt(save_ts, float(opts.t0), float(opts.t1))
+        key = None
+        if self.save_dt > 0.0:  # uniform host grid: keep one device copy per (device, grid)
+            key = (dev.index, len(save_ts), float(save_ts[0]), float(save_ts[-1]), self.save_dt)
+        if key is not None and key in _GRID_CACHE:
+            self.save_ts = _GRID_CACHE[key]
+        else:
+            self.save_ts = _dev_f64(torch, save_ts, dev)
+            if key is not None:
+                _GRID_CACHE[key] = self.save_ts
         self.T = int(self.save_ts.numel())
         self.c_params = _lib.Params()
         for k in _PARAM_FIELDS:
@@ -130,14 +162,14 @@ def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opt
 
     Everything stays on the current CUDA device and stream; nothing synchronises.
     """
-    b = _Bound(model, y0, params, contact, save_ts, B)
+    b = _Bound(model, y0, params, contact, save_ts, B, opts)
     torch = b.torch
     mask = model.full_mask() if save_mask is None else int(save_mask)
     ns = model.saved_size(mask)
     ys = out if out is not None else torch.empty((b.B, b.T, ns), dtype=torch.float64, device=b.dev)
     stats = stats_out if stats_out is not None else torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
     L = _lib.load()
-    md, sd = model.desc(), opts.desc()
+    md, sd = model.desc(), opts.desc(b.save_dt)
     stream = ctypes.c_void_p(_lib.current_stream_ptr())
     P = len(wrt)
     if P == 0:
@@ -162,7 +194,7 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
                         save_ts, obs_comp: int, obs, lp_const: float = 0.0, wrt: Sequence[int] = (),
                         dy0=None, B: Optional[int] = None):
     """Fused solve + Poisson-incidence log-likelihood + gradient: returns (lp[B], grad[B,P], stats)."""
-    b = _Bound(model, y0, params, contact, save_ts, B)
+    b = _Bound(model, y0, params, contact, save_ts, B, opts)
     torch = b.torch
     m = model.compartment_sizes()[obs_comp]
     obs_t = _dev_f64(torch, obs, b.dev)
@@ -175,7 +207,7 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
     d0 = None
     if dy0 is not None:
         d0 = _dev_f64(torch, dy0, b.dev)
-    md, sd = model.desc(), opts.desc()
+    md, sd = model.desc(), opts.desc(b.save_dt)
     _lib.check(_lib.load().dynode_poisson_loglik_grad_f64(
         ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(),
         b.T, int(obs_comp), obs_t.data_ptr(), float(lp_const), P, _lib.i32_array(list(wrt)),

@@ -59,6 +59,10 @@ typedef struct {
   double rtol, atol;
   double const_dt;
   int64_t max_steps;
+  /* Optional hint: if > 0 the caller guarantees save_ts[k] == t0 + k*save_dt for k < T-1 and
+   * save_ts[T-1] == t1 bit-for-bit (build_saveat's linspace grid); the kernel then generates the
+   * save times arithmetically instead of loading them.  0 = read save_ts. */
+  double save_dt;
 } DynodeSolverDesc;
 
 /* An ensemble array: element (b, k) lives at ptr[b*batch_stride + k]; batch_stride == 0 shares
