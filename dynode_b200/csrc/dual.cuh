@@ -103,6 +103,16 @@ template <int P> DYN_DI Dual<P> ddiv_fast(const Dual<P>& a, const Dual<P>& b) {
   }
   return r;
 }
+template <int P> DYN_DI Dual<P> drcp_fast(const Dual<P>& b) {
+  Dual<P> r;
+  r.v = rcp_fast(b.v);
+  if constexpr (P > 0) {
+    const double m = -r.v * r.v;
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.d[p] = m * b.d[p];
+  }
+  return r;
+}
 template <int P> DYN_DI Dual<P> dneg(const Dual<P>& a) {
   Dual<P> r; r.v = -a.v;
   if constexpr (P > 0) {

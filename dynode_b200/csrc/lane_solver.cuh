@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/dynode_b200.h"
 #include "dual.cuh"
@@ -88,15 +89,28 @@ struct LaneSolver {
   static DYN_DI double traj_sum(double x, const Ctx& c) { return sum_groups(sum_strains(x, c), c); }
 
   // ---- right-hand side of the flow family in lane layout -------------
-  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Ctx& c) {
+  // 1 / N_g with N_g = s_g + sum_s (e+i+r)[g,s]  (c excluded).  N_g is a linear invariant of every
+  // flow in the family (each transfer leaves one compartment of group g and enters another), and an
+  // explicit Runge-Kutta stage y + h*sum a_ij f_j preserves linear invariants to rounding.  The
+  // kernel therefore forms 1/N_g once per step from the step's initial state and reuses it for the
+  // stages of that step; the reference re-sums N at every stage, which differs by O(1e-16) relative.
+  static DYN_DI D inv_population(const D (&y)[NE], const Ctx& c) {
+    if constexpr (DENSITY) {
+      return make_dual<P>(1.0);
+    } else {
+      D part = y[II] + y[IR];
+      if constexpr (HAS_E) part = part + y[IE];
+      const D Ng = y[0] + sum_strains(part, c);
+      return drcp_fast(Ng);
+    }
+  }
+
+  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Ctx& c, const D& invN) {
     D prop;
     if constexpr (DENSITY) {
       prop = y[II];  // tests/test_simulation/test_odes.py:23  s_to_i = beta*s*i
     } else {
-      D part = y[II] + y[IR];
-      if constexpr (HAS_E) part = part + y[IE];
-      const D Ng = y[0] + sum_strains(part, c);  // N_g = s_g + sum_s (e+i+r)[g,s]   (c excluded)
-      prop = ddiv_fast(y[II], Ng);
+      prop = y[II] * invN;
     }
     // contact contraction: sum_b K[g][b] * prop[b, s]
     D acc;
@@ -238,7 +252,8 @@ struct LaneSolver {
     const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
     const double inv_n = 1.0 / (double)N;
     double tprev = a.t0, tnext;
-    rhs(a.t0, y, f[0], c);  // FSAL f0 (solver.init)
+    D invN = inv_population(y, c);
+    rhs(a.t0, y, f[0], c, invN);  // FSAL f0 (solver.init)
 
     if (a.const_dt > 0.0) {
       tnext = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
@@ -259,7 +274,7 @@ struct LaneSolver {
       const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, f[0][e], y[e]);
-      rhs(a.t0 + h0, ys, f[1], c);
+      rhs(a.t0 + h0, ys, f[1], c, invN);
       double p2 = 0.0;
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
@@ -285,31 +300,48 @@ struct LaneSolver {
 
     while (__any_sync(0xffffffffu, active)) {
       const double h = tnext - tprev;
+      invN = inv_population(y, c);
       // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, T5_a21 * f[0][e], y[e]);
-      rhs(fma(T5_c2, h, tprev), ys, f[1], c);
+      rhs(fma(T5_c2, h, tprev), ys, f[1], c, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(T5_a32, f[1][e], T5_a31 * f[0][e]), y[e]);
-      rhs(fma(T5_c3, h, tprev), ys, f[2], c);
+      rhs(fma(T5_c3, h, tprev), ys, f[2], c, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a43, f[2][e], dfma(T5_a42, f[1][e], T5_a41 * f[0][e])), y[e]);
-      rhs(fma(T5_c4, h, tprev), ys, f[3], c);
+      rhs(fma(T5_c4, h, tprev), ys, f[3], c, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a54, f[3][e], dfma(T5_a53, f[2][e], dfma(T5_a52, f[1][e], T5_a51 * f[0][e]))), y[e]);
-      rhs(fma(T5_c5, h, tprev), ys, f[4], c);
+      rhs(fma(T5_c5, h, tprev), ys, f[4], c, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a65, f[4][e], dfma(T5_a64, f[3][e], dfma(T5_a63, f[2][e],
                      dfma(T5_a62, f[1][e], T5_a61 * f[0][e])))), y[e]);
-      rhs(tnext, ys, f[5], c);
+      rhs(tnext, ys, f[5], c, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a76, f[5][e], dfma(T5_a75, f[4][e], dfma(T5_a74, f[3][e], dfma(T5_a73, f[2][e],
                      dfma(T5_a72, f[1][e], T5_a71 * f[0][e]))))), y[e]);
-      rhs(tnext, ys, f[6], c);  // ys is y1
+      rhs(tnext, ys, f[6], c, invN);  // ys is y1
+
+      // ---- dense-output coefficients, formed unconditionally right after the last stage so their
+      // independent FMAs overlap the latency-bound error-norm / controller chain below.
+      // Monomial form of the Tsit5 interpolant (tsit5.cuh kDense):
+      //   y(th) = y + (h th w11) f1 + (h th^2) (Q2 + th (Q3 + th Q4)),  Q_m = sum_i w_im f_i
+      D Q[3][NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          D acc = kDense[0][m + 1] * f[0][e];
+#pragma unroll
+          for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
+          Q[m][e] = acc;
+        }
+      }
 
       // ---- embedded error, scaled RMS norm over the whole state (PIDController.adapt_step_size).
       // A NaN error estimate propagates to err and is rejected with factor 0.2, which is what
@@ -335,9 +367,9 @@ struct LaneSolver {
           const double r = er * rcp_fast1(sc);  // 2^-46 relative: only the RMS norm sees it
           if (e == 0) part = lead ? r * r : 0.0; else part = fma(r, r, part);
         }
-        const double err = sqrt(traj_sum(part, c) * inv_n);
-        keep = err < 1.0;
-        dt_next = h * controller_factor(err, keep);
+        const double err2 = traj_sum(part, c) * inv_n;  // err^2 (RMS norm squared)
+        keep = err2 < 1.0;                               // err < 1
+        dt_next = h * controller_factor_sq(err2, keep);
       }
       double ntprev = keep ? tnext : tprev;
       double ntnext = ntprev + dt_next;
@@ -348,19 +380,6 @@ struct LaneSolver {
       const bool do_save = active && keep;
       double ts_next = do_save ? save_time(save_i) : CUDART_INF;
       if (__any_sync(0xffffffffu, ts_next <= tnext)) {
-        // monomial form of the Tsit5 interpolant (tsit5.cuh kDense):
-        //   y(th) = y + (h th w11) f1 + (h th^2) (Q2 + th (Q3 + th Q4)),  Q_m = sum_i w_im f_i
-        D Q[3][NE];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            D acc = kDense[0][m + 1] * f[0][e];
-#pragma unroll
-            for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
-            Q[m][e] = acc;
-          }
-        }
         const double inv_h = rcp_fast((tnext == tprev) ? 1.0 : h);
         const double hw = h * kDense[0][0];
         auto dense = [&](int e, double th, double hthw, double hth2) -> D {
@@ -482,11 +501,19 @@ struct LaneSolver {
   }
 };
 
-#ifndef DYN_MINBLOCKS
-#define DYN_MINBLOCKS 1
+// Resident CTAs per SM asked of ptxas (64-thread CTAs).  Measured on B200 (profiles/r1_tuning.md):
+// 5-element lanes (SEIRS+C) run best at 6 CTAs = 12 warps with 168 registers and no spills; forcing
+// 128 registers (16 warps) spills and loses 14%.  3/4-element lanes fit 128 registers -> 16 warps.
+// Tangent-carrying kernels keep every register they can get.
+constexpr int min_blocks(int flow, int p) {
+#ifdef DYN_MINBLOCKS
+  return DYN_MINBLOCKS;
+#else
+  return p > 0 ? 1 : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8);
 #endif
+}
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
-__global__ void __launch_bounds__(kThreads, DYN_MINBLOCKS) lane_solver_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, min_blocks(FLOW, P)) lane_solver_kernel(const SolveArgs a) {
   LaneSolver<FLOW, FLAGS, G, S, P, MODE>::run(a);
 }
 
@@ -497,7 +524,16 @@ cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream) {
   constexpr int per_cta = TPW * (kThreads / 32);
   const int64_t grid = (a.B + per_cta - 1) / per_cta;
   if (grid <= 0) return cudaSuccess;
-  lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+  size_t smem = 0;
+#ifdef DYN_TUNING
+  // tuning only: cap resident CTAs per SM by reserving dynamic shared memory (DYN_SMEM_PAD bytes)
+  if (const char* e = getenv("DYN_SMEM_PAD")) {
+    smem = (size_t)atol(e);
+    cudaFuncSetAttribute(lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+#endif
+  lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE><<<(unsigned)grid, kThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

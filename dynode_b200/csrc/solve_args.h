@@ -11,7 +11,10 @@ constexpr int kPMax = 2;            // max tangent directions carried per pass (
 // Directions per pass chosen so that (1+P) * 8 * NE doubles stay in registers without spilling:
 // SIR lanes hold 3 elements (P=2 -> 72 doubles), SEIRS/SEIRS_C lanes 4-5 elements (P=1 -> 80).
 constexpr int tangent_chunk(int flow) { return flow == DYNODE_FLOW_SIR ? 2 : 1; }
-constexpr int kThreads = 128;       // 4 warps per CTA
+#ifndef DYN_THREADS
+#define DYN_THREADS 64
+#endif
+constexpr int kThreads = DYN_THREADS;  // warps per CTA = kThreads / 32
 constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
 constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
 
