@@ -513,7 +513,11 @@ constexpr int min_blocks(int flow, int p) {
 #endif
 }
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
+#ifdef DYN_MAXNREG
+__global__ void __maxnreg__(DYN_MAXNREG) lane_solver_kernel(const SolveArgs a) {
+#else
 __global__ void __launch_bounds__(kThreads, min_blocks(FLOW, P)) lane_solver_kernel(const SolveArgs a) {
+#endif
   LaneSolver<FLOW, FLAGS, G, S, P, MODE>::run(a);
 }
 

@@ -49,3 +49,120 @@ def test_saved_trajectories_match_oracle(name):
     # ys[0] == y0 exactly (reference tests/test_simulation/test_odes.py:63-74)
     y0 = np.broadcast_to(case["y0"], (B, ys.shape[2]))
     assert np.array_equal(ys[:, 0, :], y0)
+
+
+def test_partial_save_mask_and_nonuniform_grid():
+    """sub_save_indices / save_step paths (reference odes.py:177-193): generic store path + loaded grid."""
+    case = make_case("seirs_multi_a2s3", 101)
+    t1 = 100
+    ts = np.linspace(0.0, t1, int(t1 // 3) + 1)  # save_step=3 -> 34 points spaced 100/33
+    from oracle import oracle as orc
+    fam, dims, theta, shared = case["oracle"]
+    for mask, idx in ((0b10001, list(range(0, 2)) + list(range(20, 26))), (0b00100, list(range(8, 14)))):
+        ys, _, st = _run_engine(case, t1, save_ts=ts, save_mask=mask)
+        ref, _, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, save_ts=ts, save_idx=idx)
+        assert ys.shape == ref.shape and np.array_equal(st, rst)
+        _assert_close(ys, ref)
+
+
+def test_constant_step_and_max_steps():
+    case = make_case("sir_age2", 40)
+    ys, _, st = _run_engine(case, 60, opts=dict(const_dt=0.5))
+    ref, _, rst = _run_oracle(case, 60, const_dt=0.5)
+    assert np.array_equal(st, rst) and np.all(st[:, 1] == 120)
+    _assert_close(ys, ref)
+    ys, _, st = _run_engine(case, 100, opts=dict(max_steps=7))
+    ref, _, rst = _run_oracle(case, 100, max_steps=7)
+    assert np.array_equal(st, rst) and np.all(st[:, 0] == 1)
+    assert np.array_equal(np.isinf(ys), np.isinf(ref))  # unreached slots keep +inf
+    fin = np.isfinite(ref)
+    _assert_close(ys[fin], ref[fin])
+
+
+def test_zero_infection_edge_and_tight_tolerance():
+    """f == 0 initial-step edge (reference tests/test_sir_dynamics/test_sir.py:75) and rtol=1e-10."""
+    import dynode_b200._lib as L
+    from dynode_b200.engine import FlowModel
+    model = FlowModel(L.FLOW_SIR, 0, 1, 1)
+    case = dict(model=model, params=dict(beta=np.array([[2 / 7]]), gamma=np.array([[1 / 7]])), contact=None,
+                y0=np.array([0.8, 0.0, 0.2]), oracle=(0, (1, 1, 1), np.array([[2 / 7, 1 / 7]]), None))
+    ys, _, st = _run_engine(case, 120)
+    ref, _, rst = _run_oracle(case, 120)
+    assert np.array_equal(st, rst) and np.all(np.isfinite(ys))
+    _assert_close(ys, ref)
+    case2 = make_case("seirs_seasonal", 64)
+    ys, _, st = _run_engine(case2, 200, opts=dict(rtol=1e-10, atol=1e-12))
+    ref, _, rst = _run_oracle(case2, 200, rtol=1e-10, atol=1e-12)
+    assert np.array_equal(st, rst)
+    _assert_close(ys, ref, rtol=1e-8)
+
+
+WRT = {
+    # case -> (engine wrt ids, oracle theta indices)
+    "sir_age2": ([0 * 16 + 0, 1 * 16 + 0], [0, 1]),
+    "sir_1bin": ([0 * 16 + 0, 1 * 16 + 0], [0, 1]),
+    "seirs_seasonal": ([0, 16, 32, 48, 64, 80], [0, 1, 2, 3, 4, 5]),
+    "seirs_multi_a2s3": ([0, 2, 16 + 1, 32 + 2, 48 + 0], [0, 2, 4, 8, 9]),
+    "sir_age_risk32": ([0, 16], [0, 1]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WRT))
+def test_forward_sensitivities_match_oracle(name):
+    B = 37
+    case = make_case(name, B)
+    t1 = min(case["t1"], 120)
+    wrt_e, wrt_o = WRT[name]
+    ys, dys, st = _run_engine(case, t1, wrt=wrt_e)
+    ref, dref, rst = _run_oracle(case, t1, wrt=wrt_o)
+    assert np.array_equal(st, rst)
+    _assert_close(ys, ref)
+    assert dys.shape == dref.shape
+    for p in range(len(wrt_e)):
+        _assert_close(dys[..., p], dref[..., p], rtol=1e-8, atol_scale=1e-11)
+
+
+def test_sensitivities_with_initial_state_tangents():
+    B = 19
+    case = make_case("seirs_multi_a2s3", B)
+    rng = np.random.default_rng(0)
+    dy0 = rng.normal(size=(B, 2, 26))
+    ys, dys, st = _run_engine(case, 90, wrt=[-1, 0], dy0=dy0)
+    ref, dref, rst = _run_oracle(case, 90, wrt=[-1, 0], dy0=dy0)
+    assert np.array_equal(st, rst)
+    _assert_close(dys, dref, rtol=1e-8, atol_scale=1e-11)
+
+
+@pytest.mark.parametrize("name,obs_comp,wrt_e,wrt_o", [
+    ("sir_age2", 2, [0, 16], [0, 1]),            # NUTS config: Poisson on diff(R), d/d(beta, gamma)
+    ("seirs_multi_a2s3", 4, [0, 1, 2, 16, 17, 18], [0, 1, 2, 3, 4, 5]),  # Poisson on diff(C)
+    ("sir_age2", 0, [], []),
+])
+def test_fused_poisson_loglik_and_gradient(name, obs_comp, wrt_e, wrt_o):
+    import torch
+    from scipy.special import gammaln
+    from dynode_b200.engine import SolverOptions, poisson_loglik_grad
+    from oracle import oracle as orc
+    B = 53
+    case = make_case(name, B)
+    t1 = 100
+    fam, dims, theta, shared = case["oracle"]
+    sizes = case["model"].compartment_sizes()
+    lo = sum(sizes[:obs_comp])
+    idx = list(range(lo, lo + sizes[obs_comp]))
+    # synthetic observations: increments of trajectory 0 (non-integer, as in the reference example)
+    truth, _, _ = orc.solve(fam, dims, case["y0"][:1] if np.ndim(case["y0"]) == 2 else case["y0"], theta[:1],
+                            shared, t1=t1, save_idx=idx)
+    obs = np.abs(np.diff(truth[0], axis=0)) + 0.05
+    lp_const = float(-gammaln(obs + 1).sum())
+    ts = np.linspace(0.0, t1, t1 + 1)
+    lp, grad, st = poisson_loglik_grad(case["model"], case["y0"], case["params"], case["contact"],
+                                       SolverOptions(t1=t1), ts, obs_comp, obs, lp_const, wrt=wrt_e)
+    torch.cuda.synchronize()
+    ys, dys, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, save_idx=idx, wrt=wrt_o)
+    lp_ref, g_ref = orc.poisson_incidence(ys, dys, obs)
+    assert np.array_equal(st.cpu().numpy(), rst)
+    assert np.allclose(lp.cpu().numpy(), lp_ref, rtol=1e-10, atol=0)
+    if wrt_e:
+        g = grad.cpu().numpy()
+        assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
