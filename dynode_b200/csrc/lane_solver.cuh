@@ -10,9 +10,15 @@
 //   lane (g, s) holds  S_g (replicated across the S lanes of a group, kept bit-identical by
 //   order-fixed segmented sums), and E/I/R/C[g, s]: NE <= 5 state elements, 8*NE doubles with the
 //   7 stage derivatives, all in registers -> no shared/local memory traffic in the step loop.
-//   32/L trajectories share a warp (SIR/SEIRS 1-bin: 32, age SIR: 16, multi-strain 2x3: 5).
+//   A warp has TPW = 32/L trajectory SLOTS (SIR/SEIRS 1-bin: 32, age SIR: 16, multi-strain 2x3: 5).
 //   Cross-lane terms (N_g, the contact contraction, dS_g, the RMS error norm) are warp shuffles.
 //   FP64 FMA on the CUDA cores; no tensor cores (contractions are <= 6x6).
+//
+// Persistent slots: adaptive step counts differ per draw (47..129 attempts for seasonal SEIRS), so
+// a warp that integrated a fixed set of trajectories would idle its finished slots until the
+// slowest one ends (measured: 10% of lane-steps for the 5-slot multi-strain case, 49% for 32
+// slots).  Instead every warp owns a contiguous chunk of the ensemble and a finished slot is
+// refilled with the warp's next trajectory (initial-step selection runs masked inside the loop).
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -39,22 +45,30 @@ struct LaneSolver {
   static constexpr int IR = II + 1;
   static constexpr int IC = IR + 1;
   static constexpr int L = G * S;
-  static constexpr int TPW = 32 / L;  // trajectories per warp
+  static constexpr int TPW = 32 / L;  // trajectory slots per warp
   static constexpr int N = G + (NE - 1) * G * S;
+  // Persistent slots pay off only where many slots share a warp (measured on B200, profiles/
+  // r1_tuning.md: +11% for 32 slots, -8% for the 5-slot multi-strain case whose step counts are
+  // tight); otherwise a warp integrates one generation of TPW trajectories.
+  static constexpr bool PERSIST = TPW >= 8;
+  // refill as soon as this many slots are idle (masked re-initialisation costs ~1.5 steps)
+  static constexpr int REFILL = TPW >= 8 ? TPW / 8 : 1;
   static_assert(L >= 1 && L <= 32, "a trajectory must fit one warp");
   using D = Dual<P>;
 
-  struct Ctx {
-    int base;   // lane of cell (0,0) of my trajectory
+  struct Geo {  // lane geometry + the shared contact row (fixed for the whole kernel)
+    int base;   // lane of cell (0,0) of my slot
     int sbase;  // lane of cell (g,0)
     int g, s;
+    double K[G];  // contact[g][:]
+  };
+  struct Prm {  // per-trajectory parameters of my cell
     D beta, gamma, sigma, omega, amp, phase;
     double period;
-    double K[G];  // contact[g][:]
   };
 
   // sum over the S strain lanes of my group, in fixed order (identical in every lane of the group)
-  static DYN_DI D sum_strains(const D& x, const Ctx& c) {
+  static DYN_DI D sum_strains(const D& x, const Geo& c) {
     if constexpr (S == 1) {
       return x;
     } else {
@@ -64,7 +78,7 @@ struct LaneSolver {
       return r;
     }
   }
-  static DYN_DI double sum_strains(double x, const Ctx& c) {
+  static DYN_DI double sum_strains(double x, const Geo& c) {
     if constexpr (S == 1) {
       return x;
     } else {
@@ -75,7 +89,7 @@ struct LaneSolver {
     }
   }
   // sum over groups of a value that is already identical across the strain lanes of each group
-  static DYN_DI double sum_groups(double x, const Ctx& c) {
+  static DYN_DI double sum_groups(double x, const Geo& c) {
     if constexpr (G == 1) {
       return x;
     } else {
@@ -86,15 +100,14 @@ struct LaneSolver {
     }
   }
   // sum of a per-lane partial over the whole trajectory; identical in all of its lanes
-  static DYN_DI double traj_sum(double x, const Ctx& c) { return sum_groups(sum_strains(x, c), c); }
+  static DYN_DI double traj_sum(double x, const Geo& c) { return sum_groups(sum_strains(x, c), c); }
 
-  // ---- right-hand side of the flow family (SURVEY.md 8a row a11) in lane layout -------------
   // 1 / N_g with N_g = s_g + sum_s (e+i+r)[g,s]  (c excluded).  N_g is a linear invariant of every
   // flow in the family (each transfer leaves one compartment of group g and enters another), and an
   // explicit Runge-Kutta stage y + h*sum a_ij f_j preserves linear invariants to rounding.  The
   // kernel therefore forms 1/N_g once per step from the step's initial state and reuses it for the
   // stages of that step; the reference re-sums N at every stage, which differs by O(1e-16) relative.
-  static DYN_DI D inv_population(const D (&y)[NE], const Ctx& c) {
+  static DYN_DI D inv_population(const D (&y)[NE], const Geo& c) {
     if constexpr (DENSITY) {
       return make_dual<P>(1.0);
     } else {
@@ -105,7 +118,9 @@ struct LaneSolver {
     }
   }
 
-  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Ctx& c, const D& invN) {
+  // ---- right-hand side of the flow family (SURVEY.md 8a row a11) in lane layout -------------
+  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Geo& c, const Prm& p,
+                         const D& invN) {
     D prop;
     if constexpr (DENSITY) {
       prop = y[II];  // tests/test_simulation/test_odes.py:23  s_to_i = beta*s*i
@@ -121,35 +136,35 @@ struct LaneSolver {
 #pragma unroll
       for (int b = 1; b < G; ++b) acc = dfma(c.K[b], dual_shfl(prop, c.base + b * S + c.s), acc);
     }
-    D beta_t = c.beta;
+    D beta_t = p.beta;
     if constexpr (SEASONAL) {
       // beta*(1 + amp*sin(2*pi*t/period + phase))   (seirs_seasonal_forcing.py:34-37)
-      const double w = ((2.0 * CUDART_PI) * t) / c.period;
-      D arg = c.phase;
+      const double w = ((2.0 * CUDART_PI) * t) / p.period;
+      D arg = p.phase;
       arg.v += w;
       double sn, cs;
       sincos(arg.v, &sn, &cs);
       D seas;
-      seas.v = fma(c.amp.v, sn, 1.0);
+      seas.v = fma(p.amp.v, sn, 1.0);
       if constexpr (P > 0) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) seas.d[p] = fma(c.amp.d[p], sn, c.amp.v * cs * arg.d[p]);
+        for (int k = 0; k < P; ++k) seas.d[k] = fma(p.amp.d[k], sn, p.amp.v * cs * arg.d[k]);
       }
-      beta_t = c.beta * seas;
+      beta_t = p.beta * seas;
     }
     const D foi = beta_t * acc;
     const D newinf = foi * y[0];
-    const D rec = c.gamma * y[II];
+    const D rec = p.gamma * y[II];
     if constexpr (WANING) {
-      dy[0] = sum_strains(dmsub(c.omega, y[IR], newinf), c);  // ds_g = sum_s (omega_s r - newinf)
-      dy[IR] = dnmadd(c.omega, y[IR], rec);                   // gamma i - omega r
+      dy[0] = sum_strains(dmsub(p.omega, y[IR], newinf), c);  // ds_g = sum_s (omega_s r - newinf)
+      dy[IR] = dnmadd(p.omega, y[IR], rec);                   // gamma i - omega r
     } else {
       dy[0] = sum_strains(dneg(newinf), c);
       dy[IR] = rec;
     }
     if constexpr (HAS_E) {
-      dy[IE] = dnmadd(c.sigma, y[IE], newinf);  // newinf - sigma e
-      dy[II] = dmsub(c.sigma, y[IE], rec);      // sigma e - gamma i
+      dy[IE] = dnmadd(p.sigma, y[IE], newinf);  // newinf - sigma e
+      dy[II] = dmsub(p.sigma, y[IE], rec);      // sigma e - gamma i
     } else {
       dy[II] = newinf - rec;
     }
@@ -165,45 +180,23 @@ struct LaneSolver {
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int tw = lane / L;
     const int q = lane - tw * L;
-    Ctx c;
+    Geo c;
     c.g = q / S;
     c.s = q - c.g * S;
     c.base = tw * L;
     c.sbase = c.base + c.g * S;
-    const int64_t traj = warp_global * TPW + tw;
-    const bool valid = (tw < TPW) && (traj < a.B);
-    const int64_t tr = valid ? traj : 0;  // invalid lanes shadow trajectory 0, never write
-    const bool lead = (c.s == 0);         // owner of the replicated S_g for norms and stores
-
-    // ---- parameters -> registers (coalesced: a warp reads a contiguous run of draws)
-    auto ld = [&](const DynodeArray& arr, int k, double dflt) -> double {
-      return arr.ptr ? __ldg(arr.ptr + tr * arr.batch_stride + k) : dflt;
-    };
-    c.beta = make_dual<P>(ld(a.prm.beta, c.s, 0.0));
-    c.gamma = make_dual<P>(ld(a.prm.gamma, c.s, 0.0));
-    c.sigma = make_dual<P>(HAS_E ? ld(a.prm.sigma, c.s, 0.0) : 0.0);
-    c.omega = make_dual<P>(WANING ? ld(a.prm.omega, c.s, 0.0) : 0.0);
-    c.amp = make_dual<P>(SEASONAL ? ld(a.prm.season_amp, 0, 0.0) : 0.0);
-    c.phase = make_dual<P>(SEASONAL ? ld(a.prm.season_phase, 0, 0.0) : 0.0);
-    c.period = SEASONAL ? ld(a.prm.season_period, 0, 1.0) : 1.0;
 #pragma unroll
     for (int b = 0; b < G; ++b)
       c.K[b] = a.prm.contact ? __ldg(a.prm.contact + c.g * G + b) : (b == c.g ? 1.0 : 0.0);
-    if constexpr (P > 0) {
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const int w = a.wrt[p];
-        if (w >= 0 && (w & 15) == c.s) {
-          const int kind = w >> 4;
-          if (kind == DYNODE_P_BETA) c.beta.d[p] = 1.0;
-          if (kind == DYNODE_P_GAMMA) c.gamma.d[p] = 1.0;
-          if (kind == DYNODE_P_SIGMA) c.sigma.d[p] = 1.0;
-          if (kind == DYNODE_P_OMEGA) c.omega.d[p] = 1.0;
-        }
-        if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_AMP) c.amp.d[p] = 1.0;
-        if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_PHASE) c.phase.d[p] = 1.0;
-      }
-    }
+    const bool slot_ok = tw < TPW;   // lanes beyond the last whole slot never own a trajectory
+    const bool lead = (c.s == 0);    // owner of the replicated S_g for norms and stores
+    const bool head = slot_ok && q == 0;
+
+    // this warp's contiguous chunk of the ensemble
+    const int64_t chunk_begin = warp_global * a.chunk;
+    const int64_t chunk_end = (chunk_begin + a.chunk < a.B) ? chunk_begin + a.chunk : a.B;
+    int64_t next = chunk_begin;  // warp-uniform: first trajectory not yet handed to a slot
+    if (chunk_begin >= a.B) return;
 
     // ---- element offsets inside a full state row and inside a saved row
     int off_full[NE], off_save[NE];
@@ -224,108 +217,215 @@ struct LaneSolver {
     }
     if (!lead) off_save[0] = -1;  // S_g is stored once, by the strain-0 lane
     const bool full_save = a.write_primal && a.save_mask == ((1u << NE) - 1u);
-    // running output pointers of the full-save fast path (advanced by N per saved time)
-    double* out_s = a.ys + traj * (int64_t)a.T * N + c.g;
-    double* out_c = a.ys + traj * (int64_t)a.T * N + G + c.g * S + c.s;
     // save time k: generated arithmetically for build_saveat's uniform grid, else loaded
     auto save_time = [&](int k) -> double {
       if (k >= a.T) return CUDART_INF;
       if (a.save_dt > 0.0) return (k == a.T - 1) ? a.t1 : fma((double)k, a.save_dt, a.t0);
       return __ldg(a.save_ts + k);
     };
-
-    // ---- initial state
-    D y[NE], f[7][NE], ys[NE];
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      y[e] = make_dual<P>(__ldg(a.y0.ptr + tr * a.y0.batch_stride + off_full[e]));
-      if constexpr (P > 0) {
-        if (a.dy0) {
-#pragma unroll
-          for (int p = 0; p < P; ++p)
-            if (a.p0 + p < a.P_total)
-              y[e].d[p] = __ldg(a.dy0 + ((tr * a.P_total + a.p0 + p) * (int64_t)N) + off_full[e]);
-        }
-      }
-    }
-
     const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
     const double inv_n = 1.0 / (double)N;
-    double tprev = a.t0, tnext;
-    D invN = inv_population(y, c);
-    rhs(a.t0, y, f[0], c, invN);  // FSAL f0 (solver.init)
-
-    if (a.const_dt > 0.0) {
-      tnext = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
-    } else {
-      // Hairer-Wanner initial step (PIDController._select_initial_step)
-      double p0 = 0.0, p1 = 0.0;
-      double scale[NE];
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        scale[e] = fma(fabs(y[e].v), rtol, atol);
-        const double w = (e == 0 && !lead) ? 0.0 : 1.0;
-        p0 += w * sq(y[e].v / scale[e]);
-        p1 += w * sq(f[0][e].v / scale[e]);
-      }
-      const double d0 = sqrt(traj_sum(p0, c) * inv_n);
-      const double d1 = sqrt(traj_sum(p1, c) * inv_n);
-      const bool small = (d0 < 1e-5) || (d1 < 1e-5);
-      const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
-#pragma unroll
-      for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, f[0][e], y[e]);
-      rhs(a.t0 + h0, ys, f[1], c, invN);
-      double p2 = 0.0;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const double w = (e == 0 && !lead) ? 0.0 : 1.0;
-        p2 += w * sq((f[1][e].v - f[0][e].v) / scale[e]);
-      }
-      const double d2 = sqrt(traj_sum(p2, c) * inv_n) / h0;
-      const double md = fmax(d1, d2);
-      const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
-      tnext = a.t0 + fmin(100.0 * h0, h1);
-    }
-    tnext = fmin(tnext, t1);
-
-    int32_t n_acc = 0, n_rej = 0, n_steps = 0;
-    int32_t save_i = 0;
-    bool active = valid && (tprev < t1) && (n_steps < a.max_steps);
-
-    // fused log-likelihood state
-    D lp_acc = make_dual<P>(0.0), obs_prev = make_dual<P>(0.0);
     const int obs_m = (a.obs_comp == 0) ? G : G * S;
     const int obs_q = (a.obs_comp == 0) ? c.g : c.g * S + c.s;
     const bool obs_owner = (a.obs_comp != 0) || lead;
 
-    while (__any_sync(0xffffffffu, active)) {
+    // ---- per-slot state (registers)
+    Prm prm;
+    D y[NE], f[7][NE], ys[NE];
+    int64_t traj = chunk_begin;  // trajectory of my slot (valid index even while idle)
+    double tprev = t1, tnext = t1;
+    int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
+    bool active = false;
+    double* out_s = a.ys;  // running output pointers of the full-save fast path
+    double* out_c = a.ys;
+    D lp_acc = make_dual<P>(0.0), obs_prev = make_dual<P>(0.0);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      y[e] = make_dual<P>(1.0);
+      f[0][e] = make_dual<P>(0.0);
+    }
+    prm.beta = prm.gamma = prm.sigma = prm.omega = prm.amp = prm.phase = make_dual<P>(0.0);
+    prm.period = 1.0;
+
+    bool had_traj = false;
+    // ================= refill idle slots from the warp's chunk =================
+    auto refill = [&]() {
+      {
+        const unsigned idle_heads = __ballot_sync(0xffffffffu, head && !active);
+        const int n_idle = __popc(idle_heads);
+        const bool any_active = __any_sync(0xffffffffu, active);
+        if (next < chunk_end && n_idle > 0 && (n_idle >= REFILL || !any_active)) {
+          const int rank = __popc(idle_heads & ((1u << c.base) - 1u));  // idle slots below mine
+          const int64_t cand = next + rank;
+          const bool take = slot_ok && !active && cand < chunk_end;
+          next = (next + n_idle < chunk_end) ? next + n_idle : chunk_end;
+          const int64_t tr = take ? cand : traj;
+          // ---- parameters and initial state of the new trajectory (masked lanes shadow their old one)
+          auto ld = [&](const DynodeArray& arr, int k, double dflt) -> double {
+            return arr.ptr ? __ldg(arr.ptr + tr * arr.batch_stride + k) : dflt;
+          };
+          Prm pn;
+          pn.beta = make_dual<P>(ld(a.prm.beta, c.s, 0.0));
+          pn.gamma = make_dual<P>(ld(a.prm.gamma, c.s, 0.0));
+          pn.sigma = make_dual<P>(HAS_E ? ld(a.prm.sigma, c.s, 0.0) : 0.0);
+          pn.omega = make_dual<P>(WANING ? ld(a.prm.omega, c.s, 0.0) : 0.0);
+          pn.amp = make_dual<P>(SEASONAL ? ld(a.prm.season_amp, 0, 0.0) : 0.0);
+          pn.phase = make_dual<P>(SEASONAL ? ld(a.prm.season_phase, 0, 0.0) : 0.0);
+          pn.period = SEASONAL ? ld(a.prm.season_period, 0, 1.0) : 1.0;
+          if constexpr (P > 0) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+              const int w = a.wrt[k];
+              if (w >= 0 && (w & 15) == c.s) {
+                const int kind = w >> 4;
+                if (kind == DYNODE_P_BETA) pn.beta.d[k] = 1.0;
+                if (kind == DYNODE_P_GAMMA) pn.gamma.d[k] = 1.0;
+                if (kind == DYNODE_P_SIGMA) pn.sigma.d[k] = 1.0;
+                if (kind == DYNODE_P_OMEGA) pn.omega.d[k] = 1.0;
+              }
+              if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_AMP) pn.amp.d[k] = 1.0;
+              if (w >= 0 && (w >> 4) == DYNODE_P_SEASON_PHASE) pn.phase.d[k] = 1.0;
+            }
+          }
+          D yn[NE], fn[NE], f1[NE];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            yn[e] = make_dual<P>(__ldg(a.y0.ptr + tr * a.y0.batch_stride + off_full[e]));
+            if constexpr (P > 0) {
+              if (a.dy0) {
+#pragma unroll
+                for (int k = 0; k < P; ++k)
+                  if (a.p0 + k < a.P_total)
+                    yn[e].d[k] = __ldg(a.dy0 + ((tr * a.P_total + a.p0 + k) * (int64_t)N) + off_full[e]);
+              }
+            }
+          }
+          const D invN0 = inv_population(yn, c);
+          rhs(a.t0, yn, fn, c, pn, invN0);  // FSAL f0 (solver.init)
+          double tn;
+          if (a.const_dt > 0.0) {
+            tn = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
+          } else {
+            // Hairer-Wanner initial step (PIDController._select_initial_step)
+            double p0 = 0.0, p1 = 0.0;
+            double scale[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              scale[e] = fma(fabs(yn[e].v), rtol, atol);
+              const double w = (e == 0 && !lead) ? 0.0 : 1.0;
+              p0 += w * sq(yn[e].v / scale[e]);
+              p1 += w * sq(fn[e].v / scale[e]);
+            }
+            const double d0 = sqrt(traj_sum(p0, c) * inv_n);
+            const double d1 = sqrt(traj_sum(p1, c) * inv_n);
+            const bool small = (d0 < 1e-5) || (d1 < 1e-5);
+            const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, fn[e], yn[e]);
+            rhs(a.t0 + h0, ys, f1, c, pn, invN0);
+            double p2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              const double w = (e == 0 && !lead) ? 0.0 : 1.0;
+              p2 += w * sq((f1[e].v - fn[e].v) / scale[e]);
+            }
+            const double d2 = sqrt(traj_sum(p2, c) * inv_n) / h0;
+            const double md = fmax(d1, d2);
+            const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
+            tn = a.t0 + fmin(100.0 * h0, h1);
+          }
+          if (take) {
+            prm = pn;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) { y[e] = yn[e]; f[0][e] = fn[e]; }
+            traj = cand;
+            tprev = a.t0;
+            tnext = fmin(tn, t1);
+            n_acc = n_rej = n_steps = 0;
+            save_i = 0;
+            out_s = a.ys + cand * (int64_t)a.T * N + c.g;
+            out_c = a.ys + cand * (int64_t)a.T * N + G + c.g * S + c.s;
+            lp_acc = make_dual<P>(0.0);
+            obs_prev = make_dual<P>(0.0);
+            active = true;
+            had_traj = true;
+          }
+        }
+      }
+    };
+    // ================= retire slots whose trajectory is complete (or ran out of steps) ==========
+    auto retire = [&](bool fin) {
+      if (__any_sync(0xffffffffu, fin)) {
+        if constexpr (MODE == MODE_SAVE) {
+          if (fin && a.write_primal) {
+            // slots never reached keep diffrax's +inf fill
+            for (int k = save_i; k < a.T; ++k) {
+              const int64_t row = (traj * a.T + k) * (int64_t)n_saved;
+#pragma unroll
+              for (int e = 0; e < NE; ++e)
+                if (off_save[e] >= 0) a.ys[row + off_save[e]] = CUDART_INF;
+            }
+          }
+        } else {
+          const double tot = traj_sum(obs_owner ? lp_acc.v : 0.0, c);
+          if (fin && q == 0 && a.write_primal) a.lp[traj] = tot + a.lp_const;
+          if constexpr (P > 0) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+              const double gp = traj_sum(obs_owner ? lp_acc.d[k] : 0.0, c);
+              if (fin && q == 0 && a.p0 + k < a.P_total) a.grad[traj * a.P_total + a.p0 + k] = gp;
+            }
+          }
+        }
+        if (fin && q == 0 && a.write_primal) {
+          int32_t* st = a.stats + traj * 4;
+          st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
+          st[DYNODE_STAT_ACCEPTED] = n_acc;
+          st[DYNODE_STAT_REJECTED] = n_rej;
+          st[DYNODE_STAT_STEPS] = n_steps;
+        }
+        if (fin) {
+          active = false;
+          tprev = tnext = t1;  // idle slots step with h = 0 (harmless) until refilled
+        }
+      }
+    };
+
+    if constexpr (!PERSIST) refill();  // one generation: every slot takes its trajectory up front
+    while (true) {
+      if constexpr (PERSIST) refill();
+      // a new trajectory whose horizon is empty (t0 == t1) or max_steps == 0 finishes in the commit
+      // block below after one masked pass; nothing to do when no slot is active
+      if (!__any_sync(0xffffffffu, active)) break;
+      const bool stepping = active && (tprev < t1) && (n_steps < a.max_steps);
+
       const double h = tnext - tprev;
-      invN = inv_population(y, c);
+      const D invN = inv_population(y, c);
       // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, T5_a21 * f[0][e], y[e]);
-      rhs(fma(T5_c2, h, tprev), ys, f[1], c, invN);
+      rhs(fma(T5_c2, h, tprev), ys, f[1], c, prm, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(T5_a32, f[1][e], T5_a31 * f[0][e]), y[e]);
-      rhs(fma(T5_c3, h, tprev), ys, f[2], c, invN);
+      rhs(fma(T5_c3, h, tprev), ys, f[2], c, prm, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a43, f[2][e], dfma(T5_a42, f[1][e], T5_a41 * f[0][e])), y[e]);
-      rhs(fma(T5_c4, h, tprev), ys, f[3], c, invN);
+      rhs(fma(T5_c4, h, tprev), ys, f[3], c, prm, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a54, f[3][e], dfma(T5_a53, f[2][e], dfma(T5_a52, f[1][e], T5_a51 * f[0][e]))), y[e]);
-      rhs(fma(T5_c5, h, tprev), ys, f[4], c, invN);
+      rhs(fma(T5_c5, h, tprev), ys, f[4], c, prm, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a65, f[4][e], dfma(T5_a64, f[3][e], dfma(T5_a63, f[2][e],
                      dfma(T5_a62, f[1][e], T5_a61 * f[0][e])))), y[e]);
-      rhs(tnext, ys, f[5], c, invN);
+      rhs(tnext, ys, f[5], c, prm, invN);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a76, f[5][e], dfma(T5_a75, f[4][e], dfma(T5_a74, f[3][e], dfma(T5_a73, f[2][e],
                      dfma(T5_a72, f[1][e], T5_a71 * f[0][e]))))), y[e]);
-      rhs(tnext, ys, f[6], c, invN);  // ys is y1
+      rhs(tnext, ys, f[6], c, prm, invN);  // ys is y1
 
       // ---- dense-output coefficients, formed unconditionally right after the last stage so their
       // independent FMAs overlap the latency-bound error-norm / controller chain below.
@@ -377,7 +477,7 @@ struct LaneSolver {
       if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);  // _clip_to_end
 
       // ---- SaveAt(ts): dense output over [tprev, tnext] for every ts[k] <= tnext
-      const bool do_save = active && keep;
+      const bool do_save = stepping && keep;
       double ts_next = do_save ? save_time(save_i) : CUDART_INF;
       if (__any_sync(0xffffffffu, ts_next <= tnext)) {
         const double inv_h = rcp_fast((tnext == tprev) ? 1.0 : h);
@@ -421,8 +521,8 @@ struct LaneSolver {
                     if (a.write_primal) a.ys[row + off_save[e]] = v.v;
                     if constexpr (P > 0) {
 #pragma unroll
-                      for (int p = 0; p < P; ++p)
-                        if (a.p0 + p < a.P_total) a.dys[(row + off_save[e]) * a.P_total + a.p0 + p] = v.d[p];
+                      for (int k = 0; k < P; ++k)
+                        if (a.p0 + k < a.P_total) a.dys[(row + off_save[e]) * a.P_total + a.p0 + k] = v.d[k];
                     }
                   }
                 }
@@ -453,7 +553,7 @@ struct LaneSolver {
       }
 
       // ---- commit
-      if (active) {
+      if (stepping) {
         ++n_steps;
         if (keep) {
           ++n_acc;
@@ -464,40 +564,15 @@ struct LaneSolver {
         }
         tprev = ntprev;
         tnext = ntnext;
-        active = (tprev < t1) && (n_steps < a.max_steps);
+      }
+      const bool done = !((tprev < t1) && (n_steps < a.max_steps));
+      if constexpr (PERSIST) {
+        retire(active && done);
+      } else {
+        active = active && !done;
       }
     }
-
-    // ---- epilogue
-    if constexpr (MODE == MODE_SAVE) {
-      if (valid && a.write_primal) {
-        // slots never reached keep diffrax's +inf fill
-        for (int k = save_i; k < a.T; ++k) {
-          const int64_t row = (traj * a.T + k) * (int64_t)n_saved;
-#pragma unroll
-          for (int e = 0; e < NE; ++e)
-            if (off_save[e] >= 0) a.ys[row + off_save[e]] = CUDART_INF;
-        }
-      }
-    } else {
-      if (!obs_owner) lp_acc = make_dual<P>(0.0);
-      const double tot = traj_sum(lp_acc.v, c);
-      if (valid && q == 0 && a.write_primal) a.lp[traj] = tot + a.lp_const;
-      if constexpr (P > 0) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const double gp = traj_sum(lp_acc.d[p], c);
-          if (valid && q == 0 && a.p0 + p < a.P_total) a.grad[traj * a.P_total + a.p0 + p] = gp;
-        }
-      }
-    }
-    if (valid && q == 0 && a.write_primal) {
-      int32_t* st = a.stats + traj * 4;
-      st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
-      st[DYNODE_STAT_ACCEPTED] = n_acc;
-      st[DYNODE_STAT_REJECTED] = n_rej;
-      st[DYNODE_STAT_STEPS] = n_steps;
-    }
+    if constexpr (!PERSIST) retire(had_traj);
   }
 };
 
@@ -513,31 +588,40 @@ constexpr int min_blocks(int flow, int p) {
 #endif
 }
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
-#ifdef DYN_MAXNREG
-__global__ void __maxnreg__(DYN_MAXNREG) lane_solver_kernel(const SolveArgs a) {
-#else
 __global__ void __launch_bounds__(kThreads, min_blocks(FLOW, P)) lane_solver_kernel(const SolveArgs a) {
-#endif
   LaneSolver<FLOW, FLAGS, G, S, P, MODE>::run(a);
 }
 
-// Host launcher: one warp integrates 32/(G*S) trajectories; the grid covers the ensemble.
+// Host launcher.  The grid is sized to the number of warps the GPU keeps resident (occupancy x SMs,
+// times a small oversubscription that evens out the tail); every warp integrates a contiguous
+// chunk of ceil(B / warps) trajectories through its 32/(G*S) slots.
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
-cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream) {
-  constexpr int TPW = LaneSolver<FLOW, FLAGS, G, S, P, MODE>::TPW;
-  constexpr int per_cta = TPW * (kThreads / 32);
-  const int64_t grid = (a.B + per_cta - 1) / per_cta;
-  if (grid <= 0) return cudaSuccess;
-  size_t smem = 0;
-#ifdef DYN_TUNING
-  // tuning only: cap resident CTAs per SM by reserving dynamic shared memory (DYN_SMEM_PAD bytes)
-  if (const char* e = getenv("DYN_SMEM_PAD")) {
-    smem = (size_t)atol(e);
-    cudaFuncSetAttribute(lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_lane_solver(const SolveArgs& a_in, cudaStream_t stream) {
+  using LS = LaneSolver<FLOW, FLAGS, G, S, P, MODE>;
+  auto kern = lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE>;
+  if (a_in.B <= 0) return cudaSuccess;
+  static thread_local int cached_dev = -1, cached_warps = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev != cached_dev) {
+    int sms = 0, per_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0)) != cudaSuccess) return e;
+    cached_warps = sms * (per_sm > 0 ? per_sm : 1) * (kThreads / 32);
+    cached_dev = dev;
   }
-#endif
-  lane_solver_kernel<FLOW, FLAGS, G, S, P, MODE><<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  constexpr int wpc = kThreads / 32;
+  SolveArgs a = a_in;
+  // non-persistent instances: one generation per warp (chunk = TPW)
+  int64_t warps = LS::PERSIST ? (int64_t)cached_warps * kOversubscribe : (int64_t)1 << 40;
+  const int64_t min_chunk = LS::TPW;                               // at least one trajectory per slot
+  const int64_t max_warps = (a.B + min_chunk - 1) / min_chunk;
+  if (warps > max_warps) warps = max_warps;
+  a.chunk = (a.B + warps - 1) / warps;
+  warps = (a.B + a.chunk - 1) / a.chunk;
+  const int64_t grid = (warps + wpc - 1) / wpc;
+  kern<<<(unsigned)grid, kThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -18,8 +18,14 @@ constexpr int kThreads = DYN_THREADS;  // warps per CTA = kThreads / 32
 constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
 constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
 
+#ifndef DYN_OVERSUBSCRIBE
+#define DYN_OVERSUBSCRIBE 1
+#endif
+constexpr int kOversubscribe = DYN_OVERSUBSCRIBE;  // grid = resident warps x this
+
 struct SolveArgs {
   int64_t B;
+  int64_t chunk;  // trajectories per warp (contiguous); set by the launcher
   DynodeArray y0;
   DynodeParams prm;
   const double* save_ts;
