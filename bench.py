@@ -103,18 +103,23 @@ def make_inputs(workload: str, B: int, seed: int):
     return make_case(WORKLOADS[workload][0], B, seed=seed)
 
 
-def cpu_oracle_leg(workload: str, sample_chunks: int, chunk: int, seed: int):
-    """Time the CPU oracle (all host threads) on sample_chunks x chunk draws of the workload."""
+def cpu_oracle_leg(workload: str, min_seconds: float, chunk: int, seed: int):
+    """Time the CPU oracle (all host threads) on chunk-sized pieces of the workload until
+    `min_seconds` of CPU wall time have been spent (the bounded sample of the cpu_baseline leg)."""
     from oracle import oracle as orc
     case = make_inputs(workload, chunk, seed)
     fam, dims, theta, shared = case["oracle"]
     orc.solve(fam, dims, case["y0"][:256] if np.ndim(case["y0"]) == 2 else case["y0"], theta[:256], shared,
               t1=case["t1"])  # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    for _ in range(sample_chunks):
+    sample_chunks = 0
+    while True:
         orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
-    dt = time.perf_counter() - t0
-    return sample_chunks * chunk / dt, orc.num_threads(), dt
+        sample_chunks += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return sample_chunks * chunk / dt, orc.num_threads(), dt, sample_chunks
 
 
 def run_reference(args):
@@ -245,9 +250,13 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    traffic = None
+    # DRAM traffic per launch from the committed `ncu --set full` capture (per trajectory x B)
+    traffic = traffic_src = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr:
+            traffic = tr["bytes_per_trajectory"] * B
+            traffic_src = tr["source"]
     except Exception:
         pass
     ach_gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
@@ -308,8 +317,7 @@ def run_ours(args):
     # ---- CPU baseline on rank 0, N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        chunks = args.cpu_chunks
-        v, cores, dt = cpu_oracle_leg(args.workload, chunks, 8192, 20260101)
+        v, cores, dt, chunks = cpu_oracle_leg(args.workload, args.cpu_seconds, 8192, 20260101)
         cpu = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
                "sample": f"{chunks}x8192 draws of the same workload ({dt:.1f} s wall), C++ oracle + OpenMP"}
 
@@ -327,7 +335,8 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": "dynode::lane_solver_kernel", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": bytes_alg, "hbm_write_probe_gbs": hbm_write_gbs},
             "roofline_fp64": {"bound": "fp64_fma", "achieved": ach_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
@@ -351,7 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override draws per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--host-chunk", type=int, default=8192)
-    ap.add_argument("--cpu-chunks", type=int, default=12)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU wall time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
