@@ -38,7 +38,8 @@ def instance_ids():
 
 
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "dynode_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "xla_ffi_shim.cc"]
+    deps.append(os.path.join(INCLUDE, "dynode_b200.h"))
     return deps
 
 
@@ -84,6 +85,24 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, ext
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return out
+
+
+XLA_LIB = os.path.join(HERE, "libdynode_b200_xla.so")
+
+
+def build_xla_shim() -> str:
+    """Compile csrc/xla_ffi_shim.cc (typed XLA-FFI handlers over the C ABI) where jaxlib's FFI headers
+    exist.  Raises ImportError in images without jax (this one): the ctypes path is used instead."""
+    import jax.ffi  # noqa: F401  (absent in this image)
+
+    build()
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", jax.ffi.include_dir(),
+           os.path.join(CSRC, "xla_ffi_shim.cc"), "-o", XLA_LIB, "-L", HERE, "-ldynode_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"xla shim build failed:\n{r.stdout}\n{r.stderr}")
+    return XLA_LIB
 
 
 if __name__ == "__main__":

@@ -166,6 +166,10 @@ def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opt
     torch = b.torch
     mask = model.full_mask() if save_mask is None else int(save_mask)
     ns = model.saved_size(mask)
+    if out is not None:
+        if (out.dtype != torch.float64 or not out.is_cuda or not out.is_contiguous()
+                or out.numel() != b.B * b.T * ns):
+            raise ValueError(f"out must be a contiguous float64 CUDA tensor of {b.B}x{b.T}x{ns} values")
     ys = out if out is not None else torch.empty((b.B, b.T, ns), dtype=torch.float64, device=b.dev)
     stats = stats_out if stats_out is not None else torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
     L = _lib.load()

@@ -229,9 +229,10 @@ def simulate_ensemble(
 
 def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices, save_step,
          *, batch_size, state_batched, throw, out=None, host_chunk=8192) -> Solution:
-    _lib.require_cuda()
+    # unsupported ODEs / solver options fail loudly before anything touches the device
     spec, model, params, contact = _resolve(ode, initial_state, ode_parameters, batch_size, state_batched)
     opts = _solver_options(solver_parameters, duration_days)
+    _lib.require_cuda()
     saveat = build_saveat(opts.t0, duration_days, save_step, sub_save_indices)
     mask = _mask_from(saveat.indices, model.n_compartments)
     B = 1 if batch_size is None else batch_size
@@ -249,7 +250,9 @@ def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, s
     cuda = torch.device("cuda", torch.cuda.current_device())
 
     if out_dev.type == "cuda" or not ensemble or B <= host_chunk:
-        ys, _, stats = engine.solve_ensemble(model, y0, params, contact, opts, saveat.times, mask, B=B)
+        dev_out = out if (out is not None and out.is_cuda) else None  # e.g. a slice of a gather buffer
+        ys, _, stats = engine.solve_ensemble(model, y0, params, contact, opts, saveat.times, mask, B=B,
+                                             out=dev_out)
         if out_dev.type != "cuda":
             if out is not None:
                 out.copy_(ys)

@@ -1,0 +1,112 @@
+"""Host-side contract of `simulate` (reference src/dynode/simulation/odes.py:35-198) that needs no GPU:
+validation order and messages, the save grid, flow registration, and that the product path refuses to
+run without the CUDA engine (no CPU fallback)."""
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import pytest
+import torch
+
+from dynode_b200 import DynodeError
+from dynode_b200.config import SolverParams
+from dynode_b200.examples import rhs as ex
+from dynode_b200.flows import UnsupportedODEError, flow_family, flow_spec_of
+from dynode_b200.simulation import AbstractODEParams, build_saveat, simulate, simulate_ensemble
+
+Y0 = (torch.tensor([99.0]), torch.tensor([1.0]), torch.tensor([0.0]))
+P = ex.DensitySIR_ODEParams(beta=0.003, gamma=0.1)
+
+
+@pytest.mark.parametrize("stop,step,count", [(100, 1, 101), (100, 2, 51), (100, 3, 34), (100, 7, 15),
+                                             (300.0, 1, 301), (150, 0, 151), (150, -4, 151)])
+def test_build_saveat_is_the_reference_linspace(stop, step, count):
+    # reference tests/test_simulation/test_odes.py:77-92 pins the count; odes.py:177-179 the rule
+    sa = build_saveat(0.0, stop, step)
+    assert len(sa.times) == count and sa.times[0] == 0.0 and sa.times[-1] == stop
+    assert np.array_equal(sa.times, np.linspace(0.0, stop, count))
+    assert sa.indices is None
+    sub = build_saveat(0.0, stop, step, (0, 2))
+    assert sub.indices == (0, 2) and np.array_equal(sub.times, sa.times)
+
+
+def test_numpy_compartments_raise_type_error_first():
+    # odes.py:93-98
+    with pytest.raises(TypeError):
+        simulate(ex.sir_density_ode, 100, (np.array([99.0]), np.array([1.0]), np.array([0.0])), P, SolverParams())
+
+
+def test_wrong_parameter_type_raises_assertion():
+    # odes.py:100-106
+    with pytest.raises(AssertionError):
+        simulate(ex.sir_density_ode, 100, Y0, ex.SIR_ODEParams(beta=0.3, gamma=0.1), SolverParams())
+    with pytest.raises(AssertionError):
+        simulate(ex.sir_density_ode, "100", Y0, P, SolverParams())
+
+
+def test_unregistered_ode_fails_loudly():
+    @dataclass
+    class MyParams(AbstractODEParams):
+        k: Any
+
+    def my_ode(t: float, state, p: MyParams):
+        return tuple(-p.k * c for c in state)
+
+    with pytest.raises(UnsupportedODEError, match="no CPU fallback"):
+        simulate(my_ode, 10, Y0, MyParams(k=1.0), SolverParams())
+    with pytest.raises(UnsupportedODEError):
+        flow_spec_of(my_ode)
+
+
+def test_model_outside_compiled_instances_fails_loudly():
+    # 5 age groups x 7 strains is not in csrc/instances.def
+    p = ex.SEIRS_MultiStrain_ODEParams(beta=torch.ones(7), gamma=torch.ones(7), sigma=torch.ones(7),
+                                       omega=torch.ones(7), contact_matrix=torch.eye(5))
+    state = (torch.ones(5),) + tuple(torch.zeros(5, 7) for _ in range(4))
+    with pytest.raises(UnsupportedODEError, match="not compiled in"):
+        simulate(ex.seirs_multi_strain_ode, 10, state, p, SolverParams())
+    with pytest.raises(UnsupportedODEError):  # wrong number of compartments for the flow
+        simulate(ex.seirs_multi_strain_ode, 10, state[:3], p, SolverParams())
+
+
+def test_unsupported_solver_options_fail_loudly():
+    from dynode_b200.config.params import AbstractSolver
+
+    class Dopri5(AbstractSolver):
+        pass
+
+    with pytest.raises(UnsupportedODEError, match="Dopri5"):
+        simulate(ex.sir_density_ode, 10, Y0, P, SolverParams(solver_method=Dopri5()))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a box without a GPU")
+def test_no_cpu_fallback_without_cuda():
+    with pytest.raises(DynodeError, match="no CPU fallback"):
+        simulate(ex.sir_density_ode, 10, Y0, P, SolverParams())
+    with pytest.raises(DynodeError, match="no CPU fallback"):
+        simulate_ensemble(ex.sir_density_ode, 10, Y0, P, SolverParams(), batch_size=4)
+
+
+def test_flow_registration_records_the_parameter_map():
+    spec = flow_spec_of(ex.seirs_ode_seasonal)
+    assert spec.flow == "seirs" and spec.seasonal and not spec.density_dependent
+    assert spec.fields["season_amp"] == "seasonality_params.forcing_amp"
+    assert spec.compartments == ("s", "e", "i", "r")
+    assert flow_spec_of(ex.sir_age_risk_ode).contact_layout == "source_target"
+    assert flow_spec_of(ex.seirs_multi_strain_ode).compartments == ("s", "e", "i", "r", "c")
+    with pytest.raises(ValueError):
+        flow_family("seir")
+    with pytest.raises(ValueError):
+        flow_family("sir", contact_layout="diag")
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dynode_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "libdynode_oracle" not in txt, f
