@@ -135,10 +135,11 @@ class _Bound:
         # host grids are checked for build_saveat's uniform pattern (lets the kernel skip the loads);
         # device-resident grids carry the hint from the caller (attribute `dynode_save_dt`)
         self.save_dt = getattr(save_ts, "dynode_save_dt", 0.0)
-        if opts is not None and not hasattr(save_ts, "dynode_save_dt"):
+        on_device = isinstance(save_ts, torch.Tensor) and save_ts.is_cuda
+        if opts is not None and not hasattr(save_ts, "dynode_save_dt") and not on_device:
             self.save_dt = uniform_save_dt(save_ts, float(opts.t0), float(opts.t1))
         key = None
-        if self.save_dt > 0.0:  # uniform host grid: keep one device copy per (device, grid)
+        if self.save_dt > 0.0 and not on_device:  # uniform host grid: one device copy per (device, grid)
             key = (dev.index, len(save_ts), float(save_ts[0]), float(save_ts[-1]), self.save_dt)
         if key is not None and key in _GRID_CACHE:
             self.save_ts = _GRID_CACHE[key]

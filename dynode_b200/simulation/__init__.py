@@ -7,4 +7,5 @@ from .odes import (  # noqa: F401
     build_saveat,
     simulate,
     simulate_ensemble,
+    simulate_incidence_loglik,
 )

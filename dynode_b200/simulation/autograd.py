@@ -1,0 +1,308 @@
+"""Differentiable, vmappable entry to the ensemble kernels.
+
+In the reference, gradients reach NUTS by JAX reverse-mode AD through `diffeqsolve`
+(RecursiveCheckpointAdjoint) and batching comes from `jax.vmap`.  Here the solve is a
+`torch.autograd.Function` whose
+
+  * forward makes ONE launch of the CUDA kernel for the whole batch, carrying forward sensitivities of the
+    discrete scheme (`dynode_solve_sens_f64`) for exactly the inputs that require grad;
+  * backward contracts the stored sensitivities with the incoming cotangent;
+  * vmap rule folds the vmapped axis into the ensemble axis, so a per-draw model vmapped over 1024 chains is
+    still one launch (the role of `vmap_method="broadcast_all"` in the XLA-FFI binding).
+
+`PoissonLoglik` is the fused variant for the NUTS hot loop: solve + Poisson-incidence log-likelihood +
+gradient in one launch, nothing but lp/grad written (`dynode_poisson_loglik_grad_f64`).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib, engine
+
+_KINDS = ("beta", "gamma", "sigma", "omega", "season_amp", "season_phase")
+_KIND_ID = {"beta": _lib.P_BETA, "gamma": _lib.P_GAMMA, "sigma": _lib.P_SIGMA, "omega": _lib.P_OMEGA,
+            "season_amp": _lib.P_SEASON_AMP, "season_phase": _lib.P_SEASON_PHASE}
+
+
+def unwrap(t):
+    """Peel functorch wrappers (vmap / grad levels) off a tensor."""
+    fc = torch._C._functorch
+    while isinstance(t, torch.Tensor) and (fc.is_batchedtensor(t) or fc.is_gradtrackingtensor(t)):
+        t = fc.get_unwrapped(t)
+    return t
+
+
+def is_transformed(t) -> bool:
+    fc = torch._C._functorch
+    return isinstance(t, torch.Tensor) and (fc.is_batchedtensor(t) or fc.is_gradtrackingtensor(t))
+
+
+def needs_grad(t) -> bool:
+    if not isinstance(t, torch.Tensor) or not torch.is_grad_enabled():
+        return False
+    if torch._C._functorch.is_gradtrackingtensor(t):
+        return True
+    return bool(unwrap(t).requires_grad)
+
+
+@dataclass(frozen=True)
+class SolveConfig:
+    """Static (non-tensor) part of a solve: hashable, shared by forward / backward / the vmap rule."""
+
+    model: engine.FlowModel
+    opts_key: Tuple  # (t0, t1, rtol, atol, const_dt, max_steps)
+    layout: Tuple[Tuple[str, int, int], ...]  # (kind, first column in theta, width)
+    wrt_cols: Tuple[int, ...]  # theta columns that carry a tangent direction
+    y0_grad: bool
+    mask: int
+    n_saved: int
+    T: int
+    # identity-compared payload (device tensors / arrays) lives outside the hash
+    payload: "SolvePayload" = None
+
+    def opts(self) -> engine.SolverOptions:
+        t0, t1, rtol, atol, const_dt, max_steps = self.opts_key
+        return engine.SolverOptions(t1=t1, t0=t0, rtol=rtol, atol=atol, const_dt=const_dt, max_steps=max_steps)
+
+    def wrt_ids(self):
+        ids = []
+        for col in self.wrt_cols:
+            for kind, first, width in self.layout:
+                if first <= col < first + width:
+                    strain = col - first if kind in ("beta", "gamma", "sigma", "omega") else 0
+                    ids.append(_lib.wrt_id(_KIND_ID[kind], strain))
+        return ids + [-1] * (self.model.state_size if self.y0_grad else 0)
+
+
+class SolvePayload:
+    """Shared device tensors of a solve (contact matrix, save grid, observations, period)."""
+
+    def __init__(self, contact=None, save_ts=None, period=None, obs=None, obs_comp: int = -1,
+                 lp_const: float = 0.0):
+        self.contact, self.save_ts, self.period = contact, save_ts, period
+        self.obs, self.obs_comp, self.lp_const = obs, obs_comp, lp_const
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+
+def _kernel_params(cfg: SolveConfig, theta: torch.Tensor):
+    p = {}
+    for kind, first, width in cfg.layout:
+        p[kind] = theta[:, first:first + width].contiguous()
+    if cfg.payload.period is not None:
+        p["season_period"] = cfg.payload.period
+    return p
+
+
+def _seeds(cfg: SolveConfig, B: int, device):
+    """dy0 [B][P][n]: zero for parameter directions, identity for the initial-state directions."""
+    if not cfg.y0_grad:
+        return None
+    n, pw = cfg.model.state_size, len(cfg.wrt_cols)
+    d = torch.zeros((B, pw + n, n), dtype=torch.float64, device=device)
+    d[:, pw:, :] = torch.eye(n, dtype=torch.float64, device=device)
+    return d
+
+
+def _fold(x: Optional[torch.Tensor], dim, B: int):
+    """[.., vmapped axis at `dim`, ..] -> rows with the vmapped axis folded into the leading one."""
+    if x is None:
+        return None, 1
+    if dim is None:
+        return x, x.shape[0]
+    x = x.movedim(dim, 0)
+    inner = x.shape[1]
+    return x.reshape(B * inner, *x.shape[2:]), inner
+
+
+def _rows(y0: torch.Tensor, theta: torch.Tensor):
+    """Broadcast the batch axes of y0 / theta against each other (a shared row stays shared)."""
+    B = max(y0.shape[0], theta.shape[0])
+    if theta.shape[0] != B:
+        theta = theta.expand(B, theta.shape[1])
+    return B, y0.contiguous(), theta.contiguous()
+
+
+class EnsembleSolve(torch.autograd.Function):
+    """(y0 [B|1, n], theta [B|1, K]) -> (ys [B, T, n_saved], stats [B, 4])."""
+
+    @staticmethod
+    def forward(y0, theta, cfg: SolveConfig):
+        B, y0c, th = _rows(y0, theta)
+        if cfg.y0_grad and y0c.shape[0] != B:
+            y0c = y0c.expand(B, y0c.shape[1]).contiguous()
+        wrt = cfg.wrt_ids()
+        ys, dys, stats = engine.solve_ensemble(cfg.model, y0c, _kernel_params(cfg, th), cfg.payload.contact,
+                                               cfg.opts(), cfg.payload.save_ts, cfg.mask, wrt=wrt,
+                                               dy0=_seeds(cfg, B, th.device), B=B)
+        if dys is None:
+            dys = ys.new_empty((0,))
+        return ys, stats, dys
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        y0, theta, cfg = inputs
+        ctx.cfg = cfg
+        ctx.shapes = (y0.shape, theta.shape)
+        ctx.save_for_backward(output[2])
+        ctx.mark_non_differentiable(output[1], output[2])
+
+    @staticmethod
+    def backward(ctx, g_ys, _g_stats, _g_dys):
+        cfg = ctx.cfg
+        (dys,) = ctx.saved_tensors
+        y0_shape, th_shape = ctx.shapes
+        g_theta = g_y0 = None
+        if dys.numel() > 0:
+            # unreached slots hold +inf in ys and garbage in dys; a finite cotangent there is the caller's
+            # business (NUTS sees a non-finite potential and rejects), so no masking here
+            g = torch.einsum("btn,btnp->bp", g_ys, dys)
+            pw = len(cfg.wrt_cols)
+            if pw and ctx.needs_input_grad[1]:
+                g_theta = g.new_zeros((g.shape[0], th_shape[1]))
+                g_theta[:, list(cfg.wrt_cols)] = g[:, :pw]
+                if th_shape[0] == 1 and g.shape[0] > 1:
+                    g_theta = g_theta.sum(0, keepdim=True)
+            if cfg.y0_grad and ctx.needs_input_grad[0]:
+                g_y0 = g[:, pw:]
+                if y0_shape[0] == 1 and g.shape[0] > 1:
+                    g_y0 = g_y0.sum(0, keepdim=True)
+        return g_y0, g_theta, None
+
+    @staticmethod
+    def vmap(info, in_dims, y0, theta, cfg):
+        B = info.batch_size
+        y0f, i0 = _fold(y0, in_dims[0], B)
+        thf, i1 = _fold(theta, in_dims[1], B)
+        inner = max(i0, i1) if (in_dims[0] is not None or in_dims[1] is not None) else 1
+        if in_dims[0] is not None and in_dims[1] is not None and i0 != i1:
+            raise ValueError("vmapped y0 and theta must have the same inner batch size")
+        if in_dims[0] is None and in_dims[1] is not None and y0f.shape[0] not in (1, B * inner):
+            y0f = y0f.repeat(B, 1)
+        if in_dims[1] is None and in_dims[0] is not None and thf.shape[0] not in (1, B * inner):
+            thf = thf.repeat(B, 1)
+        ys, stats, dys = EnsembleSolve.apply(y0f, thf, cfg)
+        ys = ys.reshape(B, -1, *ys.shape[1:])
+        stats = stats.reshape(B, -1, 4)
+        dys = dys.reshape(B, -1, *dys.shape[1:]) if dys.numel() else dys.new_empty((B, 0))
+        return (ys, stats, dys), (0, 0, 0)
+
+
+class PoissonLoglik(torch.autograd.Function):
+    """(y0 [B|1, n], theta [B|1, K]) -> (lp [B], stats [B, 4]); gradient from the same launch."""
+
+    @staticmethod
+    def forward(y0, theta, cfg: SolveConfig):
+        B, y0c, th = _rows(y0, theta)
+        if cfg.y0_grad and y0c.shape[0] != B:
+            y0c = y0c.expand(B, y0c.shape[1]).contiguous()
+        pl = cfg.payload
+        lp, grad, stats = engine.poisson_loglik_grad(cfg.model, y0c, _kernel_params(cfg, th), pl.contact,
+                                                     cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs, pl.lp_const,
+                                                     wrt=cfg.wrt_ids(), dy0=_seeds(cfg, B, th.device), B=B)
+        if grad is None:
+            grad = lp.new_empty((0,))
+        return lp, stats, grad
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        y0, theta, cfg = inputs
+        ctx.cfg = cfg
+        ctx.shapes = (y0.shape, theta.shape)
+        ctx.save_for_backward(output[2])
+        ctx.mark_non_differentiable(output[1], output[2])
+
+    @staticmethod
+    def backward(ctx, g_lp, _g_stats, _g_grad):
+        cfg = ctx.cfg
+        (grad,) = ctx.saved_tensors
+        y0_shape, th_shape = ctx.shapes
+        g_theta = g_y0 = None
+        if grad.numel() > 0:
+            g = g_lp[:, None] * grad
+            pw = len(cfg.wrt_cols)
+            if pw and ctx.needs_input_grad[1]:
+                g_theta = g.new_zeros((g.shape[0], th_shape[1]))
+                g_theta[:, list(cfg.wrt_cols)] = g[:, :pw]
+                if th_shape[0] == 1 and g.shape[0] > 1:
+                    g_theta = g_theta.sum(0, keepdim=True)
+            if cfg.y0_grad and ctx.needs_input_grad[0]:
+                g_y0 = g[:, pw:]
+                if y0_shape[0] == 1 and g.shape[0] > 1:
+                    g_y0 = g_y0.sum(0, keepdim=True)
+        return g_y0, g_theta, None
+
+    @staticmethod
+    def vmap(info, in_dims, y0, theta, cfg):
+        B = info.batch_size
+        y0f, i0 = _fold(y0, in_dims[0], B)
+        thf, i1 = _fold(theta, in_dims[1], B)
+        inner = max(i0, i1) if (in_dims[0] is not None or in_dims[1] is not None) else 1
+        if in_dims[0] is None and in_dims[1] is not None and y0f.shape[0] not in (1, B * inner):
+            y0f = y0f.repeat(B, 1)
+        if in_dims[1] is None and in_dims[0] is not None and thf.shape[0] not in (1, B * inner):
+            thf = thf.repeat(B, 1)
+        lp, stats, grad = PoissonLoglik.apply(y0f, thf, cfg)
+        lp = lp.reshape(B, -1)
+        stats = stats.reshape(B, -1, 4)
+        grad = grad.reshape(B, -1, grad.shape[-1]) if grad.numel() else grad.new_empty((B, 0))
+        return (lp, stats, grad), (0, 0, 0)
+
+
+def pack_inputs(model: engine.FlowModel, params: dict, y0: torch.Tensor, batched: bool, device):
+    """Kernel parameter dict -> (y0 [B|1, n], theta [B|1, K], layout, wrt_cols, y0_grad, period).
+
+    `params[kind]` are per-draw tensors ([S] / scalar, or [B, S] when `batched`); functorch-wrapped and
+    grad-requiring tensors pass through torch.cat, so vmap and autograd see ordinary differentiable ops."""
+    S = model.n_strains
+    cols, layout, wrt_cols, first = [], [], [], 0
+    for kind in _KINDS:
+        v = params.get(kind)
+        if v is None:
+            continue
+        width = S if kind in ("beta", "gamma", "sigma", "omega") else 1
+        v = v.to(device=device, dtype=torch.float64) if (v.device != device or v.dtype != torch.float64) else v
+        v = v.reshape(-1, width) if batched else v.reshape(1, width) if v.numel() == width else v.reshape(-1, width)
+        cols.append(v)
+        layout.append((kind, first, width))
+        if needs_grad(v):
+            wrt_cols.extend(range(first, first + width))
+        first += width
+    B = max(c.shape[0] for c in cols)
+    cols = [c if c.shape[0] == B else c.expand(B, c.shape[1]) for c in cols]
+    theta = torch.cat(cols, dim=1)
+    period = params.get("season_period")
+    if period is not None:
+        period = unwrap(period).detach().to(device=device, dtype=torch.float64).reshape(-1, 1).contiguous()
+    y0 = y0.to(device=device, dtype=torch.float64) if (y0.device != device or y0.dtype != torch.float64) else y0
+    y0 = y0.reshape(-1, model.state_size)
+    return y0, theta, tuple(layout), tuple(wrt_cols), needs_grad(y0), period
+
+
+def opts_key(opts: engine.SolverOptions) -> Tuple:
+    return (float(opts.t0), float(opts.t1), float(opts.rtol), float(opts.atol), float(opts.const_dt),
+            int(opts.max_steps))
+
+
+_TS_CACHE = {}
+
+
+def device_grid(save_ts: np.ndarray, opts: engine.SolverOptions, device) -> torch.Tensor:
+    """Device copy of a host save grid, tagged with the uniform-grid hint the kernel uses."""
+    key = (device.index, len(save_ts), float(save_ts[0]), float(save_ts[-1]))
+    t = _TS_CACHE.get(key)
+    if t is None or not np.array_equal(t.host, save_ts):
+        t = torch.as_tensor(save_ts, dtype=torch.float64, device=device)
+        t.host = np.array(save_ts, copy=True)
+        t.dynode_save_dt = engine.uniform_save_dt(t.host, float(opts.t0), float(opts.t1))
+        _TS_CACHE[key] = t
+    return t

@@ -190,9 +190,94 @@ def simulate(
     compiled flow family, RuntimeError when `max_steps` is exceeded (diffrax throw=True).
     """
     _validate_call(ode, initial_state, ode_parameters, duration_days)
+    if _wants_autograd(ode, initial_state, ode_parameters):
+        return _run_differentiable(ode, duration_days, initial_state, ode_parameters, solver_parameters,
+                                   sub_save_indices, save_step)
     sol = _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,
                save_step, batch_size=None, state_batched=False, throw=True)
     return sol
+
+
+def _wants_autograd(ode, initial_state, ode_parameters) -> bool:
+    """True when the call sits inside torch.vmap / torch.func.grad or an input requires grad: the solve
+    then goes through the differentiable, vmappable Function (simulation/autograd.py) -- the role JAX
+    tracing plays for the reference (numpyro vmaps the model and differentiates through diffeqsolve)."""
+    from . import autograd as ag
+
+    spec = getattr(ode, "__dynode_flow__", None)
+    if spec is None:
+        return False
+    tensors = list(initial_state)
+    for path in list(spec.fields.values()):
+        try:
+            tensors.append(get_path(ode_parameters, path))
+        except AttributeError:
+            pass
+    return any(ag.is_transformed(t) or ag.needs_grad(t) for t in tensors if isinstance(t, torch.Tensor))
+
+
+def _differentiable_setup(ode, duration_days, initial_state, ode_parameters, solver_parameters,
+                          sub_save_indices, save_step, **payload_kw):
+    from . import autograd as ag
+
+    spec, model, params, contact = _resolve(ode, initial_state, ode_parameters, None, False)
+    opts = _solver_options(solver_parameters, duration_days)
+    _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    saveat = build_saveat(opts.t0, duration_days, save_step, sub_save_indices)
+    mask = _mask_from(saveat.indices, model.n_compartments)
+    y0 = torch.cat([c.reshape(-1).to(device=dev, dtype=torch.float64) for c in initial_state])
+    y0r, theta, layout, wrt_cols, y0_grad, period = ag.pack_inputs(model, params, y0, False, dev)
+    payload = ag.SolvePayload(contact=None if contact is None else ag.unwrap(contact).detach().to(dev),
+                              save_ts=ag.device_grid(saveat.times, opts, dev), period=period, **payload_kw)
+    cfg = ag.SolveConfig(model=model, opts_key=ag.opts_key(opts), layout=layout, wrt_cols=wrt_cols,
+                         y0_grad=y0_grad, mask=mask, n_saved=model.saved_size(mask), T=len(saveat.times),
+                         payload=payload)
+    return cfg, y0r, theta, saveat, opts
+
+
+def _run_differentiable(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,
+                        save_step) -> Solution:
+    """Per-draw solve that torch.vmap batches into one launch and autograd differentiates (forward
+    sensitivities of the frozen-step discrete scheme).  A trajectory that runs out of `max_steps` cannot
+    raise here (the launch is asynchronous and possibly vmapped): its unreached save slots stay +inf, which
+    makes any log-density built on them non-finite, and `Solution.result` carries the code."""
+    from . import autograd as ag
+
+    cfg, y0r, theta, saveat, opts = _differentiable_setup(ode, duration_days, initial_state, ode_parameters,
+                                                          solver_parameters, sub_save_indices, save_step)
+    ys, stats, _ = ag.EnsembleSolve.apply(y0r, theta, cfg)
+    shapes = [tuple(c.shape) for c in initial_state]
+    T = cfg.T
+    st = stats[0]
+    stats_d = {"num_steps": st[_lib.STAT_STEPS], "num_accepted_steps": st[_lib.STAT_ACCEPTED],
+               "num_rejected_steps": st[_lib.STAT_REJECTED], "max_steps": int(solver_parameters.max_steps)}
+    return Solution(t0=opts.t0, t1=opts.t1, ts=cfg.payload.save_ts,
+                    ys=_split_ys(ys[0], cfg.model, cfg.mask, shapes, (T,)), stats=stats_d,
+                    result=st[_lib.STAT_RESULT])
+
+
+def simulate_incidence_loglik(ode, duration_days, initial_state, ode_parameters, solver_parameters, *,
+                              compartment: int, obs, save_step: int = 1):
+    """Fused NUTS hot path: log-likelihood of `obs` under
+    `Poisson(max(diff(ys[compartment], axis=0), 1e-6))` (the observation model of reference
+    examples/sir_infer_parameters.py:30-38) WITHOUT materialising the trajectory: one launch solves, forms
+    the increments, accumulates the log-probability and its gradient.  Differentiable w.r.t. the rates and
+    the initial state, vmappable; returns a scalar tensor per draw."""
+    from . import autograd as ag
+
+    _validate_call(ode, initial_state, ode_parameters, duration_days)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    obs_t = torch.as_tensor(obs, dtype=torch.float64, device=dev)
+    ncomp = len(initial_state)
+    comp = int(compartment) % ncomp
+    lp_const = float(-torch.lgamma(obs_t + 1.0).sum())
+    cfg, y0r, theta, saveat, opts = _differentiable_setup(
+        ode, duration_days, initial_state, ode_parameters, solver_parameters, None, save_step,
+        obs=obs_t.reshape(len(build_saveat(0.0, duration_days, save_step).times) - 1, -1).contiguous(),
+        obs_comp=comp, lp_const=lp_const)
+    lp, stats, _ = ag.PoissonLoglik.apply(y0r, theta, cfg)
+    return lp[0]
 
 
 def simulate_ensemble(

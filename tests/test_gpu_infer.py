@@ -1,0 +1,152 @@
+"""GPU: the differentiable / vmappable solve, the fused NUTS log-density and the inference processes on
+the reference's SIR inference example (examples/sir_infer_parameters.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def test_simulate_is_differentiable_and_matches_oracle_tangents():
+    from dynode_b200.config import SolverParams
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate
+    from oracle import oracle as orc
+    from tests.cases import make_case
+    case = make_case("sir_age2", 1)
+    beta = torch.tensor(case["params"]["beta"][0], dtype=torch.float64, device=_dev(), requires_grad=True)
+    gamma = torch.tensor(case["params"]["gamma"][0], dtype=torch.float64, device=_dev(), requires_grad=True)
+    y0 = torch.tensor(case["y0"], dtype=torch.float64, device=_dev())
+    state = (y0[0:2], y0[2:4], y0[4:6])
+    p = ex.AgeSIR_ODEParams(beta=beta, gamma=gamma, contact_matrix=torch.tensor(case["contact"], device=_dev()))
+    sol = simulate(ex.sir_age_ode, 100, state, p, SolverParams())
+    assert sol.ys[2].shape == (101, 2) and sol.ys[2].requires_grad
+    w = torch.linspace(0.5, 1.5, 101 * 2, dtype=torch.float64, device=_dev()).reshape(101, 2)
+    loss = (w * sol.ys[2]).sum() + sol.ys[1][50, 0] * 3.0
+    gb, gg = torch.autograd.grad(loss, (beta, gamma))
+    fam, dims, theta, shared = case["oracle"]
+    ys, dys, _ = orc.solve(fam, dims, case["y0"], theta, shared, t1=100, wrt=[0, 1])
+    ref = (w.cpu().numpy()[:, :, None] * dys[0][:, 4:6, :]).sum((0, 1)) + 3.0 * dys[0][50, 2, :]
+    assert np.allclose([float(gb), float(gg)], ref, rtol=1e-8)
+    assert np.allclose(sol.ys[2].detach().cpu().numpy(), ys[0][:, 4:6], rtol=1e-9, atol=1e-9)
+
+
+def test_gradient_with_respect_to_initial_state():
+    from dynode_b200.config import SolverParams
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate
+    y0 = torch.tensor([0.9, 0.1, 0.0], dtype=torch.float64, device=_dev(), requires_grad=True)
+    p = ex.SIR_ODEParams(beta=torch.tensor(0.3, dtype=torch.float64, device=_dev()), gamma=torch.tensor(0.1, device=_dev(), dtype=torch.float64))
+
+    def final_r(y):
+        return simulate(ex.sir_ode, 60, (y[0:1], y[1:2], y[2:3]), p, SolverParams()).ys[2][-1, 0]
+
+    (g,) = torch.autograd.grad(final_r(y0), y0)
+    eps = 1e-6
+    for j in range(3):
+        d = torch.zeros(3, dtype=torch.float64, device=_dev())
+        d[j] = eps
+        with torch.no_grad():
+            num = (final_r((y0 + d).detach().requires_grad_(True)) - final_r((y0 - d).detach().requires_grad_(True))) / (2 * eps)
+        assert abs(float(g[j]) - float(num)) < 2e-4 * max(1.0, abs(float(num)))  # adaptive steps move under FD
+
+
+def _example():
+    from dynode_b200.examples import sir_infer_parameters as m
+    cfg = m.get_config()
+    obs = m.synthetic_incidence(100).to(_dev())
+    return m, cfg, obs
+
+
+def test_vmapped_potential_equals_per_draw_and_fused_equals_general():
+    from dynode_b200.infer import ModelDensity
+    m, cfg, obs = _example()
+    md = ModelDensity(m.model, (), dict(config=cfg, tf=100, obs_data=obs))
+    mdf = ModelDensity(m.model_fused, (), dict(config=cfg, tf=100, obs_data=obs))
+    assert list(md.sites) == ["strains_0_r0", "strains_0_infectious_period"] and md.dim == 2
+    g = torch.Generator(device=_dev()).manual_seed(0)
+    Z = torch.randn(33, 2, dtype=torch.float64, device=_dev(), generator=g)
+    U, G = md.potential_and_grad(Z)
+    Uf, Gf = mdf.potential_and_grad(Z)
+    assert torch.allclose(U, Uf, rtol=1e-10) and torch.allclose(G, Gf, rtol=1e-7, atol=1e-7)
+    for k in (0, 7, 32):
+        u1, g1 = md.potential_and_grad(Z[k:k + 1])
+        assert torch.allclose(u1[0], U[k], rtol=1e-12) and torch.allclose(g1[0], G[k], rtol=1e-9, atol=1e-9)
+    # the posterior mode sits near r0 = 2, infectious period = 7
+    truth = mdf.unconstrain({"strains_0_r0": torch.tensor([2.0]), "strains_0_infectious_period": torch.tensor([7.0])})
+    Ut, Gt = mdf.potential_and_grad(truth.to(torch.float64))
+    assert float(Ut) < float(U.min()) and float(Gt.abs().max()) < 50.0
+
+
+def test_potential_gradient_against_complex_free_finite_differences():
+    from dynode_b200.infer import ModelDensity
+    m, cfg, obs = _example()
+    md = ModelDensity(m.model_fused, (), dict(config=cfg, tf=100, obs_data=obs))
+    Z = torch.tensor([[0.1, -0.3], [0.8, 0.4]], dtype=torch.float64, device=_dev())
+    U, G = md.potential_and_grad(Z)
+    eps = 1e-5
+    for j in range(2):
+        d = torch.zeros_like(Z)
+        d[:, j] = eps
+        num = (md.potential(Z + d) - md.potential(Z - d)) / (2 * eps)
+        # finite differences see the adaptive step sequence move; the kernel's gradient is the frozen-step one
+        assert torch.allclose(G[:, j], num, rtol=5e-3, atol=1e-3)
+
+
+def test_mcmc_process_recovers_the_generating_parameters():
+    from dynode_b200.infer import MCMCProcess
+    m, cfg, obs = _example()
+    proc = MCMCProcess(numpyro_model=m.model_fused, num_warmup=150, num_samples=100, num_chains=64,
+                       nuts_max_tree_depth=6, progress_bar=False)
+    proc.infer(config=cfg, tf=100, obs_data=obs)
+    s = proc.get_samples()
+    assert s["strains_0_r0"].shape == (6400,)
+    assert abs(float(s["strains_0_r0"].mean()) - 2.0) < 0.05
+    assert abs(float(s["strains_0_infectious_period"].mean()) - 7.0) < 0.3
+    summ = proc._inferer.summary()
+    assert summ["strains_0_r0"]["r_hat"] < 1.05
+    # general (trajectory-materialising) model through the same process, fewer chains
+    proc2 = MCMCProcess(numpyro_model=m.model, num_warmup=100, num_samples=50, num_chains=16,
+                        nuts_max_tree_depth=6, progress_bar=False)
+    proc2.infer(config=cfg, tf=100, obs_data=obs)
+    s2 = proc2.get_samples()
+    assert abs(float(s2["strains_0_r0"].mean()) - float(s["strains_0_r0"].mean())) < 0.05
+    pp = proc2.to_arviz()
+    assert pp["posterior_predictive"]["inf_incidence"].shape == (16 * 50, 100, 2)
+
+
+def test_svi_process_and_predictive_projection():
+    from dynode_b200.infer import Predictive, PRNGKey, SVIProcess
+    m, cfg, obs = _example()
+    proc = SVIProcess(numpyro_model=m.model_fused, num_iterations=300, num_samples=200, progress_bar=False)
+    proc.infer(config=cfg, tf=100, obs_data=obs)
+    s = proc.get_samples()
+    assert abs(float(s["strains_0_r0"].mean()) - 2.0) < 0.1
+    # project forward 200 days without data (reference sir_infer_parameters.py:156-169)
+    out = Predictive(m.model, posterior_samples=s)(PRNGKey(1), config=cfg, tf=200, obs_data=None)
+    assert out["inf_incidence"].shape == (200, 200, 2) and bool((out["inf_incidence"] >= 0).all())
+
+
+def test_sharded_ensemble_single_rank():
+    from dynode_b200.config import SolverParams
+    from dynode_b200.distributed import simulate_ensemble_sharded
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate_ensemble
+    from tests.cases import make_case
+    B = 300
+    case = make_case("seirs_multi_a2s3", B)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=_dev())
+    prm = case["params"]
+    p = ex.SEIRS_MultiStrain_ODEParams(beta=t(prm["beta"]), gamma=t(prm["gamma"]), sigma=t(prm["sigma"]),
+                                       omega=t(prm["omega"]), contact_matrix=t(case["contact"]))
+    y0 = t(case["y0"])
+    state = (y0[:, :2], y0[:, 2:8].reshape(B, 2, 3), y0[:, 8:14].reshape(B, 2, 3),
+             y0[:, 14:20].reshape(B, 2, 3), y0[:, 20:26].reshape(B, 2, 3))
+    ys, res, (lo, hi) = simulate_ensemble_sharded(ex.seirs_multi_strain_ode, 120, state, p, SolverParams(), batch_size=B)
+    ref = simulate_ensemble(ex.seirs_multi_strain_ode, 120, state, p, SolverParams(), batch_size=B, state_batched=True)
+    flat = torch.cat([c.reshape(B, 121, -1) for c in ref.ys], dim=2)
+    assert (lo, hi) == (0, B) and torch.equal(ys, flat) and int((res != 0).sum()) == 0

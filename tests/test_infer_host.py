@@ -1,0 +1,196 @@
+"""Inference layer on CPU: distributions/bijectors against scipy, site naming rules pinned by the reference's
+tests/test_infer/test_sample.py, the process wrappers on a toy model (as the reference's
+tests/test_infer/test_inference_processes.py does), NUTS against analytic posteriors."""
+import math
+
+import numpy as np
+import pytest
+import scipy.stats as st
+import torch
+
+from dynode_b200.config import DeterministicParameter
+from dynode_b200.infer import (MCMCProcess, ModelDensity, Predictive, PRNGKey, SVIProcess, build_adaptation_schedule,
+                               effective_sample_size, ppl, resolve_deterministic, sample_distributions,
+                               sample_then_resolve, split_rhat)
+from dynode_b200.infer import distributions as dist
+from dynode_b200.infer.nuts import BatchedNUTS
+
+X = torch.tensor([0.3, 1.7, 4.2], dtype=torch.float64)
+
+
+@pytest.mark.parametrize("d,ref,x", [
+    (dist.Normal(1.0, 2.0), st.norm(1.0, 2.0), X),
+    (dist.LogNormal(0.5, 0.7), st.lognorm(0.7, scale=math.exp(0.5)), X),
+    (dist.HalfNormal(1.5), st.halfnorm(scale=1.5), X),
+    (dist.Exponential(0.8), st.expon(scale=1 / 0.8), X),
+    (dist.Uniform(0.0, 5.0), st.uniform(0.0, 5.0), X),
+    (dist.Gamma(2.5, 1.5), st.gamma(2.5, scale=1 / 1.5), X),
+    (dist.Beta(0.5, 0.5), st.beta(0.5, 0.5), torch.tensor([0.1, 0.5, 0.93], dtype=torch.float64)),
+    (dist.TruncatedNormal(8.0, 2.0, low=2.0, high=15.0), st.truncnorm(-3.0, 3.5, loc=8.0, scale=2.0),
+     torch.tensor([2.5, 8.0, 14.0], dtype=torch.float64)),
+])
+def test_log_prob_matches_scipy(d, ref, x):
+    assert np.allclose(d.log_prob(x).numpy(), ref.logpdf(x.numpy()), rtol=1e-12, atol=1e-12)
+    g = torch.Generator().manual_seed(1)
+    s = d.sample(g, (20000,))
+    assert abs(float(s.mean()) - ref.mean()) < 5 * ref.std() / math.sqrt(20000) + 1e-3
+
+
+def test_poisson_log_prob_accepts_non_integer_observations():
+    rate = torch.tensor([0.5, 3.0, 10.0], dtype=torch.float64)
+    k = torch.tensor([0.0, 2.0, 12.0], dtype=torch.float64)
+    assert np.allclose(dist.Poisson(rate).log_prob(k).numpy(), st.poisson(rate.numpy()).logpmf(k.numpy()))
+    v = torch.tensor([0.25, 2.5, 11.1], dtype=torch.float64)
+    ref = v * torch.log(rate) - rate - torch.lgamma(v + 1)
+    assert torch.allclose(dist.Poisson(rate).log_prob(v), ref)
+
+
+def test_transformed_beta_prior_of_the_reference_example():
+    # r0 = 1.5 + 1 * Beta(1/2, 1/2)  (reference examples/sir_infer_parameters.py:50-53)
+    d = dist.TransformedDistribution(dist.Beta(0.5, 0.5), dist.transforms.AffineTransform(1.5, 1))
+    x = torch.tensor([1.6, 2.0, 2.45], dtype=torch.float64)
+    assert np.allclose(d.log_prob(x).numpy(), st.beta(0.5, 0.5, loc=1.5, scale=1.0).logpdf(x.numpy()))
+    assert (d.support.lower_bound, d.support.upper_bound) == (1.5, 2.5)
+
+
+@pytest.mark.parametrize("support", [dist.constraints.real, dist.constraints.positive, dist.constraints.unit_interval,
+                                     dist.constraints.interval(2.0, 15.0), dist.constraints.greater_than(3.0),
+                                     dist.constraints.less_than(-1.0)])
+def test_bijectors_round_trip_and_jacobian(support):
+    t = dist.biject_to(support)
+    z = torch.tensor([-2.0, 0.1, 3.0], dtype=torch.float64, requires_grad=True)
+    x = t(z)
+    assert torch.allclose(t.inv(x), z, atol=1e-10)
+    (jac,) = torch.autograd.grad(x.sum(), z)
+    assert torch.allclose(t.log_abs_det_jacobian(z, x), torch.log(jac.abs()), atol=1e-10)
+
+
+def _names(fn):
+    return list(ppl.trace(fn).get_trace().keys())
+
+
+def test_site_naming_rules():
+    # reference tests/test_infer/test_sample.py:49-117
+    tree = {"a": dist.Normal(), "b": [1, dist.Normal()], "c": np.array([dist.Normal(), 1], dtype=object),
+            "d": {"nested_dict": dist.Normal()}, "e": DeterministicParameter("a")}
+    names = _names(lambda: sample_then_resolve(tree, rng_key=PRNGKey(0)))
+    assert names == ["a", "b_1", "c_0", "d_nested_dict", "e"]
+    names = _names(lambda: sample_then_resolve(tree, rng_key=PRNGKey(0), _prefix="test_"))
+    assert names == ["test_a", "test_b_1", "test_c_0", "test_d_nested_dict", "test_e"]
+    out = sample_then_resolve(tree, rng_key=PRNGKey(0))
+    assert isinstance(out["a"], torch.Tensor) and out["a"] == out["e"]
+    assert isinstance(out["b"][1], torch.Tensor) and out["b"][0] == 1
+
+
+def test_resolve_deterministic_lists_and_slices():
+    t = {"a": [0, 1, 3, 4], "b": DeterministicParameter("a", index=1), "c": DeterministicParameter("a", index=slice(0, 2))}
+    r = resolve_deterministic(t, root_params=t)
+    assert r["b"] == 1 and r["c"] == [0, 1]
+    with pytest.raises(Exception, match="unable to find"):
+        resolve_deterministic({"x": DeterministicParameter("nope")}, root_params={})
+
+
+def test_sampling_outside_context_needs_a_key():
+    with pytest.raises(ValueError, match="rng_key"):
+        sample_distributions({"a": dist.Normal()})
+    with ppl.seed(rng_seed=3):
+        v = sample_distributions({"a": dist.Normal()})["a"]
+    with ppl.seed(rng_seed=3):
+        assert sample_distributions({"a": dist.Normal()})["a"] == v
+    with pytest.raises(ValueError, match="unique names"):
+        ppl.trace(ppl.seed(lambda: (ppl.sample("x", dist.Normal()), ppl.sample("x", dist.Normal())), 0)).get_trace()
+
+
+def test_adaptation_schedule_is_stans():
+    assert build_adaptation_schedule(10) == [(0, 9)]
+    assert build_adaptation_schedule(500) == [(0, 74), (75, 99), (100, 149), (150, 249), (250, 449), (450, 499)]
+    s = build_adaptation_schedule(100)
+    assert s[0] == (0, 14) and s[-1] == (90, 99) and s[1][0] == 15 and s[-2][1] == 89
+
+
+def test_nuts_recovers_a_correlated_gaussian():
+    cov = torch.tensor([[1.0, 0.8], [0.8, 1.5]], dtype=torch.float64)
+    mu = torch.tensor([1.0, -2.0], dtype=torch.float64)
+    prec = torch.linalg.inv(cov)
+
+    def pg(z):
+        d = z - mu
+        g = d @ prec
+        return 0.5 * (d * g).sum(1), g
+
+    eng = BatchedNUTS(pg, max_tree_depth=6, generator=torch.Generator().manual_seed(5))
+    z, extra, last = eng.run(torch.zeros(48, 2, dtype=torch.float64), 120, 80)
+    x = z.reshape(-1, 2)
+    assert torch.allclose(x.mean(0), mu, atol=0.08)
+    assert torch.allclose(torch.cov(x.T), cov, atol=0.15)
+    assert float(extra["diverging"].sum()) == 0
+    assert 0.7 < float(extra["accept_prob"].mean()) < 0.98
+    assert float(split_rhat(z[:, :, 0])) < 1.05 and float(effective_sample_size(z[:, :, 0])) > 500
+    assert eng.grad_evals % 48 == 0  # counted per chain
+
+
+def _toy_model(obs=None):
+    mu = ppl.sample("mu", dist.Normal(0.0, 10.0))
+    sigma = ppl.sample("sigma", dist.HalfNormal(5.0))
+    ppl.deterministic("mu_plus_one", mu + 1.0)
+    ppl.sample("y", dist.Normal(mu, sigma), obs=obs)
+
+
+def test_mcmc_process_on_a_toy_model():
+    # reference tests/test_infer/test_inference_processes.py:15-40: runs and returns num_samples draws
+    obs = torch.tensor(np.random.default_rng(0).normal(3.0, 2.0, 60))
+    proc = MCMCProcess(numpyro_model=_toy_model, num_samples=60, num_warmup=100, num_chains=8,
+                       nuts_max_tree_depth=6, progress_bar=False)
+    with pytest.raises(AssertionError, match="call infer"):
+        proc.get_samples()
+    proc.infer(obs=obs)
+    s = proc.get_samples()
+    assert set(s) == {"mu", "sigma"} and s["mu"].shape == (8 * 60,)
+    assert proc.get_samples(group_by_chain=True)["mu"].shape == (8, 60)
+    assert "mu_plus_one" in proc.get_samples(exclude_deterministic=False)
+    assert abs(float(s["mu"].mean()) - float(obs.mean())) < 0.3
+    assert abs(float(s["sigma"].mean()) - float(obs.std())) < 0.4
+    az = proc.to_arviz()
+    assert az["posterior_predictive"]["y"].shape == (480, 60) and az["prior"]["mu"].shape == (60,)
+    summ = proc._inferer.summary()
+    assert summ["mu"]["r_hat"] < 1.1
+
+
+def test_svi_process_on_a_toy_model():
+    obs = torch.tensor(np.random.default_rng(1).normal(-1.0, 0.5, 80))
+    proc = SVIProcess(numpyro_model=_toy_model, num_iterations=300, num_samples=200, progress_bar=False)
+    proc.infer(obs=obs)
+    s = proc.get_samples()
+    assert s["mu"].shape == (200,) and abs(float(s["mu"].mean()) + 1.0) < 0.2
+    assert abs(float(s["sigma"].mean()) - 0.5) < 0.15
+    assert "mu_plus_one" in proc.get_samples(exclude_deterministic=False)
+    losses = proc._inference_state.losses
+    assert float(losses[-20:].mean()) < float(losses[:20].mean())
+    az = proc.to_arviz()
+    assert az["log_likelihood"]["y"].shape == (200, 80)
+
+
+def test_predictive_samples_observation_sites():
+    post = {"mu": torch.full((50,), 2.0, dtype=torch.float64), "sigma": torch.full((50,), 0.1, dtype=torch.float64)}
+    out = Predictive(_toy_model, posterior_samples=post)(PRNGKey(0), obs=None)
+    assert out["y"].shape == (50,) and abs(float(out["y"].mean()) - 2.0) < 0.1
+    prior = Predictive(_toy_model, num_samples=30, exclude_deterministic=False)(PRNGKey(0), obs=None)
+    assert prior["mu"].shape == (30,) and torch.allclose(prior["mu_plus_one"], prior["mu"] + 1.0)
+
+
+def test_potential_matches_a_hand_written_density():
+    obs = torch.tensor([0.5, 1.5], dtype=torch.float64)
+    md = ModelDensity(_toy_model, (), {"obs": obs}, device=torch.device("cpu"))
+    assert md.dim == 2 and list(md.sites) == ["mu", "sigma"]
+    z = torch.tensor([[0.3, -0.2], [1.0, 0.5]], dtype=torch.float64)
+    U, g = md.potential_and_grad(z)
+    mu, sig = z[:, 0], torch.exp(z[:, 1])
+    lp = (st.norm(0, 10).logpdf(mu.numpy()) + st.halfnorm(scale=5).logpdf(sig.numpy()) + z[:, 1].numpy()
+          + st.norm(mu.numpy()[:, None], sig.numpy()[:, None]).logpdf(obs.numpy()[None, :]).sum(1))
+    assert np.allclose(U.numpy(), -lp, rtol=1e-12)
+    eps = 1e-6
+    for j in range(2):
+        dz = torch.zeros_like(z)
+        dz[:, j] = eps
+        num = (md.potential(z + dz) - md.potential(z - dz)) / (2 * eps)
+        assert torch.allclose(g[:, j], num, rtol=1e-6, atol=1e-8)
