@@ -41,10 +41,12 @@ class MCMC:
     """numpyro.infer.MCMC stand-in: `run`, `get_samples`, `get_extra_fields`, `last_state`, `print_summary`."""
 
     def __init__(self, sampler: NUTS, num_warmup: int, num_samples: int, num_chains: int = 1,
-                 progress_bar: bool = True, chain_method: str = "vectorized"):
+                 progress_bar: bool = True, chain_method: str = "vectorized", cuda_graph: Optional[bool] = None,
+                 sync_every: int = 4):
         self.sampler, self.num_warmup, self.num_samples, self.num_chains = sampler, num_warmup, num_samples, num_chains
         self.progress_bar = progress_bar
         self.chain_method = chain_method
+        self.cuda_graph, self.sync_every = cuda_graph, sync_every
         self._samples_z: Optional[torch.Tensor] = None
         self._states: Dict[str, Dict[str, torch.Tensor]] = {}
         self._states_flat: Dict[str, Dict[str, torch.Tensor]] = {}
@@ -61,24 +63,25 @@ class MCMC:
         z0 = init_z if init_z is not None else self.sampler.init_strategy(md, self.num_chains)
         z0 = z0.to(md.device)
         gen = key.fold_in(12).generator(md.device)
+        if md.device.type == "cuda":
+            torch.cuda.manual_seed(key.fold_in(13).seed % (2**63 - 1))  # graph-replayed rounds draw from it
         s = self.sampler
         eng = BatchedNUTS(md.potential_and_grad, max_tree_depth=s.max_tree_depth,
                           target_accept_prob=s.target_accept_prob, dense_mass=s.dense_mass,
                           step_size=s.step_size, adapt_step_size=s.adapt_step_size,
-                          adapt_mass_matrix=s.adapt_mass_matrix, generator=gen)
+                          adapt_mass_matrix=s.adapt_mass_matrix, generator=gen, cuda_graph=self.cuda_graph,
+                          sync_every=self.sync_every)
         self.engine = eng
         progress = None
         if self.progress_bar:
             total = self.num_warmup + self.num_samples
-            every = max(1, total // 10)
 
-            def progress(t, st):
-                if (t + 1) % every == 0 or t + 1 == total:
-                    phase = "warmup" if t < self.num_warmup else "sample"
-                    print(f"[dynode_b200.infer] {phase} {t + 1}/{total}  chains={self.num_chains}  "
-                          f"mean step_size={float(st.step_size.mean()):.3g}  "
-                          f"mean accept={float(st.stats['accept_prob'].mean()):.2f}  "
-                          f"mean leapfrogs={float(st.stats['num_steps'].double().mean()):.1f}")
+            def progress(t, e):
+                phase = "warmup" if t < self.num_warmup else "sample"
+                print(f"[dynode_b200.infer] {phase} {t + 1}/{total}  chains={self.num_chains}  "
+                      f"rounds={e.rounds}  mean step_size={float(e.step_size.mean()):.3g}  "
+                      f"mean accept={float(e.stats['accept_prob'].mean()):.2f}  "
+                      f"mean leapfrogs={float(e.stats['num_steps'].mean()):.1f}  graph={e.graph_used}")
 
         z, extra, last = eng.run(z0, self.num_warmup, self.num_samples, progress)
         self._samples_z, self._extra, self.last_state = z, extra, last

@@ -5,16 +5,24 @@ The reference runs numpyro's `MCMC(NUTS(model, dense_mass=True, max_tree_depth, 
 chains run one after another on a CPU.  This sampler keeps numpyro's algorithm -- iterative tree doubling
 with checkpointed U-turn tests, multinomial proposal sampling with a biased top-level transition,
 divergence at an energy error of 1000, dual-averaging step size (target 0.8, t0=10, kappa=0.75,
-gamma=0.05), Stan's windowed dense mass-matrix adaptation with Welford covariance and shrinkage -- but
-advances ALL chains in lock-step: every leapfrog round is ONE batched evaluation of
-`potential_and_grad(z[C, D])`, i.e. one ensemble launch of the ODE kernel for C chains.  Chain state lives
-in device tensors; per-chain control flow is masks, not Python branches.
+gamma=0.05), Stan's windowed dense mass-matrix adaptation with Welford covariance and shrinkage -- and
+re-organises it for the GPU:
+
+  * all chains advance together; every *round* is ONE batched `potential_and_grad(z[C, D])`, i.e. one
+    ensemble launch of the ODE kernel, plus masked tensor updates of the per-chain tree state;
+  * chains are NOT held in lock-step per transition: a chain whose tree is complete commits its
+    transition (sample, step-size and covariance updates) and starts its next tree in the very next
+    round.  Chains only wait for each other at the adaptation-window boundaries, so the number of rounds
+    is set by the mean tree size, not by the largest tree among the chains at every transition;
+  * all state lives in persistent device buffers updated in place, so on CUDA the whole round -- model
+    evaluation included -- is captured once into a CUDA graph and replayed (one graph launch per round,
+    one host sync every `sync_every` rounds to see whether the window is finished).
 """
 
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from types import SimpleNamespace
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
@@ -62,32 +70,20 @@ def _tree_index_tables(max_depth: int, device):
     return idx_min.to(device), idx_max.to(device)
 
 
-@dataclass
-class NUTSState:
-    z: torch.Tensor        # [C, D] unconstrained position
-    U: torch.Tensor        # [C] potential energy
-    g: torch.Tensor        # [C, D] gradient of U
-    step_size: torch.Tensor  # [C]
-    inv_mass: torch.Tensor   # [C, D, D]
-    i: int = 0
-    # dual averaging
-    da_x: torch.Tensor = None
-    da_xavg: torch.Tensor = None
-    da_gavg: torch.Tensor = None
-    da_t: torch.Tensor = None
-    da_prox: torch.Tensor = None
-    # Welford accumulators of the current slow window
-    wf_n: int = 0
-    wf_mean: torch.Tensor = None
-    wf_m2: torch.Tensor = None
-    stats: Dict[str, torch.Tensor] = field(default_factory=dict)
+def _put(dst: torch.Tensor, mask: torch.Tensor, src) -> None:
+    """dst[mask] = src[mask], in place, static shapes (one fused select kernel)."""
+    m = mask.reshape(mask.shape + (1,) * (dst.dim() - mask.dim()))
+    if not isinstance(src, torch.Tensor):
+        src = torch.full_like(dst, src)
+    torch.where(m, src, dst, out=dst)
 
 
 class BatchedNUTS:
     def __init__(self, potential_and_grad: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                  max_tree_depth: int = 10, target_accept_prob: float = 0.8, dense_mass: bool = True,
                  step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, cuda_graph: Optional[bool] = None,
+                 sync_every: int = 4):
         self.pg = potential_and_grad
         self.max_depth = int(max_tree_depth)
         self.target = float(target_accept_prob)
@@ -95,19 +91,25 @@ class BatchedNUTS:
         self.init_step = float(step_size)
         self.adapt_ss, self.adapt_mm = adapt_step_size, adapt_mass_matrix
         self.gen = generator
-        self.grad_evals = 0  # batched evaluations x chains
-        self._tables = None
+        self.cuda_graph = cuda_graph
+        self.sync_every = max(1, int(sync_every))
+        self.grad_evals = 0          # leapfrogs that belong to a tree (what "NUTS grad-evals" counts)
+        self.launched_evals = 0      # rounds x chains (includes chains idling at a window boundary)
+        self.rounds = 0
+        self.graph_used = False
+        self.b: Optional[SimpleNamespace] = None
 
     # ------------------------------------------------------------------ helpers
-    def _randn(self, *shape, like):
-        return torch.randn(*shape, dtype=like.dtype, device=like.device, generator=self.gen)
+    def _randn(self, *shape):
+        b = self.b
+        return torch.randn(*shape, dtype=b.dtype, device=b.dev, generator=self._g)
 
-    def _rand(self, *shape, like):
-        return torch.rand(*shape, dtype=like.dtype, device=like.device, generator=self.gen)
+    def _rand(self, *shape):
+        b = self.b
+        return torch.rand(*shape, dtype=b.dtype, device=b.dev, generator=self._g)
 
     def _eval(self, z):
         U, g = self.pg(z)
-        self.grad_evals += z.shape[0]
         bad = ~torch.isfinite(U) | ~torch.isfinite(g).all(dim=1)
         U = torch.where(bad, torch.full_like(U, math.inf), U)
         g = torch.where(bad[:, None], torch.zeros_like(g), g)
@@ -125,222 +127,302 @@ class BatchedNUTS:
         rc = r_sum - 0.5 * (r_left + r_right)
         return ((v_l * rc).sum(-1) <= 0) | ((v_r * rc).sum(-1) <= 0)
 
-    # ------------------------------------------------------------------ initialisation
-    def init(self, z0: torch.Tensor) -> NUTSState:
+    # ------------------------------------------------------------------ buffers
+    def _allocate(self, z0: torch.Tensor, num_samples: int):
         C, D = z0.shape
-        U, g = self._eval(z0)
-        if not torch.isfinite(U).all():
-            raise RuntimeError("cannot find valid initial parameters: the potential is not finite at the "
-                               "initial position of some chain")
-        eye = torch.eye(D, dtype=z0.dtype, device=z0.device).expand(C, D, D).contiguous()
-        ss = torch.full((C,), self.init_step, dtype=z0.dtype, device=z0.device)
-        st = NUTSState(z=z0.clone(), U=U, g=g, step_size=ss, inv_mass=eye)
-        self._da_reset(st)
-        self._wf_reset(st)
-        self._tables = _tree_index_tables(self.max_depth, z0.device)
-        return st
+        dev, dt, md = z0.device, z0.dtype, self.max_depth
+        f = lambda *s: torch.zeros(*s, dtype=dt, device=dev)
+        l = lambda *s: torch.zeros(*s, dtype=torch.long, device=dev)
+        bl = lambda *s: torch.zeros(*s, dtype=torch.bool, device=dev)
+        b = SimpleNamespace(C=C, D=D, dev=dev, dtype=dt)
+        b.z, b.U, b.g = z0.clone(), f(C), f(C, D)
+        b.eps = torch.full((C,), self.init_step, dtype=dt, device=dev)
+        b.imm = torch.eye(D, dtype=dt, device=dev).expand(C, D, D).contiguous()
+        b.msqrt = b.imm.clone()
+        b.k, b.nwin = l(C), l(())
+        b.active, b.need_tree = bl(C), bl(C)
+        b.energy0 = f(C)
+        for name in ("zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP", "r_sum", "s_z", "s_r", "s_g", "s_zP", "s_gP", "s_rsum"):
+            setattr(b, name, f(C, D))
+        for name in ("UP", "weight", "sum_acc", "s_UP", "s_w", "s_acc"):
+            setattr(b, name, f(C))
+        for name in ("depth", "nprop", "s_n"):
+            setattr(b, name, l(C))
+        for name in ("turning", "diverging", "s_right", "s_turn", "s_div"):
+            setattr(b, name, bl(C))
+        b.r_ck, b.rs_ck = f(C, md, D), f(C, md, D)
+        b.da_x, b.da_xavg, b.da_gavg, b.da_t = f(C), f(C), f(C), f(C)
+        b.da_prox = torch.log(10.0 * b.eps)
+        b.wf_n, b.wf_mean, b.wf_m2 = f(C), f(C, D), f(C, D, D)
+        b.f_adapt, b.f_middle, b.f_sampling = bl(()), bl(()), bl(())
+        N = max(1, num_samples)
+        b.out_z = f(C, N, D)
+        b.out_stats = {k: f(C, N) for k in ("accept_prob", "num_steps", "diverging", "potential_energy", "tree_depth")}
+        b.last_accept, b.last_steps = f(C), f(C)
+        b.n_useful = l(())
+        b.any_active = bl(())
+        b.idx_min_tab, b.idx_max_tab = _tree_index_tables(md, dev)
+        b.ar = torch.arange(C, device=dev)
+        b.lvl = torch.arange(md, device=dev)
+        self.b = b
 
-    def _da_reset(self, st: NUTSState):
-        zeros = torch.zeros_like(st.step_size)
-        st.da_prox = torch.log(10.0 * st.step_size)
-        st.da_x, st.da_xavg, st.da_gavg, st.da_t = zeros.clone(), zeros.clone(), zeros.clone(), zeros.clone()
+    # ------------------------------------------------------------------ one round for all chains
+    def _round(self):
+        b = self.b
+        C, D, md = b.C, b.D, self.max_depth
+        imm, eps = b.imm, b.eps
+        act = b.active.clone()  # chains that take part in this round
 
-    def _wf_reset(self, st: NUTSState):
-        C, D = st.z.shape
-        st.wf_n = 0
-        st.wf_mean = torch.zeros((C, D), dtype=st.z.dtype, device=st.z.device)
-        st.wf_m2 = torch.zeros((C, D, D), dtype=st.z.dtype, device=st.z.device)
+        # ---- chains beginning a transition: fresh momentum r ~ N(0, M), one-node tree at the current state
+        nt = act & b.need_tree
+        r0 = torch.einsum("cij,cj->ci", b.msqrt, self._randn(C, D))
+        _put(b.energy0, nt, b.U + self._kinetic(imm, r0))
+        for dst, src in ((b.zL, b.z), (b.zR, b.z), (b.zP, b.z), (b.gL, b.g), (b.gR, b.g), (b.gP, b.g),
+                         (b.rL, r0), (b.rR, r0), (b.r_sum, r0)):
+            _put(dst, nt, src)
+        _put(b.UP, nt, b.U)
+        for dst in (b.weight, b.sum_acc):
+            _put(dst, nt, 0.0)
+        for dst in (b.depth, b.nprop, b.s_n):
+            _put(dst, nt, 0)
+        for dst in (b.turning, b.diverging):
+            _put(dst, nt, False)
+        _put(b.need_tree, nt, False)
 
-    # ------------------------------------------------------------------ one transition for all chains
-    def step(self, st: NUTSState) -> NUTSState:
-        C, D = st.z.shape
-        dev, dt = st.z.device, st.z.dtype
-        md = self.max_depth
-        imm, eps = st.inv_mass, st.step_size
-        idx_min_tab, idx_max_tab = self._tables
-        ar = torch.arange(C, device=dev)
-        lvl = torch.arange(md, device=dev)
+        # ---- chains starting a new doubling: pick a direction, start from that edge of the tree
+        start = act & (b.s_n == 0)
+        _put(b.s_right, start, self._rand(C) < 0.5)
+        sr = b.s_right[:, None]
+        _put(b.s_z, start, torch.where(sr, b.zR, b.zL))
+        _put(b.s_r, start, torch.where(sr, b.rR, b.rL))
+        _put(b.s_g, start, torch.where(sr, b.gR, b.gL))
 
-        # momentum r ~ N(0, M), M = inv_mass^-1: r = L^-T xi with inv_mass = L L^T
-        L = torch.linalg.cholesky(imm)
-        r0 = torch.linalg.solve_triangular(L.transpose(1, 2), self._randn(C, D, 1, like=st.z), upper=True)[..., 0]
-        energy0 = st.U + self._kinetic(imm, r0)
+        # ---- one leapfrog for every chain (idle chains are evaluated too and discarded)
+        h = torch.where(b.s_right, eps, -eps)[:, None]
+        r_half = b.s_r - 0.5 * h * b.s_g
+        z_new = b.s_z + h * self._vel(imm, r_half)
+        U_new, g_new = self._eval(z_new)
+        r_new = r_half - 0.5 * h * g_new
+        delta = U_new + self._kinetic(imm, r_new) - b.energy0
+        delta = torch.where(torch.isnan(delta), torch.full_like(delta, math.inf), delta)
+        leaf_w = -delta
+        leaf_div = delta > MAX_DELTA_ENERGY
+        leaf_acc = torch.clamp(torch.exp(-delta), max=1.0)
 
-        # whole-tree state
-        zL, rL, gL = st.z.clone(), r0.clone(), st.g.clone()
-        zR, rR, gR = st.z.clone(), r0.clone(), st.g.clone()
-        zP, UP, gP = st.z.clone(), st.U.clone(), st.g.clone()
-        depth = torch.zeros(C, dtype=torch.long, device=dev)
-        weight = torch.zeros(C, dtype=dt, device=dev)
-        r_sum = r0.clone()
-        turning = torch.zeros(C, dtype=torch.bool, device=dev)
-        diverging = torch.zeros(C, dtype=torch.bool, device=dev)
-        sum_acc = torch.zeros(C, dtype=dt, device=dev)
-        nprop = torch.zeros(C, dtype=torch.long, device=dev)
-        active = torch.ones(C, dtype=torch.bool, device=dev)
+        # ---- fold the leaf into the subtree (uniform/multinomial transition inside a subtree)
+        first = b.s_n == 0
+        new_w = torch.where(first, leaf_w, torch.logaddexp(b.s_w, leaf_w))
+        p_take = torch.where(first, torch.ones_like(leaf_w), torch.sigmoid(leaf_w - b.s_w))
+        take = act & (self._rand(C) < p_take)
+        _put(b.s_zP, take, z_new)
+        _put(b.s_UP, take, U_new)
+        _put(b.s_gP, take, g_new)
+        _put(b.s_rsum, act, torch.where(first[:, None], r_new, b.s_rsum + r_new))
+        _put(b.s_z, act, z_new)
+        _put(b.s_r, act, r_new)
+        _put(b.s_g, act, g_new)
+        _put(b.s_w, act, new_w)
+        _put(b.s_acc, act, torch.where(first, leaf_acc, b.s_acc + leaf_acc))
+        _put(b.s_div, act, leaf_div)
 
-        # subtree under construction
-        s_n = torch.zeros(C, dtype=torch.long, device=dev)  # leaves so far
-        s_right = torch.zeros(C, dtype=torch.bool, device=dev)
-        s_z, s_r, s_g = st.z.clone(), r0.clone(), st.g.clone()           # moving edge
-        s_z0, s_r0, s_g0 = st.z.clone(), r0.clone(), st.g.clone()        # first leaf (inner edge)
-        s_zP, s_UP, s_gP = st.z.clone(), st.U.clone(), st.g.clone()
-        s_w = torch.zeros(C, dtype=dt, device=dev)
-        s_rsum = torch.zeros(C, D, dtype=dt, device=dev)
-        s_turn = torch.zeros(C, dtype=torch.bool, device=dev)
-        s_div = torch.zeros(C, dtype=torch.bool, device=dev)
-        s_acc = torch.zeros(C, dtype=dt, device=dev)
-        r_ck = torch.zeros(C, md, D, dtype=dt, device=dev)
-        rs_ck = torch.zeros(C, md, D, dtype=dt, device=dev)
+        # ---- checkpointed U-turn tests over the sub-subtrees that this leaf completes
+        n = b.s_n
+        i_min, i_max = b.idx_min_tab[n], b.idx_max_tab[n]
+        even = (n % 2 == 0) & act
+        slot = (b.lvl[None, :] == i_max[:, None]) & even[:, None]
+        _put(b.r_ck, slot, r_new[:, None, :].expand(C, md, D))
+        _put(b.rs_ck, slot, b.s_rsum[:, None, :].expand(C, md, D))
+        sub_sum = b.s_rsum[:, None, :] - b.rs_ck + b.r_ck                # [C, md, D]
+        v_l = torch.einsum("cij,cmj->cmi", imm, b.r_ck)
+        v_r = self._vel(imm, r_new)[:, None, :]
+        rc = sub_sum - 0.5 * (b.r_ck + r_new[:, None, :])
+        turn_lv = ((v_l * rc).sum(-1) <= 0) | ((v_r * rc).sum(-1) <= 0)  # [C, md]
+        in_rng = (b.lvl[None, :] >= i_min[:, None]) & (b.lvl[None, :] <= i_max[:, None])
+        it_turn = (turn_lv & in_rng).any(1) & ~first
+        _put(b.s_turn, act, it_turn)
+        _put(b.s_n, act, b.s_n + 1)
 
-        def sel(m, a, b):
-            return torch.where(m.reshape(-1, *([1] * (a.dim() - 1))), a, b)
+        # ---- subtree finished (full size, U-turn or divergence): double the tree
+        target = torch.ones_like(b.depth) << b.depth
+        done_sub = act & ((b.s_n >= target) | b.s_turn | b.s_div)
+        p_bias = torch.clamp(torch.exp(b.s_w - b.weight), max=1.0)
+        p_bias = torch.where(b.s_turn | b.s_div, torch.zeros_like(p_bias), p_bias)
+        take2 = done_sub & (self._rand(C) < p_bias)
+        _put(b.zP, take2, b.s_zP)
+        _put(b.UP, take2, b.s_UP)
+        _put(b.gP, take2, b.s_gP)
+        mR, mL = done_sub & b.s_right, done_sub & ~b.s_right
+        for dst, src in ((b.zR, b.s_z), (b.rR, b.s_r), (b.gR, b.s_g)):
+            _put(dst, mR, src)
+        for dst, src in ((b.zL, b.s_z), (b.rL, b.s_r), (b.gL, b.s_g)):
+            _put(dst, mL, src)
+        _put(b.weight, done_sub, torch.logaddexp(b.weight, b.s_w))
+        _put(b.r_sum, done_sub, b.r_sum + b.s_rsum)
+        _put(b.turning, done_sub, b.s_turn | self._is_turning(imm, b.rL, b.rR, b.r_sum))
+        _put(b.diverging, done_sub, b.s_div)
+        _put(b.sum_acc, done_sub, b.sum_acc + b.s_acc)
+        _put(b.nprop, done_sub, b.nprop + b.s_n)
+        _put(b.depth, done_sub, b.depth + 1)
+        _put(b.s_n, done_sub, 0)
 
-        rounds = 0
+        # ---- tree complete: commit the transition for those chains and let them start the next one
+        fin = done_sub & ((b.depth >= md) | b.turning | b.diverging)
+        accept = b.sum_acc / b.nprop.clamp(min=1).to(b.dtype)
+        _put(b.z, fin, b.zP)
+        _put(b.U, fin, b.UP)
+        _put(b.g, fin, b.gP)
+        _put(b.last_accept, fin, accept)
+        _put(b.last_steps, fin, b.nprop.to(b.dtype))
+        # dual averaging of log step size (warmup windows)
+        ad = fin & b.f_adapt
+        tt = b.da_t + 1.0
+        gavg = (1.0 - 1.0 / (tt + 10.0)) * b.da_gavg + (self.target - accept) / (tt + 10.0)
+        x = b.da_prox - torch.sqrt(tt) / 0.05 * gavg
+        wt = tt ** (-0.75)
+        xavg = (1.0 - wt) * b.da_xavg + wt * x
+        _put(b.da_t, ad, tt)
+        _put(b.da_gavg, ad, gavg)
+        _put(b.da_x, ad, x)
+        _put(b.da_xavg, ad, xavg)
+        _put(b.eps, ad, torch.exp(x.clamp(-700.0, 700.0)))
+        # Welford covariance of the positions (slow windows)
+        wf = fin & b.f_middle
+        n1 = b.wf_n + 1.0
+        d1 = b.z - b.wf_mean
+        mean1 = b.wf_mean + d1 / n1[:, None]
+        d2 = b.z - mean1
+        _put(b.wf_m2, wf, b.wf_m2 + d1[:, :, None] * d2[:, None, :])
+        _put(b.wf_mean, wf, mean1)
+        _put(b.wf_n, wf, n1)
+        # store the draw (sampling window)
+        st = fin & b.f_sampling
+        kk = b.k.clamp(max=b.out_z.shape[1] - 1)
+        cur = b.out_z[b.ar, kk]
+        b.out_z[b.ar, kk] = torch.where(st[:, None], b.z, cur)
+        for name, val in (("accept_prob", accept), ("num_steps", b.nprop.to(b.dtype)),
+                          ("diverging", b.diverging.to(b.dtype)), ("potential_energy", b.U),
+                          ("tree_depth", b.depth.to(b.dtype))):
+            buf = b.out_stats[name]
+            buf[b.ar, kk] = torch.where(st, val, buf[b.ar, kk])
+        _put(b.k, fin, b.k + 1)
+        _put(b.need_tree, fin, True)
+        _put(b.active, fin & (b.k >= b.nwin), False)
+        b.n_useful += act.sum()
+        b.any_active.copy_(b.active.any())
+
+    # ------------------------------------------------------------------ graph capture
+    def _prepare_round_fn(self):
+        b = self.b
+        want = self.cuda_graph if self.cuda_graph is not None else b.dev.type == "cuda"
+        self._g = self.gen
+        self._round_fn = self._round
+        self.graph_used = False
+        if not want or b.dev.type != "cuda":
+            return
+        try:
+            self._g = None  # the default CUDA generator is graph-safe (philox offsets are patched per replay)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up rounds are real rounds of the algorithm
+                    self._round()
+                    self.rounds += 1
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._round()
+            self._graph = graph
+            self._round_fn = graph.replay
+            self.graph_used = True
+        except Exception as e:  # same kernels either way; say that replay is off and why
+            import warnings
+            torch.cuda.synchronize()
+            self._g = self.gen
+            self._round_fn = self._round
+            warnings.warn(f"BatchedNUTS: CUDA-graph capture of the round failed ({type(e).__name__}: {e}); "
+                          "running rounds eagerly")
+
+    # ------------------------------------------------------------------ driver
+    def _refresh_mass_sqrt(self):
+        b = self.b
+        L = torch.linalg.cholesky_ex(b.imm, check_errors=False).L
+        eye = torch.eye(b.D, dtype=b.dtype, device=b.dev).expand(b.C, b.D, b.D)
+        b.msqrt.copy_(torch.linalg.solve_triangular(L.transpose(1, 2), eye, upper=True))  # L^-T
+
+    def _run_window(self, length: int, adapt: bool, middle: bool, sampling: bool):
+        b = self.b
+        b.k.zero_()
+        b.nwin.fill_(length)
+        b.active.fill_(True)
+        b.f_adapt.fill_(adapt)
+        b.f_middle.fill_(middle)
+        b.f_sampling.fill_(sampling)
+        b.any_active.fill_(True)
         while True:
-            if not bool(active.any()):
+            for _ in range(self.sync_every):
+                self._round_fn()
+                self.rounds += 1
+            if not bool(b.any_active):
                 break
-            rounds += 1
-            # ---- chains starting a new doubling: pick a direction, start from that edge of the tree
-            start = active & (s_n == 0)
-            go_right = self._rand(C, like=st.z) < 0.5
-            s_right = torch.where(start, go_right, s_right)
-            s_z = sel(start, sel(s_right, zR, zL), s_z)
-            s_r = sel(start, sel(s_right, rR, rL), s_r)
-            s_g = sel(start, sel(s_right, gR, gL), s_g)
-
-            # ---- one leapfrog for every chain (inactive chains are evaluated too and discarded)
-            h = torch.where(s_right, eps, -eps)[:, None]
-            r_half = s_r - 0.5 * h * s_g
-            z_new = s_z + h * self._vel(imm, r_half)
-            U_new, g_new = self._eval(z_new)
-            r_new = r_half - 0.5 * h * g_new
-            delta = U_new + self._kinetic(imm, r_new) - energy0
-            delta = torch.where(torch.isnan(delta), torch.full_like(delta, math.inf), delta)
-            leaf_w = -delta
-            leaf_div = delta > MAX_DELTA_ENERGY
-            leaf_acc = torch.clamp(torch.exp(-delta), max=1.0)
-
-            # ---- fold the leaf into the subtree (uniform/multinomial transition inside a subtree)
-            first = s_n == 0
-            new_w = torch.where(first, leaf_w, torch.logaddexp(s_w, leaf_w))
-            p_take = torch.where(first, torch.ones_like(leaf_w), torch.sigmoid(leaf_w - s_w))
-            take = active & (self._rand(C, like=st.z) < p_take)
-            s_zP, s_UP, s_gP = sel(take, z_new, s_zP), torch.where(take, U_new, s_UP), sel(take, g_new, s_gP)
-            new_rsum = torch.where(first[:, None], r_new, s_rsum + r_new)
-            upd = active
-            s_z0, s_r0, s_g0 = sel(upd & first, z_new, s_z0), sel(upd & first, r_new, s_r0), sel(upd & first, g_new, s_g0)
-            s_z, s_r, s_g = sel(upd, z_new, s_z), sel(upd, r_new, s_r), sel(upd, g_new, s_g)
-            s_w = torch.where(upd, new_w, s_w)
-            s_rsum = sel(upd, new_rsum, s_rsum)
-            s_acc = torch.where(upd, torch.where(first, leaf_acc, s_acc + leaf_acc), s_acc)
-            s_div = torch.where(upd, leaf_div, s_div)
-
-            # ---- checkpointed U-turn tests over the sub-subtrees that this leaf completes
-            n = s_n
-            i_min, i_max = idx_min_tab[n], idx_max_tab[n]
-            even = (n % 2 == 0) & upd
-            slot = torch.zeros(C, md, dtype=torch.bool, device=dev)
-            slot[ar, i_max.clamp(max=md - 1)] = even
-            r_ck = torch.where(slot[:, :, None], r_new[:, None, :], r_ck)
-            rs_ck = torch.where(slot[:, :, None], s_rsum[:, None, :], rs_ck)
-            sub_sum = s_rsum[:, None, :] - rs_ck + r_ck                     # [C, md, D]
-            v_l = torch.einsum("cij,cmj->cmi", imm, r_ck)
-            v_r = self._vel(imm, r_new)[:, None, :]
-            rc = sub_sum - 0.5 * (r_ck + r_new[:, None, :])
-            turn_lv = ((v_l * rc).sum(-1) <= 0) | ((v_r * rc).sum(-1) <= 0)  # [C, md]
-            in_rng = (lvl[None, :] >= i_min[:, None]) & (lvl[None, :] <= i_max[:, None])
-            it_turn = (turn_lv & in_rng).any(1)
-            s_turn = torch.where(upd, torch.where(first, torch.zeros_like(it_turn), it_turn), s_turn)
-            s_n = torch.where(upd, s_n + 1, s_n)
-
-            # ---- subtree finished (full size, U-turn or divergence): double the tree
-            target = torch.ones_like(depth) << depth
-            done_sub = active & ((s_n >= target) | s_turn | s_div)
-            p_bias = torch.clamp(torch.exp(s_w - weight), max=1.0)
-            p_bias = torch.where(s_turn | s_div, torch.zeros_like(p_bias), p_bias)
-            take2 = done_sub & (self._rand(C, like=st.z) < p_bias)
-            zP, UP, gP = sel(take2, s_zP, zP), torch.where(take2, s_UP, UP), sel(take2, s_gP, gP)
-            mR, mL = done_sub & s_right, done_sub & ~s_right
-            zR, rR, gR = sel(mR, s_z, zR), sel(mR, s_r, rR), sel(mR, s_g, gR)
-            zL, rL, gL = sel(mL, s_z, zL), sel(mL, s_r, rL), sel(mL, s_g, gL)
-            weight = torch.where(done_sub, torch.logaddexp(weight, s_w), weight)
-            r_sum = sel(done_sub, r_sum + s_rsum, r_sum)
-            new_turn = s_turn | self._is_turning(imm, rL, rR, r_sum)
-            turning = torch.where(done_sub, new_turn, turning)
-            diverging = torch.where(done_sub, s_div, diverging)
-            sum_acc = torch.where(done_sub, sum_acc + s_acc, sum_acc)
-            nprop = torch.where(done_sub, nprop + s_n, nprop)
-            depth = torch.where(done_sub, depth + 1, depth)
-            s_n = torch.where(done_sub, torch.zeros_like(s_n), s_n)
-            finished = done_sub & ((depth >= md) | turning | diverging)
-            active = active & ~finished
-
-        accept = sum_acc / nprop.clamp(min=1).to(dt)
-        st.z, st.U, st.g = zP, UP, gP
-        st.stats = {"accept_prob": accept, "num_steps": nprop, "tree_depth": depth, "diverging": diverging,
-                    "potential_energy": UP, "rounds": rounds}
-        return st
-
-    # ------------------------------------------------------------------ warmup adaptation
-    def _adapt(self, st: NUTSState, t: int, schedule, window_idx: int) -> int:
-        num_windows = len(schedule)
-        w_end = schedule[window_idx][1]
-        if self.adapt_ss:
-            gstat = self.target - st.stats["accept_prob"]
-            st.da_t = st.da_t + 1
-            tt = st.da_t
-            st.da_gavg = (1 - 1 / (tt + 10.0)) * st.da_gavg + gstat / (tt + 10.0)
-            st.da_x = st.da_prox - torch.sqrt(tt) / 0.05 * st.da_gavg
-            wt = tt ** (-0.75)
-            st.da_xavg = (1 - wt) * st.da_xavg + wt * st.da_x
-            st.step_size = torch.exp(st.da_x.clamp(-700.0, 700.0))
-        middle = 0 < window_idx < num_windows - 1
-        if self.adapt_mm and middle:
-            st.wf_n += 1
-            d = st.z - st.wf_mean
-            st.wf_mean = st.wf_mean + d / st.wf_n
-            d2 = st.z - st.wf_mean
-            st.wf_m2 = st.wf_m2 + d[:, :, None] * d2[:, None, :]
-        if t == w_end:
-            if self.adapt_mm and middle and st.wf_n > 1:
-                n = st.wf_n
-                cov = st.wf_m2 / (n - 1)
-                D = cov.shape[-1]
-                eye = torch.eye(D, dtype=cov.dtype, device=cov.device)
-                cov = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * eye
-                if not self.dense:
-                    cov = torch.diag_embed(torch.diagonal(cov, dim1=1, dim2=2))
-                st.inv_mass = cov
-                self._wf_reset(st)
-            if self.adapt_ss:
-                st.step_size = torch.exp(st.da_xavg.clamp(-700.0, 700.0))
-                self._da_reset(st)
-            window_idx += 1
-        return window_idx
 
     def run(self, z0: torch.Tensor, num_warmup: int, num_samples: int, progress: Optional[Callable] = None):
-        """Returns (samples z [C, num_samples, D], per-sample stats dict, final state)."""
-        st = self.init(z0)
+        """Returns (samples z [C, num_samples, D], per-sample stats dict, final state namespace)."""
+        self._allocate(z0, num_samples)
+        b = self.b
+        self._g = self.gen
+        U, g = self._eval(b.z)
+        if not bool(torch.isfinite(U).all()):
+            raise RuntimeError("cannot find valid initial parameters: the potential is not finite at the "
+                               "initial position of some chain")
+        b.U.copy_(U)
+        b.g.copy_(g)
+        b.need_tree.fill_(True)
+        self._prepare_round_fn()
         schedule = build_adaptation_schedule(num_warmup) if num_warmup > 0 else []
-        w = 0
-        C, D = z0.shape
-        out = torch.empty((C, num_samples, D), dtype=z0.dtype, device=z0.device)
-        keep = {k: torch.empty((C, num_samples), dtype=torch.float64, device=z0.device)
-                for k in ("accept_prob", "num_steps", "diverging", "potential_energy")}
-        for t in range(num_warmup + num_samples):
-            st = self.step(st)
-            st.i = t + 1
-            if t < num_warmup:
-                w = self._adapt(st, t, schedule, w)
-            else:
-                k = t - num_warmup
-                out[:, k] = st.z
-                for name in keep:
-                    keep[name][:, k] = st.stats[name].to(torch.float64)
+        done = 0
+        for w, (a, e) in enumerate(schedule):
+            middle = 0 < w < len(schedule) - 1
+            self._run_window(e - a + 1, adapt=self.adapt_ss, middle=middle and self.adapt_mm, sampling=False)
+            if middle:
+                if self.adapt_mm:
+                    n = float(e - a + 1)
+                    if n > 1:
+                        cov = b.wf_m2 / (n - 1.0)
+                        eye = torch.eye(b.D, dtype=b.dtype, device=b.dev)
+                        cov = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * eye
+                        if not self.dense:
+                            cov = torch.diag_embed(torch.diagonal(cov, dim1=1, dim2=2))
+                        b.imm.copy_(cov)
+                        self._refresh_mass_sqrt()
+                    b.wf_n.zero_(); b.wf_mean.zero_(); b.wf_m2.zero_()
+                if self.adapt_ss:
+                    b.eps.copy_(torch.exp(b.da_xavg.clamp(-700.0, 700.0)))
+                    b.da_prox.copy_(torch.log(10.0 * b.eps))
+                    for t in (b.da_x, b.da_xavg, b.da_gavg, b.da_t):
+                        t.zero_()
+            done = e + 1
             if progress is not None:
-                progress(t, st)
-        return out, keep, st
+                progress(done - 1, self)
+        if schedule and self.adapt_ss:
+            b.eps.copy_(torch.exp(b.da_xavg.clamp(-700.0, 700.0)))  # final step size = averaged iterate
+        if num_samples > 0:
+            self._run_window(num_samples, adapt=False, middle=False, sampling=True)
+            if progress is not None:
+                progress(num_warmup + num_samples - 1, self)
+        self.grad_evals = int(b.n_useful)
+        self.launched_evals = self.rounds * b.C
+        stats = {k: v.clone() for k, v in b.out_stats.items()}
+        return b.out_z.clone(), stats, b
+
+    # convenience for progress lines
+    @property
+    def step_size(self):
+        return self.b.eps
+
+    @property
+    def stats(self):
+        return {"accept_prob": self.b.last_accept, "num_steps": self.b.last_steps}
 
 
 def effective_sample_size(x: torch.Tensor) -> torch.Tensor:

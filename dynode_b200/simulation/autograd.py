@@ -113,6 +113,16 @@ def _seeds(cfg: SolveConfig, B: int, device):
     return d
 
 
+def _scatter_cols(g: torch.Tensor, cols: Tuple[int, ...], K: int) -> torch.Tensor:
+    """[B, len(cols)] -> [B, K] with column j of g placed at cols[j] (no index tensors: graph-capturable)."""
+    if cols == tuple(range(K)):
+        return g[:, :K]
+    out = g.new_zeros((g.shape[0], K))
+    for j, c in enumerate(cols):
+        out[:, c] = g[:, j]
+    return out
+
+
 def _fold(x: Optional[torch.Tensor], dim, B: int):
     """[.., vmapped axis at `dim`, ..] -> rows with the vmapped axis folded into the leading one."""
     if x is None:
@@ -168,8 +178,7 @@ class EnsembleSolve(torch.autograd.Function):
             g = torch.einsum("btn,btnp->bp", g_ys, dys)
             pw = len(cfg.wrt_cols)
             if pw and ctx.needs_input_grad[1]:
-                g_theta = g.new_zeros((g.shape[0], th_shape[1]))
-                g_theta[:, list(cfg.wrt_cols)] = g[:, :pw]
+                g_theta = _scatter_cols(g[:, :pw], cfg.wrt_cols, th_shape[1])
                 if th_shape[0] == 1 and g.shape[0] > 1:
                     g_theta = g_theta.sum(0, keepdim=True)
             if cfg.y0_grad and ctx.needs_input_grad[0]:
@@ -231,8 +240,7 @@ class PoissonLoglik(torch.autograd.Function):
             g = g_lp[:, None] * grad
             pw = len(cfg.wrt_cols)
             if pw and ctx.needs_input_grad[1]:
-                g_theta = g.new_zeros((g.shape[0], th_shape[1]))
-                g_theta[:, list(cfg.wrt_cols)] = g[:, :pw]
+                g_theta = _scatter_cols(g[:, :pw], cfg.wrt_cols, th_shape[1])
                 if th_shape[0] == 1 and g.shape[0] > 1:
                     g_theta = g_theta.sum(0, keepdim=True)
             if cfg.y0_grad and ctx.needs_input_grad[0]:
@@ -258,6 +266,30 @@ class PoissonLoglik(torch.autograd.Function):
         return (lp, stats, grad), (0, 0, 0)
 
 
+_CONST_CACHE = {}
+
+
+def const_to_device(t: torch.Tensor, device) -> torch.Tensor:
+    """Device copy of a small constant host tensor, cached by content.
+
+    Models rebuild their constants on every call (`config.initializer.get_initial_state()`, python-float
+    rates, the contact matrix).  Caching the device copies keeps the per-call path free of host-to-device
+    copies, which is what lets a whole model evaluation be captured in a CUDA graph."""
+    if t.device == device:
+        return t if t.dtype == torch.float64 else t.to(torch.float64)
+    if is_transformed(t) or t.requires_grad or t.device.type != "cpu" or t.numel() > 65536:
+        return t.to(device=device, dtype=torch.float64)
+    tc = t.detach().to(torch.float64).contiguous()
+    key = (device.index, tuple(tc.shape), tc.numpy().tobytes())
+    hit = _CONST_CACHE.get(key)
+    if hit is None:
+        if len(_CONST_CACHE) > 4096:
+            _CONST_CACHE.clear()
+        hit = tc.to(device)
+        _CONST_CACHE[key] = hit
+    return hit
+
+
 def pack_inputs(model: engine.FlowModel, params: dict, y0: torch.Tensor, batched: bool, device):
     """Kernel parameter dict -> (y0 [B|1, n], theta [B|1, K], layout, wrt_cols, y0_grad, period).
 
@@ -270,7 +302,7 @@ def pack_inputs(model: engine.FlowModel, params: dict, y0: torch.Tensor, batched
         if v is None:
             continue
         width = S if kind in ("beta", "gamma", "sigma", "omega") else 1
-        v = v.to(device=device, dtype=torch.float64) if (v.device != device or v.dtype != torch.float64) else v
+        v = const_to_device(v, device)
         v = v.reshape(-1, width) if batched else v.reshape(1, width) if v.numel() == width else v.reshape(-1, width)
         cols.append(v)
         layout.append((kind, first, width))
@@ -282,8 +314,8 @@ def pack_inputs(model: engine.FlowModel, params: dict, y0: torch.Tensor, batched
     theta = torch.cat(cols, dim=1)
     period = params.get("season_period")
     if period is not None:
-        period = unwrap(period).detach().to(device=device, dtype=torch.float64).reshape(-1, 1).contiguous()
-    y0 = y0.to(device=device, dtype=torch.float64) if (y0.device != device or y0.dtype != torch.float64) else y0
+        period = const_to_device(unwrap(period).detach(), device).reshape(-1, 1).contiguous()
+    y0 = const_to_device(y0, device)
     y0 = y0.reshape(-1, model.state_size)
     return y0, theta, tuple(layout), tuple(wrt_cols), needs_grad(y0), period
 

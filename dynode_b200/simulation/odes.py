@@ -226,9 +226,9 @@ def _differentiable_setup(ode, duration_days, initial_state, ode_parameters, sol
     dev = torch.device("cuda", torch.cuda.current_device())
     saveat = build_saveat(opts.t0, duration_days, save_step, sub_save_indices)
     mask = _mask_from(saveat.indices, model.n_compartments)
-    y0 = torch.cat([c.reshape(-1).to(device=dev, dtype=torch.float64) for c in initial_state])
+    y0 = torch.cat([ag.const_to_device(c, dev).reshape(-1) for c in initial_state])
     y0r, theta, layout, wrt_cols, y0_grad, period = ag.pack_inputs(model, params, y0, False, dev)
-    payload = ag.SolvePayload(contact=None if contact is None else ag.unwrap(contact).detach().to(dev),
+    payload = ag.SolvePayload(contact=None if contact is None else ag.const_to_device(ag.unwrap(contact).detach(), dev),
                               save_ts=ag.device_grid(saveat.times, opts, dev), period=period, **payload_kw)
     cfg = ag.SolveConfig(model=model, opts_key=ag.opts_key(opts), layout=layout, wrt_cols=wrt_cols,
                          y0_grad=y0_grad, mask=mask, n_saved=model.saved_size(mask), T=len(saveat.times),
@@ -257,6 +257,23 @@ def _run_differentiable(ode, duration_days, initial_state, ode_parameters, solve
                     result=st[_lib.STAT_RESULT])
 
 
+_OBS_CACHE: Dict[int, tuple] = {}
+
+
+def _observation_constants(obs, dev, rows: int):
+    """(device observations [T-1][m], -sum lgamma(obs+1)) cached per observation object: the constant is
+    reduced on the device once, so the hot loop never synchronises on it."""
+    hit = _OBS_CACHE.get(id(obs))
+    if hit is not None and hit[0] is obs:
+        return hit[1], hit[2]
+    obs_t = torch.as_tensor(obs, dtype=torch.float64).to(dev).reshape(rows, -1).contiguous()
+    lp_const = float(-torch.lgamma(obs_t + 1.0).sum())
+    if len(_OBS_CACHE) > 64:
+        _OBS_CACHE.clear()
+    _OBS_CACHE[id(obs)] = (obs, obs_t, lp_const)
+    return obs_t, lp_const
+
+
 def simulate_incidence_loglik(ode, duration_days, initial_state, ode_parameters, solver_parameters, *,
                               compartment: int, obs, save_step: int = 1):
     """Fused NUTS hot path: log-likelihood of `obs` under
@@ -267,15 +284,15 @@ def simulate_incidence_loglik(ode, duration_days, initial_state, ode_parameters,
     from . import autograd as ag
 
     _validate_call(ode, initial_state, ode_parameters, duration_days)
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
-    obs_t = torch.as_tensor(obs, dtype=torch.float64, device=dev)
+    _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
     ncomp = len(initial_state)
     comp = int(compartment) % ncomp
-    lp_const = float(-torch.lgamma(obs_t + 1.0).sum())
+    T1 = len(build_saveat(0.0, duration_days, save_step).times) - 1
+    obs_t, lp_const = _observation_constants(obs, dev, T1)
     cfg, y0r, theta, saveat, opts = _differentiable_setup(
         ode, duration_days, initial_state, ode_parameters, solver_parameters, None, save_step,
-        obs=obs_t.reshape(len(build_saveat(0.0, duration_days, save_step).times) - 1, -1).contiguous(),
-        obs_comp=comp, lp_const=lp_const)
+        obs=obs_t, obs_comp=comp, lp_const=lp_const)
     lp, stats, _ = ag.PoissonLoglik.apply(y0r, theta, cfg)
     return lp[0]
 

@@ -126,7 +126,7 @@ def test_nuts_recovers_a_correlated_gaussian():
     assert float(extra["diverging"].sum()) == 0
     assert 0.7 < float(extra["accept_prob"].mean()) < 0.98
     assert float(split_rhat(z[:, :, 0])) < 1.05 and float(effective_sample_size(z[:, :, 0])) > 500
-    assert eng.grad_evals % 48 == 0  # counted per chain
+    assert 0 < eng.grad_evals <= eng.launched_evals  # tree leapfrogs vs rounds x chains
 
 
 def _toy_model(obs=None):
