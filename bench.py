@@ -153,6 +153,87 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def nuts_leg(args, dev, world, barrier):
+    """NUTS grad-evals/s (BASELINE metric 2) on config 2, per GPU and whole job.
+
+    kernel: dynode_poisson_loglik_grad_f64 alone on B random unconstrained draws z ~ N(0,1)^2 mapped
+            through the priors' bijectors (device-resident, CUDA events);
+    sampler: the many-chain NUTS of dynode_b200.infer on the fused model, counting the leapfrogs that
+            belong to a tree (wall clock, warm-up + sampling)."""
+    import torch
+    import torch.distributed as dist
+
+    from dynode_b200.examples import sir_infer_parameters as m
+    from dynode_b200.infer import MCMC, NUTS, ModelDensity, PRNGKey
+
+    rank = int(os.environ.get("RANK", "0"))
+    cfg = m.get_config()
+    obs = m.synthetic_incidence(100).to(dev)
+    md = ModelDensity(m.model_fused, (), dict(config=cfg, tf=100, obs_data=obs))
+    out = {"config": "C2 age-stratified SIR (n=6), 100 d, Poisson likelihood on diff(R), P=2 (beta, gamma)",
+           "unit": "grad-evals/s"}
+    # kernel-level: one launch = B (log-density, gradient) evaluations
+    Bk = 1 << 20
+    g = torch.Generator(device=dev).manual_seed(20260102 + rank)
+    Z = torch.randn(Bk, 2, dtype=torch.float64, device=dev, generator=g)
+    cons = md.constrain(Z)
+    r0, inf = cons["strains_0_r0"], cons["strains_0_infectious_period"]
+    from dynode_b200 import _lib, engine
+    from tests.cases import make_case
+    case = make_case("sir_age2", 1)
+    prm = {"beta": (r0 / inf).reshape(-1, 1).contiguous(), "gamma": (1.0 / inf).reshape(-1, 1).contiguous()}
+    y0 = torch.as_tensor(case["y0"], dtype=torch.float64, device=dev)
+    contact = torch.as_tensor(case["contact"], dtype=torch.float64, device=dev)
+    ts = np.linspace(0.0, 100.0, 101)
+    opts = engine.SolverOptions(t1=100.0)
+    wrt = [_lib.wrt_id(_lib.P_BETA, 0), _lib.wrt_id(_lib.P_GAMMA, 0)]
+
+    def kstep():
+        return engine.poisson_loglik_grad(case["model"], y0, prm, contact, opts, ts, 2, obs, 0.0, wrt=wrt, B=Bk)
+
+    for _ in range(3):
+        lp, grad, st = kstep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        lp, grad, st = kstep()
+    e1.record()
+    barrier()
+    kms = e0.elapsed_time(e1) / 5
+    if world > 1:
+        t = torch.tensor([kms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms = float(t.item())
+    n_att = float(st[:, 3].double().mean())
+    out["kernel"] = {"value": world * Bk / (kms * 1e-3), "draws_per_gpu": Bk, "ms_per_launch": kms,
+                     "mean_attempted_steps": n_att,
+                     "finite_fraction": float(torch.isfinite(lp).double().mean())}
+    # sampler-level
+    C = args.nuts_chains
+    mc = MCMC(NUTS(m.model_fused, max_tree_depth=10), num_warmup=100, num_samples=50, num_chains=C,
+              progress_bar=False)
+    barrier()
+    t0 = time.perf_counter()
+    mc.run(PRNGKey(8675314 + rank), config=cfg, tf=100, obs_data=obs)
+    barrier()
+    dt = time.perf_counter() - t0
+    evals = torch.tensor([float(mc.engine.grad_evals), dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        tot = evals.clone()
+        dist.all_reduce(tot[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot[1:], op=dist.ReduceOp.MAX)
+        evals = tot
+    s = mc.get_samples()
+    out["sampler"] = {"value": float(evals[0]) / float(evals[1]), "chains_per_gpu": C, "num_warmup": 100,
+                      "num_samples": 50, "wall_s": float(evals[1]), "rounds": mc.engine.rounds,
+                      "cuda_graph": mc.engine.graph_used,
+                      "posterior_mean_r0": float(s["strains_0_r0"].mean()),
+                      "posterior_mean_infectious_period": float(s["strains_0_infectious_period"].mean())}
+    out["value"] = out["sampler"]["value"]
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -314,6 +395,39 @@ def run_ours(args):
                "api": "dynode_b200.simulation.simulate_ensemble (pinned host in/out, chunked H2D/solve/D2H overlap)",
                "max_abs_diff_vs_device_run": chk}
 
+    # ---- all-gather of the saved trajectories (N > 1): the only collective of the path, reported beside
+    # `value`, never inside it.  Rows are gathered in place into a [world*Bg, T, n] buffer over NVLink.
+    gather = None
+    if world > 1 and not args.no_gather:
+        from dynode_b200.distributed import GatherBuffer
+        Bg = min(B, args.gather_draws)
+        gb = GatherBuffer(world * Bg, (T, ns), device=dev)
+        gb.local.copy_(ys[:Bg])
+        for _ in range(2):
+            gb.all_gather()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            gb.all_gather()
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        gbytes = Bg * T * ns * 8
+        gather = {"collective": "all_gather_into_tensor (NCCL, in place)", "draws_per_gpu": Bg,
+                  "bytes_per_rank": gbytes, "ms": gms,
+                  "busbw_gbs": gbytes * (world - 1) / (gms * 1e-3) / 1e9,
+                  "trajectories_per_s_with_gather": world * Bg / ((ms_per_step * Bg / B + gms) * 1e-3)}
+        del gb
+
+    # ---- second BASELINE metric: NUTS grad-evals/s on config 2 (age-stratified SIR, Poisson incidence
+    # likelihood, gradient w.r.t. r0 and the infectious period), fused kernel + many-chain sampler
+    nuts = None
+    if not args.no_nuts:
+        nuts = nuts_leg(args, dev, world, barrier)
+
     # ---- CPU baseline on rank 0, N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -343,6 +457,8 @@ def run_ours(args):
                               "frac": ach_tf / fp64_peak_tf, "peak_source": "dynode_probe_dfma measured in this run",
                               "algorithmic_flops_per_launch": flops_alg, "attempted_steps_total": n_att},
             "cpu_baseline": cpu,
+            "gather": gather,
+            "nuts": nuts,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line))
@@ -362,6 +478,10 @@ def main():
     ap.add_argument("--host-chunk", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU wall time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nuts", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--gather-draws", type=int, default=20000, help="draws per GPU in the all-gather leg")
+    ap.add_argument("--nuts-chains", type=int, default=4096, help="chains per GPU in the NUTS leg")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

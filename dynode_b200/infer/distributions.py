@@ -21,10 +21,11 @@ _F64 = torch.float64
 
 
 def _t(x, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Numbers become 0-dim HOST tensors: they mix with device tensors as scalars, and no host-to-device
+    copy is issued (such a copy would break CUDA-graph capture of the model evaluation)."""
     if isinstance(x, torch.Tensor):
         return x if x.dtype == _F64 else x.to(_F64)
-    dev = like.device if isinstance(like, torch.Tensor) else None
-    return torch.as_tensor(x, dtype=_F64, device=dev)
+    return torch.as_tensor(x, dtype=_F64)
 
 
 # ------------------------------------------------------------------------------ constraints

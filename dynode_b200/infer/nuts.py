@@ -336,12 +336,15 @@ class BatchedNUTS:
             self._round_fn = graph.replay
             self.graph_used = True
         except Exception as e:  # same kernels either way; say that replay is off and why
+            import traceback
             import warnings
+            self.capture_error = traceback.format_exc()
             torch.cuda.synchronize()
             self._g = self.gen
             self._round_fn = self._round
+            where = "".join(self.capture_error.splitlines(keepends=True)[-14:])
             warnings.warn(f"BatchedNUTS: CUDA-graph capture of the round failed ({type(e).__name__}: {e}); "
-                          "running rounds eagerly")
+                          f"running rounds eagerly\n{where}")
 
     # ------------------------------------------------------------------ driver
     def _refresh_mass_sqrt(self):
