@@ -55,12 +55,25 @@ struct LaneSolver {
   static constexpr int REFILL = TPW >= 8 ? TPW / 8 : 1;
   static_assert(L >= 1 && L <= 32, "a trajectory must fit one warp");
   using D = Dual<P>;
+  // Shared-memory offload: the dense-output coefficients Q (3*NE doubles, written once per step, read only
+  // by the save loop) and the per-trajectory rates + contact row live in per-thread columns of shared
+  // memory instead of registers.  Measured on B200 (profiles/r1/kernel_variants.md): +4 % for the 1-bin
+  // SEIRS lanes (seasonal C3 workload), -3 % for the 5-element SEIRS+C lane even though it then fits 16
+  // instead of 12 warps per SM -- so it is on for FLOW_SEIRS only (DYN_SMEM_OFFLOAD: -1 auto, 0 off, 1 all).
+  static constexpr bool OFFLOAD = P == 0 && (DYN_SMEM_OFFLOAD == 1 || (DYN_SMEM_OFFLOAD < 0 && FLOW == DYNODE_FLOW_SEIRS));
+  static constexpr int OFF_Q = 0, OFF_PRM = 3 * NE, OFF_K = OFF_PRM + 4, OFF_SEAS = OFF_K + G;
+  static constexpr int NOFF = OFFLOAD ? OFF_SEAS + (SEASONAL ? 3 : 0) : 1;
+  // volatile: the rates are loop-invariant, and the whole point is that they are NOT kept in registers
+  static DYN_DI double lds_v(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+  }
 
   struct Geo {  // lane geometry + the shared contact row (fixed for the whole kernel)
     int base;   // lane of cell (0,0) of my slot
     int sbase;  // lane of cell (g,0)
     int g, s;
-    double K[G];  // contact[g][:]
   };
   struct Prm {  // per-trajectory parameters of my cell
     D beta, gamma, sigma, omega, amp, phase;
@@ -119,8 +132,8 @@ struct LaneSolver {
   }
 
   // ---- right-hand side of the flow family in lane layout -------------
-  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Geo& c, const Prm& p,
-                         const D& invN) {
+  static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Geo& c, const double (&K)[G],
+                         const Prm& p, const D& invN) {
     D prop;
     if constexpr (DENSITY) {
       prop = y[II];  // tests/test_simulation/test_odes.py:23  s_to_i = beta*s*i
@@ -130,11 +143,11 @@ struct LaneSolver {
     // contact contraction: sum_b K[g][b] * prop[b, s]
     D acc;
     if constexpr (G == 1) {
-      acc = c.K[0] * prop;
+      acc = K[0] * prop;
     } else {
-      acc = c.K[0] * dual_shfl(prop, c.base + c.s);
+      acc = K[0] * dual_shfl(prop, c.base + c.s);
 #pragma unroll
-      for (int b = 1; b < G; ++b) acc = dfma(c.K[b], dual_shfl(prop, c.base + b * S + c.s), acc);
+      for (int b = 1; b < G; ++b) acc = dfma(K[b], dual_shfl(prop, c.base + b * S + c.s), acc);
     }
     D beta_t = p.beta;
     if constexpr (SEASONAL) {
@@ -185,9 +198,21 @@ struct LaneSolver {
     c.s = q - c.g * S;
     c.base = tw * L;
     c.sbase = c.base + c.g * S;
+    double Kr[G];  // contact[g][:]
 #pragma unroll
     for (int b = 0; b < G; ++b)
-      c.K[b] = a.prm.contact ? __ldg(a.prm.contact + c.g * G + b) : (b == c.g ? 1.0 : 0.0);
+      Kr[b] = a.prm.contact ? __ldg(a.prm.contact + c.g * G + b) : (b == c.g ? 1.0 : 0.0);
+    __shared__ double sm_off[NOFF][kThreads];
+    double* const my = &sm_off[0][threadIdx.x];  // value v of this thread sits at my[v * kThreads]
+    if constexpr (OFFLOAD) {
+#pragma unroll
+      for (int b = 0; b < G; ++b) my[(OFF_K + b) * kThreads] = Kr[b];
+    }
+    // the parameters of my slot's trajectory as the step loop sees them
+    auto cur_K = [&](double (&K)[G]) {
+#pragma unroll
+      for (int b = 0; b < G; ++b) K[b] = OFFLOAD ? lds_v(my + (OFF_K + b) * kThreads) : Kr[b];
+    };
     const bool slot_ok = tw < TPW;   // lanes beyond the last whole slot never own a trajectory
     const bool lead = (c.s == 0);    // owner of the replicated S_g for norms and stores
     const bool head = slot_ok && q == 0;
@@ -301,7 +326,9 @@ struct LaneSolver {
             }
           }
           const D invN0 = inv_population(yn, c);
-          rhs(a.t0, yn, fn, c, pn, invN0);  // FSAL f0 (solver.init)
+          double Kl[G];
+          cur_K(Kl);
+          rhs(a.t0, yn, fn, c, Kl, pn, invN0);  // FSAL f0 (solver.init)
           double tn;
           if (a.const_dt > 0.0) {
             tn = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
@@ -322,7 +349,7 @@ struct LaneSolver {
             const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
 #pragma unroll
             for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, fn[e], yn[e]);
-            rhs(a.t0 + h0, ys, f1, c, pn, invN0);
+            rhs(a.t0 + h0, ys, f1, c, Kl, pn, invN0);
             double p2 = 0.0;
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
@@ -335,7 +362,19 @@ struct LaneSolver {
             tn = a.t0 + fmin(100.0 * h0, h1);
           }
           if (take) {
-            prm = pn;
+            if constexpr (OFFLOAD) {
+              my[(OFF_PRM + 0) * kThreads] = pn.beta.v;
+              my[(OFF_PRM + 1) * kThreads] = pn.gamma.v;
+              my[(OFF_PRM + 2) * kThreads] = pn.sigma.v;
+              my[(OFF_PRM + 3) * kThreads] = pn.omega.v;
+              if constexpr (SEASONAL) {
+                my[(OFF_SEAS + 0) * kThreads] = pn.amp.v;
+                my[(OFF_SEAS + 1) * kThreads] = pn.phase.v;
+                my[(OFF_SEAS + 2) * kThreads] = pn.period;
+              }
+            } else {
+              prm = pn;
+            }
 #pragma unroll
             for (int e = 0; e < NE; ++e) { y[e] = yn[e]; f[0][e] = fn[e]; }
             traj = cand;
@@ -401,31 +440,61 @@ struct LaneSolver {
 
       const double h = tnext - tprev;
       const D invN = inv_population(y, c);
+      // Rates and contact row of my cell for this step.  Offloaded kernels re-read them from shared memory
+      // ONCE per step through an index the compiler cannot prove loop-invariant, so they occupy registers
+      // only while the stages run (not during the Q / error / save phases where pressure peaks) and the
+      // loads issue early, under the 1/N_g computation.
+      Prm pl;
+      double Kl[G];
+      if constexpr (OFFLOAD) {
+        int o = 0;
+        asm volatile("" : "+r"(o));  // opaque zero
+        const double* src = my + o;
+        pl.beta.v = src[(OFF_PRM + 0) * kThreads];
+        pl.gamma.v = src[(OFF_PRM + 1) * kThreads];
+        pl.sigma.v = src[(OFF_PRM + 2) * kThreads];
+        pl.omega.v = src[(OFF_PRM + 3) * kThreads];
+        if constexpr (SEASONAL) {
+          pl.amp.v = src[(OFF_SEAS + 0) * kThreads];
+          pl.phase.v = src[(OFF_SEAS + 1) * kThreads];
+          pl.period = src[(OFF_SEAS + 2) * kThreads];
+        } else {
+          pl.amp.v = pl.phase.v = 0.0;
+          pl.period = 1.0;
+        }
+#pragma unroll
+        for (int b = 0; b < G; ++b) Kl[b] = src[(OFF_K + b) * kThreads];
+      } else {
+        pl = prm;
+#pragma unroll
+        for (int b = 0; b < G; ++b) Kl[b] = Kr[b];
+      }
+      auto stage_rhs = [&](double t, D (&out)[NE]) { rhs(t, ys, out, c, Kl, pl, invN); };
       // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, T5_a21 * f[0][e], y[e]);
-      rhs(fma(T5_c2, h, tprev), ys, f[1], c, prm, invN);
+      stage_rhs(fma(T5_c2, h, tprev), f[1]);
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(T5_a32, f[1][e], T5_a31 * f[0][e]), y[e]);
-      rhs(fma(T5_c3, h, tprev), ys, f[2], c, prm, invN);
+      stage_rhs(fma(T5_c3, h, tprev), f[2]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a43, f[2][e], dfma(T5_a42, f[1][e], T5_a41 * f[0][e])), y[e]);
-      rhs(fma(T5_c4, h, tprev), ys, f[3], c, prm, invN);
+      stage_rhs(fma(T5_c4, h, tprev), f[3]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a54, f[3][e], dfma(T5_a53, f[2][e], dfma(T5_a52, f[1][e], T5_a51 * f[0][e]))), y[e]);
-      rhs(fma(T5_c5, h, tprev), ys, f[4], c, prm, invN);
+      stage_rhs(fma(T5_c5, h, tprev), f[4]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a65, f[4][e], dfma(T5_a64, f[3][e], dfma(T5_a63, f[2][e],
                      dfma(T5_a62, f[1][e], T5_a61 * f[0][e])))), y[e]);
-      rhs(tnext, ys, f[5], c, prm, invN);
+      stage_rhs(tnext, f[5]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a76, f[5][e], dfma(T5_a75, f[4][e], dfma(T5_a74, f[3][e], dfma(T5_a73, f[2][e],
                      dfma(T5_a72, f[1][e], T5_a71 * f[0][e]))))), y[e]);
-      rhs(tnext, ys, f[6], c, prm, invN);  // ys is y1
+      stage_rhs(tnext, f[6]);  // ys is y1
 
       // ---- dense-output coefficients, formed unconditionally right after the last stage so their
       // independent FMAs overlap the latency-bound error-norm / controller chain below.
@@ -439,7 +508,11 @@ struct LaneSolver {
           D acc = kDense[0][m + 1] * f[0][e];
 #pragma unroll
           for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
-          Q[m][e] = acc;
+          if constexpr (OFFLOAD) {
+            my[(OFF_Q + m * NE + e) * kThreads] = acc.v;
+          } else {
+            Q[m][e] = acc;
+          }
         }
       }
 
@@ -483,8 +556,16 @@ struct LaneSolver {
         const double inv_h = rcp_fast((tnext == tprev) ? 1.0 : h);
         const double hw = h * kDense[0][0];
         auto dense = [&](int e, double th, double hthw, double hth2) -> D {
-          D u = dfma(th, Q[2][e], Q[1][e]);
-          u = dfma(th, u, Q[0][e]);
+          D q0, q1, q2;
+          if constexpr (OFFLOAD) {
+            q0 = make_dual<P>(my[(OFF_Q + 0 * NE + e) * kThreads]);
+            q1 = make_dual<P>(my[(OFF_Q + 1 * NE + e) * kThreads]);
+            q2 = make_dual<P>(my[(OFF_Q + 2 * NE + e) * kThreads]);
+          } else {
+            q0 = Q[0][e]; q1 = Q[1][e]; q2 = Q[2][e];
+          }
+          D u = dfma(th, q2, q1);
+          u = dfma(th, u, q0);
           return dfma(hth2, u, dfma(hthw, f[0][e], y[e]));
         };
         if (MODE == MODE_SAVE && P == 0 && full_save) {
@@ -621,7 +702,12 @@ cudaError_t launch_lane_solver(const SolveArgs& a_in, cudaStream_t stream) {
   a.chunk = (a.B + warps - 1) / warps;
   warps = (a.B + a.chunk - 1) / a.chunk;
   const int64_t grid = (warps + wpc - 1) / wpc;
-  kern<<<(unsigned)grid, kThreads, 0, stream>>>(a);
+  // tuning knob: DYNODE_DEBUG_SMEM=<bytes> of unused dynamic shared memory per CTA lowers the number of
+  // resident CTAs (occupancy experiments, profiles/r1/occupancy.md); 0 in production
+  static const int debug_smem = [] { const char* v = getenv("DYNODE_DEBUG_SMEM"); return v ? atoi(v) : 0; }();
+  if (debug_smem > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, debug_smem);
+  kern<<<(unsigned)grid, kThreads, debug_smem, stream>>>(a);
   return cudaGetLastError();
 }
 

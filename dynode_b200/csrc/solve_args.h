@@ -18,6 +18,10 @@ constexpr int kThreads = DYN_THREADS;  // warps per CTA = kThreads / 32
 constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
 constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
 
+#ifndef DYN_SMEM_OFFLOAD
+#define DYN_SMEM_OFFLOAD (-1)
+#endif
+
 #ifndef DYN_OVERSUBSCRIBE
 #define DYN_OVERSUBSCRIBE 1
 #endif

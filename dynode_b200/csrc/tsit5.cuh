@@ -169,24 +169,21 @@ __device__ __forceinline__ double controller_factor(double err, bool keep) {
 // square root.  Seed from the SFU in fp32, two Newton steps z <- z*(1.1 - 0.1*x*z^10) in fp64.
 // Clip thresholds in err^2: err <= 5e-6 -> 2.5e-11, err >= 2000 -> 4e6.
 __device__ __forceinline__ double controller_factor_sq(double err2, bool keep) {
-  double factor;
-  if (err2 <= 2.5e-11) {
-    factor = 10.0;
-  } else if (!(err2 < 4.0e6)) {
-    factor = 0.2;
-  } else {
-    double z = (double)exp2f(-0.1f * __log2f((float)err2));
+  // Branch-free: the root is always taken on err^2 clamped into [2.5e-11, 4e6]; at the clamp ends
+  // 0.9 * x^(-1/10) is 10.3 resp. 0.197, i.e. already outside [lo, 10], so the final clip returns exactly
+  // what the three-way branch did (NaN / inf -> upper clamp -> 0.2 on the rejected step).
+  const double x = !(err2 < 4.0e6) ? 4.0e6 : fmax(err2, 2.5e-11);
+  double z = (double)exp2f(-0.1f * __log2f((float)x));
+  const double mx = -0.1 * x;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const double z2 = z * z;
-      const double z4 = z2 * z2;
-      const double z5 = z4 * z;
-      z = z * fma(-0.1 * err2, z5 * z5, 1.1);
-    }
-    factor = 0.9 * z;
+  for (int it = 0; it < 2; ++it) {
+    const double z2 = z * z;
+    const double z4 = z2 * z2;
+    const double z5 = z4 * z;
+    z = z * fma(mx, z5 * z5, 1.1);
   }
   const double lo = keep ? 1.0 : 0.2;
-  return fmin(fmax(factor, lo), 10.0);
+  return fmin(fmax(0.9 * z, lo), 10.0);
 }
 
 }  // namespace tsit5
