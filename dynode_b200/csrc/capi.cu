@@ -26,7 +26,7 @@ typedef cudaError_t (*LaunchFn)(const SolveArgs&, cudaStream_t);
 
 struct Instance {
   int flow, flags, g, s, chunk;
-  LaunchFn save0, saveP, lik0, likP;
+  LaunchFn save0, saveP, lik0, likP, saveJ;
 };
 
 #define X(IDX, FLOW, FLAGS, G, S)                                                        \
@@ -34,7 +34,8 @@ struct Instance {
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_SAVE>,                                 \
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_SAVE>,               \
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK>,                               \
-   &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK>},
+   &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK>,             \
+   &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_SAVE_JUMPS>},
 static const Instance kInstances[] = {
 #include "instances.def"
 };
@@ -76,6 +77,10 @@ static int check_common(const DynodeModelDesc* model, const DynodeSolverDesc* sv
   if (!(sv->t1 >= sv->t0)) return fail("t1 must be >= t0");
   if (!(sv->const_dt > 0.0) && !(sv->rtol > 0.0 && sv->atol > 0.0)) return fail("rtol/atol must be positive");
   if (sv->max_steps <= 0) return fail("max_steps must be positive");
+  if (sv->n_jump < 0 || sv->n_jump > kMaxJumps) return fail("n_jump must be in [0, %d]", kMaxJumps);
+  if (sv->n_jump > 0 && !sv->jump_ts) return fail("jump_ts is null");
+  if (sv->n_jump > 0 && sv->const_dt > 0.0)
+    return fail("discontinuity points apply to the adaptive controller only (odes.py:115-131)");
   return 0;
 }
 
@@ -89,6 +94,8 @@ static void fill_common(SolveArgs& a, const DynodeSolverDesc* sv, int64_t B, Dyn
   a.T = T;
   a.t0 = sv->t0; a.t1 = sv->t1; a.rtol = sv->rtol; a.atol = sv->atol; a.const_dt = sv->const_dt;
   a.save_dt = sv->save_dt > 0.0 ? sv->save_dt : 0.0;
+  a.jump_ts = sv->n_jump > 0 ? sv->jump_ts : nullptr;
+  a.n_jump = sv->n_jump > 0 ? sv->n_jump : 0;
   a.max_steps = (int32_t)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.write_primal = 1;
   a.wrt[0] = a.wrt[1] = -1;
@@ -109,9 +116,11 @@ static int run_passes(const Instance* inst, SolveArgs& a, int32_t n_wrt, const i
                       cudaStream_t stream) {
   if (a.B == 0) return 0;
   cudaError_t e;
+  if (a.n_jump > 0 && (n_wrt > 0 || loglik))
+    return fail("unsupported: discontinuity points together with sensitivities / the fused log-likelihood");
   if (n_wrt == 0) {
     a.P_total = 0;
-    e = (loglik ? inst->lik0 : inst->save0)(a, stream);
+    e = (loglik ? inst->lik0 : (a.n_jump > 0 ? inst->saveJ : inst->save0))(a, stream);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
   }

@@ -50,6 +50,8 @@ struct LaneSolver {
   // Persistent slots pay off only where many slots share a warp (measured on B200, profiles/
   // r1_tuning.md: +11% for 32 slots, -8% for the 5-slot multi-strain case whose step counts are
   // tight); otherwise a warp integrates one generation of TPW trajectories.
+  static constexpr bool JUMPS = MODE == MODE_SAVE_JUMPS;
+  static constexpr bool IS_SAVE = MODE != MODE_LOGLIK;
   static constexpr bool PERSIST = TPW >= 8;
   // refill as soon as this many slots are idle (masked re-initialisation costs ~1.5 steps)
   static constexpr int REFILL = TPW >= 8 ? TPW / 8 : 1;
@@ -186,6 +188,20 @@ struct LaneSolver {
 
   static DYN_DI double sq(double x) { return x * x; }
 
+  // ClipStepSizeController(jump_ts): a step [t0, t1] that would contain a discontinuity point ends just
+  // before it.  i0 = #{jump <= t0}, i1 = #{jump <= t1}; a jump lies in (t0, t1] iff
+  // i0 < i1, and then t1 <- prevbefore(jump[i0]).
+  static DYN_DI double clip_to_jumps(const SolveArgs& a, double t0, double t1, bool& made_jump) {
+    int i0 = 0, i1 = 0;
+    for (int k = 0; k < a.n_jump; ++k) {
+      const double j = __ldg(a.jump_ts + k);
+      i0 += (j <= t0);
+      i1 += (j <= t1);
+    }
+    made_jump = i0 < i1;
+    return made_jump ? nextafter(__ldg(a.jump_ts + (i0 < a.n_jump ? i0 : a.n_jump - 1)), -CUDART_INF) : t1;
+  }
+
   // ---- the kernel body ------------------------------------------------------------------
   static __device__ void run(const SolveArgs& a) {
     using namespace tsit5;
@@ -261,6 +277,7 @@ struct LaneSolver {
     double tprev = t1, tnext = t1;
     int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
     bool active = false;
+    bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
     double* out_s = a.ys;  // running output pointers of the full-save fast path
     double* out_c = a.ys;
     D lp_acc = make_dual<P>(0.0), obs_prev = make_dual<P>(0.0);
@@ -379,6 +396,7 @@ struct LaneSolver {
             for (int e = 0; e < NE; ++e) { y[e] = yn[e]; f[0][e] = fn[e]; }
             traj = cand;
             tprev = a.t0;
+            if constexpr (JUMPS) tn = clip_to_jumps(a, a.t0, tn, made_jump);
             tnext = fmin(tn, t1);
             n_acc = n_rej = n_steps = 0;
             save_i = 0;
@@ -395,7 +413,7 @@ struct LaneSolver {
     // ================= retire slots whose trajectory is complete (or ran out of steps) ==========
     auto retire = [&](bool fin) {
       if (__any_sync(0xffffffffu, fin)) {
-        if constexpr (MODE == MODE_SAVE) {
+        if constexpr (IS_SAVE) {
           if (fin && a.write_primal) {
             // slots never reached keep diffrax's +inf fill
             for (int k = save_i; k < a.T; ++k) {
@@ -545,7 +563,13 @@ struct LaneSolver {
         dt_next = h * controller_factor_sq(err2, keep);
       }
       double ntprev = keep ? tnext : tprev;
+      bool next_made_jump = false;
+      if constexpr (JUMPS) {
+        // a kept step that ended just before a jump restarts exactly at the jump (nextafter), see a8
+        if (keep && made_jump) ntprev = nextafter(tnext, CUDART_INF);
+      }
       double ntnext = ntprev + dt_next;
+      if constexpr (JUMPS) ntnext = clip_to_jumps(a, ntprev, ntnext, next_made_jump);
       ntprev = fmin(ntprev, t1);
       if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);  // _clip_to_end
 
@@ -568,7 +592,7 @@ struct LaneSolver {
           u = dfma(th, u, q0);
           return dfma(hth2, u, dfma(hthw, f[0][e], y[e]));
         };
-        if (MODE == MODE_SAVE && P == 0 && full_save) {
+        if (IS_SAVE && P == 0 && full_save) {
           // fast path: every compartment saved -> compile-time offsets off two running pointers
           while (true) {
             const bool pend = ts_next <= tnext;
@@ -593,7 +617,7 @@ struct LaneSolver {
             if (pend) {
               const double th = (ts_next - tprev) * inv_h;
               const double hthw = hw * th, hth2 = (h * th) * th;
-              if constexpr (MODE == MODE_SAVE) {
+              if constexpr (IS_SAVE) {
                 const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
@@ -645,6 +669,20 @@ struct LaneSolver {
         }
         tprev = ntprev;
         tnext = ntnext;
+      }
+      if constexpr (JUMPS) {
+        // no FSAL across a discontinuity: f0 is re-evaluated at (jump, y1) for the slots that crossed one
+        const bool crossed = stepping && keep && made_jump;
+        if (__any_sync(0xffffffffu, crossed)) {
+          D fj[NE];
+          const D invNj = inv_population(y, c);
+          rhs(tprev, y, fj, c, Kl, pl, invNj);
+          if (crossed) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) f[0][e] = fj[e];
+          }
+        }
+        if (stepping) made_jump = next_made_jump;
       }
       const bool done = !((tprev < t1) && (n_steps < a.max_steps));
       if constexpr (PERSIST) {

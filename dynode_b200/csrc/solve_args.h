@@ -17,6 +17,8 @@ constexpr int tangent_chunk(int flow) { return flow == DYNODE_FLOW_SIR ? 2 : 1; 
 constexpr int kThreads = DYN_THREADS;  // warps per CTA = kThreads / 32
 constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
 constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
+constexpr int MODE_SAVE_JUMPS = 2;  // MODE_SAVE with ClipStepSizeController(jump_ts) step clipping (P == 0)
+constexpr int kMaxJumps = 32;
 
 #ifndef DYN_SMEM_OFFLOAD
 #define DYN_SMEM_OFFLOAD (-1)
@@ -41,6 +43,9 @@ struct SolveArgs {
   double* ys;      // [B][T][n_saved]   (written when write_primal)
   int32_t* stats;  // [B][4]            (written when write_primal)
   int32_t write_primal;
+  // discontinuity points (SolverParams.discontinuity_points -> jump_ts), sorted ascending, device memory
+  const double* jump_ts;
+  int32_t n_jump;
   // sensitivities: this pass carries directions p0 .. p0+P-1 of P_total
   int32_t P_total, p0;
   int32_t wrt[kPMax];

@@ -63,10 +63,27 @@ class SolverOptions:
     atol: float = 1e-6
     const_dt: float = 0.0
     max_steps: int = 10**6
+    jump_ts: Tuple[float, ...] = ()  # SolverParams.discontinuity_points
 
     def desc(self, save_dt: float = 0.0) -> _lib.SolverDesc:
-        return _lib.SolverDesc(float(self.t0), float(self.t1), float(self.rtol), float(self.atol),
-                               float(self.const_dt), int(self.max_steps), float(save_dt))
+        d = _lib.SolverDesc(float(self.t0), float(self.t1), float(self.rtol), float(self.atol),
+                            float(self.const_dt), int(self.max_steps), float(save_dt), None, 0)
+        if len(self.jump_ts) > 0:
+            dev_t = _jump_tensor(tuple(sorted(float(x) for x in self.jump_ts)))
+            d.jump_ts, d.n_jump = dev_t.data_ptr(), int(dev_t.numel())
+            self._keep = dev_t  # keeps the device copy alive across the launch
+        return d
+
+
+_JUMP_CACHE: Dict[tuple, object] = {}
+
+
+def _jump_tensor(ts: tuple):
+    torch = _lib.require_cuda()
+    key = (torch.cuda.current_device(), ts)
+    if key not in _JUMP_CACHE:
+        _JUMP_CACHE[key] = torch.tensor(ts, dtype=torch.float64, device="cuda")
+    return _JUMP_CACHE[key]
 
 
 def uniform_save_dt(save_ts, t0: float, t1: float) -> float:

@@ -55,7 +55,7 @@ class SolveConfig:
     """Static (non-tensor) part of a solve: hashable, shared by forward / backward / the vmap rule."""
 
     model: engine.FlowModel
-    opts_key: Tuple  # (t0, t1, rtol, atol, const_dt, max_steps)
+    opts_key: Tuple  # (t0, t1, rtol, atol, const_dt, max_steps, jump_ts)
     layout: Tuple[Tuple[str, int, int], ...]  # (kind, first column in theta, width)
     wrt_cols: Tuple[int, ...]  # theta columns that carry a tangent direction
     y0_grad: bool
@@ -66,8 +66,9 @@ class SolveConfig:
     payload: "SolvePayload" = None
 
     def opts(self) -> engine.SolverOptions:
-        t0, t1, rtol, atol, const_dt, max_steps = self.opts_key
-        return engine.SolverOptions(t1=t1, t0=t0, rtol=rtol, atol=atol, const_dt=const_dt, max_steps=max_steps)
+        t0, t1, rtol, atol, const_dt, max_steps, jumps = self.opts_key
+        return engine.SolverOptions(t1=t1, t0=t0, rtol=rtol, atol=atol, const_dt=const_dt, max_steps=max_steps,
+                                    jump_ts=jumps)
 
     def wrt_ids(self):
         ids = []
@@ -322,7 +323,7 @@ def pack_inputs(model: engine.FlowModel, params: dict, y0: torch.Tensor, batched
 
 def opts_key(opts: engine.SolverOptions) -> Tuple:
     return (float(opts.t0), float(opts.t1), float(opts.rtol), float(opts.atol), float(opts.const_dt),
-            int(opts.max_steps))
+            int(opts.max_steps), tuple(opts.jump_ts))
 
 
 _TS_CACHE = {}

@@ -89,10 +89,8 @@ def _solver_options(solver_parameters, duration_days) -> engine.SolverOptions:
         raise UnsupportedODEError(
             f"solver {type(solver_parameters.solver_method).__name__} is not implemented on the device; "
             "only Tsit5 is (reference default, config/params.py:28-34)")
-    if len(solver_parameters.discontinuity_points) > 0:
-        raise UnsupportedODEError(
-            "discontinuity_points (ClipStepSizeController jump_ts) are not implemented on the device yet")
     return engine.SolverOptions(
+        jump_ts=tuple(float(x) for x in solver_parameters.discontinuity_points),
         t0=0.0, t1=float(duration_days), rtol=solver_parameters.ode_solver_rel_tolerance,
         atol=solver_parameters.ode_solver_abs_tolerance,
         const_dt=float(solver_parameters.constant_step_size), max_steps=int(solver_parameters.max_steps))

@@ -63,6 +63,10 @@ typedef struct {
    * save_ts[T-1] == t1 bit-for-bit (build_saveat's linspace grid); the kernel then generates the
    * save times arithmetically instead of loading them.  0 = read save_ts. */
   double save_dt;
+  /* SolverParams.discontinuity_points (odes.py:120-131: ClipStepSizeController(jump_ts)): n_jump <= 32
+   * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none. */
+  const double* jump_ts;
+  int32_t n_jump;
 } DynodeSolverDesc;
 
 /* An ensemble array: element (b, k) lives at ptr[b*batch_stride + k]; batch_stride == 0 shares

@@ -295,7 +295,20 @@ struct SolveCfg {
   int64_t max_steps;
   const double* save_ts; int T;
   const int32_t* save_idx; int n_saved;
+  const double* jump_ts; int n_jump;  // SolverParams.discontinuity_points (odes.py:120-131), sorted
 };
+
+// ClipStepSizeController(jump_ts): with i0 = #{jump <= t0} and i1 = #{jump <= t1}
+// (searchsorted side="right"), a jump lies in (t0, t1] iff i0 < i1; the step then ends at
+// prevbefore(jump[i0]) and the NEXT accepted step starts at nextafter(that) == the jump itself, with the
+// FSAL derivative re-evaluated there.
+inline double clip_to_jumps(const SolveCfg& c, double t0, double t1, bool& made_jump) {
+  int i0 = 0, i1 = 0;
+  for (int k = 0; k < c.n_jump; ++k) { i0 += (c.jump_ts[k] <= t0); i1 += (c.jump_ts[k] <= t1); }
+  made_jump = i0 < i1;
+  if (!made_jump) return t1;
+  return std::nextafter(c.jump_ts[std::min(i0, c.n_jump - 1)], -std::numeric_limits<double>::infinity());
+}
 
 // Hairer-Wanner initial step (diffrax PIDController._select_initial_step).
 template <class T>
@@ -346,6 +359,8 @@ void solve_one(int fam, Dims dm, const SolveCfg& c, const Dual<P>* y0, const Dua
     double dt0 = select_initial_step<T>(fam, dm, n, c, y.data(), f[0].data(), th, sh);
     tnext = c.t0 + dt0;
   }
+  bool made_jump = false;
+  if (c.n_jump > 0 && !(c.const_dt > 0.0)) tnext = clip_to_jumps(c, c.t0, tnext, made_jump);
   tnext = std::min(tnext, c.t1);
   int64_t num_steps = 0; int32_t n_acc = 0, n_rej = 0; int save_i = 0;
 
@@ -390,7 +405,11 @@ void solve_one(int fam, Dims dm, const SolveCfg& c, const Dual<P>* y0, const Dua
       dt_next = h * factor;
     }
     double ntprev = keep ? tnext : tprev;
+    bool next_made_jump = false;
+    const bool jumps = c.n_jump > 0 && !(c.const_dt > 0.0);
+    if (jumps && keep && made_jump) ntprev = std::nextafter(tnext, inf);
     double ntnext = ntprev + dt_next;
+    if (jumps) ntnext = clip_to_jumps(c, ntprev, ntnext, next_made_jump);
     ntprev = std::min(ntprev, c.t1);
     // _clip_to_end
     if (ntnext > c.t1 - 1e-10) ntnext = keep ? c.t1 : ntprev + 0.5 * (c.t1 - ntprev);
@@ -415,9 +434,11 @@ void solve_one(int fam, Dims dm, const SolveCfg& c, const Dual<P>* y0, const Dua
         ++save_i;
       }
       y = y1; f[0] = f[6];
+      if (jumps && made_jump) rhs<T>(fam, dm, ntprev, y.data(), th, sh, f[0].data());  // no FSAL across a jump
     } else {
       n_rej += 1;
     }
+    if (jumps) made_jump = next_made_jump;
     tprev = ntprev; tnext = ntnext;
   }
   stats[0] = (tprev < c.t1) ? 1 : 0;  // 1 = max_steps reached
@@ -485,10 +506,10 @@ int oracle_solve(int fam, int A, int R, int S, int64_t B, const double* y0, int6
                  double rtol, double atol, int64_t max_steps, double const_dt,
                  const double* save_ts, int T, const int32_t* save_idx, int n_saved, int n_wrt,
                  const int32_t* wrt, const double* dy0, double* ys, double* dys, int32_t* stats,
-                 int nthreads) {
+                 int nthreads, const double* jump_ts, int n_jump) {
   Dims dm{A, R, S};
   if (state_size(fam, dm) < 0 || A * R > MAXG || S > MAXS) return 1;
-  SolveCfg c{t0, t1, rtol, atol, const_dt, max_steps, save_ts, T, save_idx, n_saved};
+  SolveCfg c{t0, t1, rtol, atol, const_dt, max_steps, save_ts, T, save_idx, n_saved, jump_ts, n_jump};
 #define ORC_CASE(PP) case PP: return solve_batch<PP>(fam, dm, c, B, y0, y0_bs, theta, th_bs, shared, \
                                                     wrt, dy0, ys, dys, stats, nthreads);
   switch (n_wrt) {

@@ -48,6 +48,7 @@ def lib() -> ctypes.CDLL:
             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
             ctypes.c_int64, ctypes.c_double,
             dp, ctypes.c_int, ip, ctypes.c_int, ctypes.c_int, ip, dp, dp, dp, ip, ctypes.c_int,
+            dp, ctypes.c_int,
         ]
         L.oracle_rhs.restype = ctypes.c_int
         L.oracle_rhs.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, dp, dp, dp, dp]
@@ -112,7 +113,8 @@ def rhs(family: int, dims, t: float, y, theta, shared=None) -> np.ndarray:
 def solve(family: int, dims, y0, theta, shared=None, *, t1, t0: float = 0.0, rtol: float = 1e-5,
           atol: float = 1e-6, max_steps: int = 10**6, const_dt: float = 0.0,
           save_ts: Optional[np.ndarray] = None, save_idx: Optional[Sequence[int]] = None,
-          wrt: Sequence[int] = (), dy0: Optional[np.ndarray] = None, nthreads: int = 0):
+          wrt: Sequence[int] = (), dy0: Optional[np.ndarray] = None, nthreads: int = 0,
+          jump_ts: Sequence[float] = ()):
     """Batched solve.  y0: (B, n) or (n,) shared; theta: (B, P) or (P,) shared.
 
     Returns (ys[B,T,n_saved], dys[B,T,n_saved,n_wrt] or None, stats[B,4]) with
@@ -149,7 +151,8 @@ def solve(family: int, dims, y0, theta, shared=None, *, t1, t0: float = 0.0, rto
     rc = lib().oracle_solve(family, *dims, B, _dp(y0), y0_bs, _dp(theta), th_bs, _dp(sh),
                             float(t0), float(t1), rtol, atol, int(max_steps), float(const_dt),
                             _dp(save_ts), T, _ip(sidx), ns, P, _ip(wrt_a), _dp(dy0), _dp(ys),
-                            _dp(dys), _ip(stats), int(nthreads))
+                            _dp(dys), _ip(stats), int(nthreads),
+                            _dp(_c(sorted(jump_ts))) if len(jump_ts) else None, len(jump_ts))
     if rc != 0:
         raise ValueError(f"oracle_solve failed rc={rc}")
     return ys, dys, stats

@@ -70,7 +70,7 @@ def _rms(x):
 
 
 def solve(ode, y0_tuple, args, t1, *, t0=0.0, rtol=1e-5, atol=1e-6, max_steps=10**6,
-          const_dt=0.0, save_ts=None, return_steps=False):
+          const_dt=0.0, save_ts=None, return_steps=False, jump_ts=()):
     """Integrate `ode(t, state_tuple, args) -> tuple` from t0 to t1.
 
     Returns (ys_tuple with leading time axis, stats dict).  Unreached save slots stay inf.
@@ -111,6 +111,19 @@ def solve(ode, y0_tuple, args, t1, *, t0=0.0, rtol=1e-5, atol=1e-6, max_steps=10
         md = max(d1, d2)
         h1 = max(1e-6, h0 * 1e-3) if md <= 1e-15 else (0.01 / md) ** (1 / 5)
         tnext = tprev + min(100 * h0, h1)
+    jumps = np.sort(np.asarray(jump_ts, dtype=np.float64)) if (len(jump_ts) and not const_dt > 0) else None
+
+    def clip_to_jumps(a, b):
+        """ClipStepSizeController(jump_ts): searchsorted(side='right') indices of a and b; a jump in (a, b]
+        ends the step at prevbefore(jump)."""
+        i0, i1 = np.searchsorted(jumps, a, side="right"), np.searchsorted(jumps, b, side="right")
+        if i0 < i1:
+            return float(np.nextafter(jumps[min(i0, jumps.size - 1)], -np.inf)), True
+        return b, False
+
+    made_jump = False
+    if jumps is not None:
+        tnext, made_jump = clip_to_jumps(tprev, tnext)
     tnext = min(tnext, t1)
     n_steps = n_acc = n_rej = 0
     si = 0
@@ -139,7 +152,12 @@ def solve(ode, y0_tuple, args, t1, *, t0=0.0, rtol=1e-5, atol=1e-6, max_steps=10
             factor = float(np.clip(0.9 * inv ** 0.2, 1.0 if keep else 0.2, 10.0))
             dt = h * factor
         ntprev = tnext if keep else tprev
+        next_made_jump = False
+        if jumps is not None and keep and made_jump:
+            ntprev = float(np.nextafter(tnext, np.inf))
         ntnext = ntprev + dt
+        if jumps is not None:
+            ntnext, next_made_jump = clip_to_jumps(ntprev, ntnext)
         ntprev = min(ntprev, t1)
         if ntnext > t1 - 1e-10:
             ntnext = t1 if keep else ntprev + 0.5 * (t1 - ntprev)
@@ -152,8 +170,12 @@ def solve(ode, y0_tuple, args, t1, *, t0=0.0, rtol=1e-5, atol=1e-6, max_steps=10
                 si += 1
             steps.append((tprev, tnext))
             y, f0 = y1, fl
+            if jumps is not None and made_jump:
+                f0 = f(ntprev, y)  # no FSAL across a jump
         else:
             n_rej += 1
+        if jumps is not None:
+            made_jump = next_made_jump
         tprev, tnext = ntprev, ntnext
     stats = dict(result=int(tprev < t1), num_accepted_steps=n_acc, num_rejected_steps=n_rej,
                  num_steps=n_steps)

@@ -70,7 +70,7 @@ def test_unsupported_model_fails_loudly_without_touching_the_gpu(lib):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SEIRS_C, 0, 5, 7)
     assert lib.dynode_is_supported(ctypes.byref(d)) == 0
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)
@@ -88,11 +88,13 @@ def test_unsupported_model_fails_loudly_without_touching_the_gpu(lib):
     (lambda sv, prm: setattr(sv, "rtol", 0.0), "rtol/atol"),
     (lambda sv, prm: setattr(sv, "max_steps", 0), "max_steps"),
     (lambda sv, prm: setattr(prm, "gamma", __import__("dynode_b200")._lib.Array(None, 0)), "beta/gamma"),
+    (lambda sv, prm: setattr(sv, "n_jump", 99), "n_jump"),
+    (lambda sv, prm: setattr(sv, "n_jump", 2), "jump_ts is null"),
 ])
 def test_argument_validation_messages(lib, mutate, needle):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SIR, 0, 1, 1)
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)
@@ -107,7 +109,7 @@ def test_argument_validation_messages(lib, mutate, needle):
 def test_empty_ensemble_is_a_no_op(lib):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SIR, 0, 1, 1)
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)

@@ -166,3 +166,18 @@ def test_fused_poisson_loglik_and_gradient(name, obs_comp, wrt_e, wrt_o):
     if wrt_e:
         g = grad.cpu().numpy()
         assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
+
+
+@pytest.mark.parametrize("name", ["seirs_seasonal", "seirs_multi_a2s3", "sir_age2"])
+def test_discontinuity_points_match_oracle(name):
+    """SolverParams.discontinuity_points -> ClipStepSizeController(jump_ts) (reference odes.py:120-131)."""
+    B = 131
+    case = make_case(name, B)
+    t1 = min(case["t1"], 200)
+    jumps = (30.0, 100.5, 150.0)
+    ys, _, st = _run_engine(case, t1, opts=dict(jump_ts=jumps))
+    ref, _, rst = _run_oracle(case, t1, jump_ts=jumps)
+    assert np.array_equal(st, rst) and np.all(st[:, 0] == 0)
+    _assert_close(ys, ref)
+    ys0, _, st0 = _run_engine(case, t1)
+    assert not np.array_equal(st, st0)
