@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "dynode_version", "dynode_last_error", "dynode_state_size", "dynode_num_compartments",
     "dynode_saved_size", "dynode_is_supported", "dynode_solve_f64", "dynode_solve_sens_f64",
     "dynode_poisson_loglik_grad_f64", "dynode_probe_dfma", "dynode_probe_hbm_write",
+    "dynode_nuts_round_pre", "dynode_nuts_round_post",
 )
 
 
@@ -52,6 +53,21 @@ class Params(ctypes.Structure):
     _fields_ = [("beta", Array), ("gamma", Array), ("sigma", Array), ("omega", Array),
                 ("season_amp", Array), ("season_phase", Array), ("season_period", Array),
                 ("contact", ctypes.c_void_p)]
+
+
+_NUTS_PTRS = (
+    "z U g eps imm msqrt k nwin active need_tree f_adapt f_middle f_sampling energy0 "
+    "zL rL gL zR rR gR zP gP r_sum UP weight sum_acc depth nprop turning diverging "
+    "s_n s_right s_turn s_div s_z s_r s_g s_zP s_gP s_rsum s_UP s_w s_acc r_ck rs_ck z_new r_half "
+    "da_x da_xavg da_gavg da_t da_prox wf_n wf_mean wf_m2 out_z out_accept out_steps out_div out_energy "
+    "out_depth last_accept last_steps n_leap").split()
+
+
+class NutsState(ctypes.Structure):
+    """DynodeNutsState of include/dynode_b200_nuts.h (field order is the header's)."""
+
+    _fields_ = ([("C", ctypes.c_int32), ("D", ctypes.c_int32), ("max_depth", ctypes.c_int32), ("N", ctypes.c_int32),
+                 ("target_accept", ctypes.c_double)] + [(n, ctypes.c_void_p) for n in _NUTS_PTRS])
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -85,6 +101,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_poisson_loglik_grad_f64.restype = ctypes.c_int
     L.dynode_poisson_loglik_grad_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, i32, vp, dbl, i32,
                                                  ctypes.POINTER(i32), vp, vp, vp, vp, vp]
+    NP = ctypes.POINTER(NutsState)
+    L.dynode_nuts_round_pre.restype = ctypes.c_int
+    L.dynode_nuts_round_pre.argtypes = [NP, vp, vp, vp]
+    L.dynode_nuts_round_post.restype = ctypes.c_int
+    L.dynode_nuts_round_post.argtypes = [NP, vp, vp, vp, vp]
     L.dynode_probe_dfma.restype = i64
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int

@@ -22,6 +22,15 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
+// shared with nuts_round.cu
+int fail_msg(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
 typedef cudaError_t (*LaunchFn)(const SolveArgs&, cudaStream_t);
 
 struct Instance {

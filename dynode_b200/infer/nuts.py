@@ -83,7 +83,7 @@ class BatchedNUTS:
                  max_tree_depth: int = 10, target_accept_prob: float = 0.8, dense_mass: bool = True,
                  step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True,
                  generator: Optional[torch.Generator] = None, cuda_graph: Optional[bool] = None,
-                 sync_every: int = 4):
+                 sync_every: int = 4, cuda_kernels: Optional[bool] = None):
         self.pg = potential_and_grad
         self.max_depth = int(max_tree_depth)
         self.target = float(target_accept_prob)
@@ -92,6 +92,7 @@ class BatchedNUTS:
         self.adapt_ss, self.adapt_mm = adapt_step_size, adapt_mass_matrix
         self.gen = generator
         self.cuda_graph = cuda_graph
+        self.cuda_kernels = cuda_kernels  # None: use the hand-written round kernels whenever the chains are on CUDA
         self.sync_every = max(1, int(sync_every))
         self.grad_evals = 0          # leapfrogs that belong to a tree (what "NUTS grad-evals" counts)
         self.launched_evals = 0      # rounds x chains (includes chains idling at a window boundary)
@@ -160,6 +161,8 @@ class BatchedNUTS:
         b.out_stats = {k: f(C, N) for k in ("accept_prob", "num_steps", "diverging", "potential_energy", "tree_depth")}
         b.last_accept, b.last_steps = f(C), f(C)
         b.n_useful = l(())
+        b.n_leap = l(C)
+        b.z_new, b.r_half = f(C, D), f(C, D)
         b.any_active = bl(())
         b.idx_min_tab, b.idx_max_tab = _tree_index_tables(md, dev)
         b.ar = torch.arange(C, device=dev)
@@ -172,10 +175,11 @@ class BatchedNUTS:
         C, D, md = b.C, b.D, self.max_depth
         imm, eps = b.imm, b.eps
         act = b.active.clone()  # chains that take part in this round
+        rnd_n, rnd_u = self._randn(C, D), self._rand(C, 3)  # same draws, same roles as the CUDA round
 
         # ---- chains beginning a transition: fresh momentum r ~ N(0, M), one-node tree at the current state
         nt = act & b.need_tree
-        r0 = torch.einsum("cij,cj->ci", b.msqrt, self._randn(C, D))
+        r0 = torch.einsum("cij,cj->ci", b.msqrt, rnd_n)
         _put(b.energy0, nt, b.U + self._kinetic(imm, r0))
         for dst, src in ((b.zL, b.z), (b.zR, b.z), (b.zP, b.z), (b.gL, b.g), (b.gR, b.g), (b.gP, b.g),
                          (b.rL, r0), (b.rR, r0), (b.r_sum, r0)):
@@ -191,7 +195,7 @@ class BatchedNUTS:
 
         # ---- chains starting a new doubling: pick a direction, start from that edge of the tree
         start = act & (b.s_n == 0)
-        _put(b.s_right, start, self._rand(C) < 0.5)
+        _put(b.s_right, start, rnd_u[:, 0] < 0.5)
         sr = b.s_right[:, None]
         _put(b.s_z, start, torch.where(sr, b.zR, b.zL))
         _put(b.s_r, start, torch.where(sr, b.rR, b.rL))
@@ -213,7 +217,7 @@ class BatchedNUTS:
         first = b.s_n == 0
         new_w = torch.where(first, leaf_w, torch.logaddexp(b.s_w, leaf_w))
         p_take = torch.where(first, torch.ones_like(leaf_w), torch.sigmoid(leaf_w - b.s_w))
-        take = act & (self._rand(C) < p_take)
+        take = act & (rnd_u[:, 1] < p_take)
         _put(b.s_zP, take, z_new)
         _put(b.s_UP, take, U_new)
         _put(b.s_gP, take, g_new)
@@ -247,7 +251,7 @@ class BatchedNUTS:
         done_sub = act & ((b.s_n >= target) | b.s_turn | b.s_div)
         p_bias = torch.clamp(torch.exp(b.s_w - b.weight), max=1.0)
         p_bias = torch.where(b.s_turn | b.s_div, torch.zeros_like(p_bias), p_bias)
-        take2 = done_sub & (self._rand(C) < p_bias)
+        take2 = done_sub & (rnd_u[:, 2] < p_bias)
         _put(b.zP, take2, b.s_zP)
         _put(b.UP, take2, b.s_UP)
         _put(b.gP, take2, b.s_gP)
@@ -310,12 +314,49 @@ class BatchedNUTS:
         b.n_useful += act.sum()
         b.any_active.copy_(b.active.any())
 
+    # ------------------------------------------------------------------ the same round on the CUDA kernels
+    def _bind_cuda_state(self):
+        """DynodeNutsState over the persistent buffers (include/dynode_b200_nuts.h)."""
+        from .. import _lib
+        b = self.b
+        st = _lib.NutsState()
+        st.C, st.D, st.max_depth, st.N = b.C, b.D, self.max_depth, b.out_z.shape[1]
+        st.target_accept = self.target
+        alias = {"out_accept": b.out_stats["accept_prob"], "out_steps": b.out_stats["num_steps"],
+                 "out_div": b.out_stats["diverging"], "out_energy": b.out_stats["potential_energy"],
+                 "out_depth": b.out_stats["tree_depth"]}
+        for name in _lib._NUTS_PTRS:
+            t = alias.get(name, getattr(b, name, None))
+            assert t is not None and t.is_cuda and t.is_contiguous(), name
+            setattr(st, name, t.data_ptr())
+        self._st = st
+        self._lib = _lib
+
+    def _round_cuda(self):
+        import ctypes
+        b, L = self.b, self._lib.load()
+        rnd_n, rnd_u = self._randn(b.C, b.D), self._rand(b.C, 3)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._lib.check(L.dynode_nuts_round_pre(ctypes.byref(self._st), rnd_n.data_ptr(), rnd_u.data_ptr(), stream))
+        U_new, g_new = self.pg(b.z_new)
+        U_new, g_new = U_new.contiguous(), g_new.contiguous()
+        self._lib.check(L.dynode_nuts_round_post(ctypes.byref(self._st), U_new.data_ptr(), g_new.data_ptr(),
+                                                 rnd_u.data_ptr(), stream))
+        b.any_active.copy_(b.active.any())
+
     # ------------------------------------------------------------------ graph capture
     def _prepare_round_fn(self):
         b = self.b
         want = self.cuda_graph if self.cuda_graph is not None else b.dev.type == "cuda"
         self._g = self.gen
-        self._round_fn = self._round
+        use_kernels = self.cuda_kernels if self.cuda_kernels is not None else b.dev.type == "cuda"
+        if use_kernels and b.dev.type != "cuda":
+            raise RuntimeError("the NUTS round kernels need the chains on a CUDA device")
+        self.kernels_used = bool(use_kernels)
+        if use_kernels:
+            self._bind_cuda_state()
+        round_impl = self._round_cuda if use_kernels else self._round
+        self._round_fn = round_impl
         self.graph_used = False
         if not want or b.dev.type != "cuda":
             return
@@ -325,13 +366,13 @@ class BatchedNUTS:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(3):  # warm-up rounds are real rounds of the algorithm
-                    self._round()
+                    round_impl()
                     self.rounds += 1
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._round()
+                round_impl()
             self._graph = graph
             self._round_fn = graph.replay
             self.graph_used = True
@@ -413,7 +454,7 @@ class BatchedNUTS:
             self._run_window(num_samples, adapt=False, middle=False, sampling=True)
             if progress is not None:
                 progress(num_warmup + num_samples - 1, self)
-        self.grad_evals = int(b.n_useful)
+        self.grad_evals = int(b.n_useful) + int(b.n_leap.sum())
         self.launched_evals = self.rounds * b.C
         stats = {k: v.clone() for k, v in b.out_stats.items()}
         return b.out_z.clone(), stats, b

@@ -1,0 +1,77 @@
+/* dynode_b200_nuts.h -- C ABI of the many-chain NUTS bookkeeping kernels.
+ *
+ * The reference runs numpyro's NUTS (MCMC(NUTS(model, dense_mass=True, max_tree_depth, init_to_median)),
+ * reference src/dynode/infer/inference.py:149-163) one chain after another on the CPU.  Here every chain is
+ * one CUDA thread: a *round* advances all chains by one leapfrog step and is
+ *
+ *     dynode_nuts_round_pre   (new momentum / new doubling where due, first half of the leapfrog)
+ *     potential_and_grad      (the model; its ODE part is dynode_poisson_loglik_grad_f64 / dynode_solve_sens_f64)
+ *     dynode_nuts_round_post  (second half of the leapfrog, multinomial sampling inside the subtree,
+ *                              checkpointed U-turn tests, tree doubling, and -- when a chain's tree is
+ *                              complete -- the transition commit: dual-averaging step size, Welford
+ *                              covariance, storage of the draw)
+ *
+ * Both launches are stream-ordered, allocate nothing and keep no state outside the buffers the caller owns,
+ * so a whole round (model included) can be captured in a CUDA graph.  All pointers are DEVICE pointers.
+ * Layouts are row-major with the chain index first: [C], [C][D], [C][D][D], [C][max_depth][D], [C][N][D].
+ */
+#ifndef DYNODE_B200_NUTS_H_
+#define DYNODE_B200_NUTS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNODE_NUTS_MAX_DIM 16
+#define DYNODE_NUTS_MAX_DEPTH 12
+
+typedef struct {
+  int32_t C, D, max_depth, N; /* chains, dimension, numpyro max_tree_depth, draws kept per chain */
+  double target_accept;       /* dual averaging target (0.8) */
+  /* chain state */
+  double *z, *U, *g;    /* [C][D], [C], [C][D]: position, potential energy, its gradient */
+  double *eps;          /* [C] step size */
+  double *imm, *msqrt;  /* [C][D][D] inverse mass matrix; factor with momentum = msqrt @ N(0, I) */
+  /* window bookkeeping (chains run asynchronously inside an adaptation window) */
+  int64_t *k;           /* [C] transitions completed in the current window */
+  const int64_t *nwin;  /* [1] transitions each chain has to make in this window */
+  uint8_t *active, *need_tree; /* [C] */
+  const uint8_t *f_adapt, *f_middle, *f_sampling; /* [1] flags of the current window */
+  /* whole tree */
+  double *energy0;                  /* [C] */
+  double *zL, *rL, *gL, *zR, *rR, *gR, *zP, *gP, *r_sum; /* [C][D] */
+  double *UP, *weight, *sum_acc;    /* [C] */
+  int64_t *depth, *nprop;           /* [C] */
+  uint8_t *turning, *diverging;     /* [C] */
+  /* subtree under construction */
+  int64_t *s_n;                     /* [C] leaves so far */
+  uint8_t *s_right, *s_turn, *s_div; /* [C] */
+  double *s_z, *s_r, *s_g, *s_zP, *s_gP, *s_rsum; /* [C][D] */
+  double *s_UP, *s_w, *s_acc;       /* [C] */
+  double *r_ck, *rs_ck;             /* [C][max_depth][D] U-turn checkpoints */
+  /* leapfrog scratch written by _pre, read by _post */
+  double *z_new, *r_half;           /* [C][D] */
+  /* adaptation */
+  double *da_x, *da_xavg, *da_gavg, *da_t, *da_prox; /* [C] dual averaging of log step size */
+  double *wf_n, *wf_mean, *wf_m2;   /* [C], [C][D], [C][D][D] Welford accumulators */
+  /* outputs */
+  double *out_z;                    /* [C][N][D] */
+  double *out_accept, *out_steps, *out_div, *out_energy, *out_depth; /* [C][N] */
+  double *last_accept, *last_steps; /* [C] */
+  int64_t *n_leap;                  /* [C] leapfrogs that belonged to a tree */
+} DynodeNutsState;
+
+/* rnd_n [C][D] standard normals (fresh momentum), rnd_u [C][3] uniforms (direction, subtree transition,
+ * top-level transition).  Returns 0 when enqueued, nonzero + dynode_last_error() otherwise. */
+int dynode_nuts_round_pre(const DynodeNutsState* st, const double* rnd_n, const double* rnd_u, void* stream);
+
+/* U_new [C], g_new [C][D]: potential energy and gradient at st->z_new (non-finite values mark a divergent leaf). */
+int dynode_nuts_round_post(const DynodeNutsState* st, const double* U_new, const double* g_new,
+                           const double* rnd_u, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNODE_B200_NUTS_H_ */

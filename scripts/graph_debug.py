@@ -16,6 +16,6 @@ for mod in (m.model_fused, m.model):
             torch.cuda.synchronize(); dt = time.perf_counter() - t
         for x in w: print("WARNING:", x.message)
         e = mc.engine
-        print(f"{mod.__name__} graph={e.graph_used} C={C}: {dt:.2f} s, rounds {e.rounds}, tree grad-evals {e.grad_evals} "
+        print(f"{mod.__name__} graph={e.graph_used} kernels={e.kernels_used} C={C}: {dt:.2f} s, rounds {e.rounds}, tree grad-evals {e.grad_evals} "
               f"({e.grad_evals/dt:.3g}/s), {dt/e.rounds*1e6:.0f} us/round", flush=True)
         mc.print_summary()
