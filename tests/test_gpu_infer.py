@@ -177,8 +177,10 @@ def test_config5_age_risk_strain_nuts():
 
 
 def test_cuda_nuts_round_equals_the_torch_round():
-    """dynode_nuts_round_pre/post (one thread per chain) against the masked-tensor round of infer/nuts.py:
-    same state, same random numbers -> the same chains."""
+    """dynode_nuts_round_pre/post (one thread per chain) against the masked-tensor round of infer/nuts.py, in
+    lock-step from the same state with the same random numbers: every state field agrees round by round
+    (compared over 120 rounds -- beyond a few hundred, rounding differences between cuBLAS bmm and the
+    per-thread dot products are amplified by warm-up trajectories that run near the stability limit)."""
     from dynode_b200.infer.nuts import BatchedNUTS
     dev = _dev()
     cov = torch.tensor([[1.0, 0.6, 0.0], [0.6, 2.0, -0.4], [0.0, -0.4, 0.5]], dtype=torch.float64, device=dev)
@@ -190,19 +192,41 @@ def test_cuda_nuts_round_equals_the_torch_round():
         g = d @ prec
         return 0.5 * (d * g).sum(1), g
 
-    outs = []
+    C = 96
+    engs = []
     for kernels in (False, True):
-        eng = BatchedNUTS(pg, max_tree_depth=7, generator=torch.Generator(device=dev).manual_seed(11),
-                          cuda_graph=False, cuda_kernels=kernels)
-        z, extra, st = eng.run(torch.zeros(96, 3, dtype=torch.float64, device=dev), 60, 30)
-        outs.append((z, extra, eng.grad_evals, st.eps.clone(), st.imm.clone()))
-    (za, ea, na, epsa, imma), (zb, eb, nb, epsb, immb) = outs
-    same = ((za - zb).abs().amax(dim=(1, 2)) < 1e-8)
-    assert float(same.double().mean()) > 0.97  # a knife-edge accept/reject may flip in a few chains
-    assert abs(na - nb) <= 0.02 * na
-    assert torch.allclose(epsa[same], epsb[same], rtol=1e-8) and torch.allclose(imma[same], immb[same], rtol=1e-7, atol=1e-10)
-    assert torch.allclose(ea["num_steps"][same], eb["num_steps"][same])
-    # and with graph replay the sampler still recovers the target
+        e = BatchedNUTS(pg, max_tree_depth=5, generator=torch.Generator(device=dev).manual_seed(11),
+                        cuda_graph=False, cuda_kernels=kernels)
+        e._allocate(torch.zeros(C, 3, dtype=torch.float64, device=dev), 30)
+        e._g = e.gen
+        U, g = e._eval(e.b.z)
+        e.b.U.copy_(U)
+        e.b.g.copy_(g)
+        e.b.need_tree.fill_(True)
+        e._prepare_round_fn()
+        b = e.b
+        b.nwin.fill_(12)
+        b.active.fill_(True)
+        b.f_adapt.fill_(True)
+        b.f_middle.fill_(True)
+        b.f_sampling.fill_(True)
+        engs.append(e)
+    fields = ["z", "U", "g", "eps", "k", "active", "need_tree", "energy0", "zL", "rL", "gL", "zR", "rR", "gR", "zP",
+              "gP", "r_sum", "UP", "weight", "sum_acc", "depth", "nprop", "turning", "diverging", "s_n", "s_right",
+              "s_turn", "s_div", "s_z", "s_r", "s_g", "s_zP", "s_gP", "s_rsum", "s_UP", "s_w", "s_acc", "da_x",
+              "da_xavg", "da_gavg", "da_t", "wf_n", "wf_mean", "wf_m2", "out_z"]
+    for rnd in range(120):
+        for e in engs:
+            e._round_fn()
+        a, b = engs[0].b, engs[1].b
+        for f in fields:
+            x, y = getattr(a, f).double(), getattr(b, f).double()
+            assert torch.allclose(x, y, rtol=1e-8, atol=1e-9, equal_nan=True), (rnd, f)
+    assert int(engs[0].b.k.min()) >= 3 and not bool(engs[0].b.active.all())  # trees were built, chains finished
+    assert int(engs[0].b.n_useful) == int(engs[1].b.n_leap.sum())
+    for name in ("accept_prob", "num_steps", "diverging", "potential_energy", "tree_depth"):
+        assert torch.allclose(engs[0].b.out_stats[name], engs[1].b.out_stats[name], rtol=1e-8, atol=1e-9)
+    # and with graph replay the sampler recovers the target
     eng = BatchedNUTS(pg, max_tree_depth=7, cuda_graph=True, cuda_kernels=True)
     z, extra, st = eng.run(torch.zeros(512, 3, dtype=torch.float64, device=dev), 150, 100)
     assert eng.graph_used and eng.kernels_used
