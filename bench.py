@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override draws per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--host-chunk", type=int, default=8192)
+    ap.add_argument("--host-chunk", type=int, default=2048)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU wall time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nuts", action="store_true")

@@ -308,7 +308,7 @@ def simulate_ensemble(
     state_batched: Optional[bool] = None,
     throw: bool = True,
     out: Optional[torch.Tensor] = None,
-    host_chunk: int = 8192,
+    host_chunk: int = 2048,
 ) -> Solution:
     """`simulate` over an ensemble of `batch_size` parameter draws in one launch per device chunk.
 
@@ -328,7 +328,7 @@ def simulate_ensemble(
 
 
 def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices, save_step,
-         *, batch_size, state_batched, throw, out=None, host_chunk=8192) -> Solution:
+         *, batch_size, state_batched, throw, out=None, host_chunk=2048) -> Solution:
     # unsupported ODEs / solver options fail loudly before anything touches the device
     spec, model, params, contact = _resolve(ode, initial_state, ode_parameters, batch_size, state_batched)
     opts = _solver_options(solver_parameters, duration_days)
