@@ -107,7 +107,8 @@ static void fill_common(SolveArgs& a, const DynodeSolverDesc* sv, int64_t B, Dyn
   a.n_jump = sv->n_jump > 0 ? sv->n_jump : 0;
   a.max_steps = (int32_t)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.write_primal = 1;
-  a.wrt[0] = a.wrt[1] = -1;
+  a.n_pass = 1;
+  for (int k = 0; k < kMaxWrt; ++k) a.wrt[k] = -1;
 }
 
 static int check_wrt(const DynodeModelDesc* m, int32_t n_wrt, const int32_t* wrt) {
@@ -129,19 +130,20 @@ static int run_passes(const Instance* inst, SolveArgs& a, int32_t n_wrt, const i
     return fail("unsupported: discontinuity points together with sensitivities / the fused log-likelihood");
   if (n_wrt == 0) {
     a.P_total = 0;
+    a.n_pass = 1;
     e = (loglik ? inst->lik0 : (a.n_jump > 0 ? inst->saveJ : inst->save0))(a, stream);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
   }
-  // tangent directions ride the same step sequence in passes of `chunk` directions (registers)
+  // tangent directions ride the same step sequence in groups of `chunk` directions (registers); all groups
+  // of all trajectories are work items of ONE launch (solve_args.h), so a many-parameter gradient for a few
+  // hundred NUTS chains still fills the GPU instead of serialising ceil(P/chunk) small launches
   a.P_total = n_wrt;
-  for (int p0 = 0; p0 < n_wrt; p0 += inst->chunk) {
-    a.p0 = p0;
-    for (int k = 0; k < kPMax; ++k) a.wrt[k] = (k < inst->chunk && p0 + k < n_wrt) ? wrt[p0 + k] : -1;
-    a.write_primal = (p0 == 0);
-    e = (loglik ? inst->likP : inst->saveP)(a, stream);
-    if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
-  }
+  a.n_pass = (n_wrt + inst->chunk - 1) / inst->chunk;
+  for (int k = 0; k < kMaxWrt; ++k) a.wrt[k] = k < n_wrt ? wrt[k] : -1;
+  a.write_primal = 1;
+  e = (loglik ? inst->likP : inst->saveP)(a, stream);
+  if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 

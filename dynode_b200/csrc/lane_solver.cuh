@@ -235,9 +235,10 @@ struct LaneSolver {
 
     // this warp's contiguous chunk of the ensemble
     const int64_t chunk_begin = warp_global * a.chunk;
-    const int64_t chunk_end = (chunk_begin + a.chunk < a.B) ? chunk_begin + a.chunk : a.B;
+    const int64_t Bv = a.B * a.n_pass;  // work items: (trajectory, tangent group) pairs
+    const int64_t chunk_end = (chunk_begin + a.chunk < Bv) ? chunk_begin + a.chunk : Bv;
     int64_t next = chunk_begin;  // warp-uniform: first trajectory not yet handed to a slot
-    if (chunk_begin >= a.B) return;
+    if (chunk_begin >= Bv) return;
 
     // ---- element offsets inside a full state row and inside a saved row
     int off_full[NE], off_save[NE];
@@ -273,7 +274,9 @@ struct LaneSolver {
     // ---- per-slot state (registers)
     Prm prm;
     D y[NE], f[7][NE], ys[NE];
-    int64_t traj = chunk_begin;  // trajectory of my slot (valid index even while idle)
+    int64_t traj = chunk_begin / a.n_pass;  // trajectory of my slot (valid index even while idle)
+    int p0s = 0;                            // first tangent direction my slot carries
+    bool wp = a.write_primal != 0;          // my slot writes the primal outputs (tangent group 0)
     double tprev = t1, tnext = t1;
     int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
     bool active = false;
@@ -301,7 +304,10 @@ struct LaneSolver {
           const int64_t cand = next + rank;
           const bool take = slot_ok && !active && cand < chunk_end;
           next = (next + n_idle < chunk_end) ? next + n_idle : chunk_end;
-          const int64_t tr = take ? cand : traj;
+          const int64_t cand_tr = (a.n_pass == 1) ? cand : cand / a.n_pass;
+          const int cand_p0 = (a.n_pass == 1) ? 0 : (int)(cand - cand_tr * a.n_pass) * P;
+          const int64_t tr = take ? cand_tr : traj;
+          const int p0n = take ? cand_p0 : p0s;
           // ---- parameters and initial state of the new trajectory (masked lanes shadow their old one)
           auto ld = [&](const DynodeArray& arr, int k, double dflt) -> double {
             return arr.ptr ? __ldg(arr.ptr + tr * arr.batch_stride + k) : dflt;
@@ -317,7 +323,7 @@ struct LaneSolver {
           if constexpr (P > 0) {
 #pragma unroll
             for (int k = 0; k < P; ++k) {
-              const int w = a.wrt[k];
+              const int w = (p0n + k < a.P_total) ? a.wrt[p0n + k] : -1;
               if (w >= 0 && (w & 15) == c.s) {
                 const int kind = w >> 4;
                 if (kind == DYNODE_P_BETA) pn.beta.d[k] = 1.0;
@@ -337,8 +343,8 @@ struct LaneSolver {
               if (a.dy0) {
 #pragma unroll
                 for (int k = 0; k < P; ++k)
-                  if (a.p0 + k < a.P_total)
-                    yn[e].d[k] = __ldg(a.dy0 + ((tr * a.P_total + a.p0 + k) * (int64_t)N) + off_full[e]);
+                  if (p0n + k < a.P_total)
+                    yn[e].d[k] = __ldg(a.dy0 + ((tr * a.P_total + p0n + k) * (int64_t)N) + off_full[e]);
               }
             }
           }
@@ -394,14 +400,16 @@ struct LaneSolver {
             }
 #pragma unroll
             for (int e = 0; e < NE; ++e) { y[e] = yn[e]; f[0][e] = fn[e]; }
-            traj = cand;
+            traj = cand_tr;
+            p0s = cand_p0;
+            wp = a.write_primal && cand_p0 == 0;
             tprev = a.t0;
             if constexpr (JUMPS) tn = clip_to_jumps(a, a.t0, tn, made_jump);
             tnext = fmin(tn, t1);
             n_acc = n_rej = n_steps = 0;
             save_i = 0;
-            out_s = a.ys + cand * (int64_t)a.T * N + c.g;
-            out_c = a.ys + cand * (int64_t)a.T * N + G + c.g * S + c.s;
+            out_s = a.ys + cand_tr * (int64_t)a.T * N + c.g;
+            out_c = a.ys + cand_tr * (int64_t)a.T * N + G + c.g * S + c.s;
             lp_acc = make_dual<P>(0.0);
             obs_prev = make_dual<P>(0.0);
             active = true;
@@ -414,7 +422,7 @@ struct LaneSolver {
     auto retire = [&](bool fin) {
       if (__any_sync(0xffffffffu, fin)) {
         if constexpr (IS_SAVE) {
-          if (fin && a.write_primal) {
+          if (fin && wp) {
             // slots never reached keep diffrax's +inf fill
             for (int k = save_i; k < a.T; ++k) {
               const int64_t row = (traj * a.T + k) * (int64_t)n_saved;
@@ -425,16 +433,16 @@ struct LaneSolver {
           }
         } else {
           const double tot = traj_sum(obs_owner ? lp_acc.v : 0.0, c);
-          if (fin && q == 0 && a.write_primal) a.lp[traj] = tot + a.lp_const;
+          if (fin && q == 0 && wp) a.lp[traj] = tot + a.lp_const;
           if constexpr (P > 0) {
 #pragma unroll
             for (int k = 0; k < P; ++k) {
               const double gp = traj_sum(obs_owner ? lp_acc.d[k] : 0.0, c);
-              if (fin && q == 0 && a.p0 + k < a.P_total) a.grad[traj * a.P_total + a.p0 + k] = gp;
+              if (fin && q == 0 && p0s + k < a.P_total) a.grad[traj * a.P_total + p0s + k] = gp;
             }
           }
         }
-        if (fin && q == 0 && a.write_primal) {
+        if (fin && q == 0 && wp) {
           int32_t* st = a.stats + traj * 4;
           st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
           st[DYNODE_STAT_ACCEPTED] = n_acc;
@@ -623,11 +631,11 @@ struct LaneSolver {
                 for (int e = 0; e < NE; ++e) {
                   const D v = dense(e, th, hthw, hth2);
                   if (off_save[e] >= 0) {
-                    if (a.write_primal) a.ys[row + off_save[e]] = v.v;
+                    if (wp) a.ys[row + off_save[e]] = v.v;
                     if constexpr (P > 0) {
 #pragma unroll
                       for (int k = 0; k < P; ++k)
-                        if (a.p0 + k < a.P_total) a.dys[(row + off_save[e]) * a.P_total + a.p0 + k] = v.d[k];
+                        if (p0s + k < a.P_total) a.dys[(row + off_save[e]) * a.P_total + p0s + k] = v.d[k];
                     }
                   }
                 }
@@ -735,10 +743,12 @@ cudaError_t launch_lane_solver(const SolveArgs& a_in, cudaStream_t stream) {
   // non-persistent instances: one generation per warp (chunk = TPW)
   int64_t warps = LS::PERSIST ? (int64_t)cached_warps * kOversubscribe : (int64_t)1 << 40;
   const int64_t min_chunk = LS::TPW;                               // at least one trajectory per slot
-  const int64_t max_warps = (a.B + min_chunk - 1) / min_chunk;
+  if (a.n_pass < 1) a.n_pass = 1;
+  const int64_t Bv = a.B * a.n_pass;
+  const int64_t max_warps = (Bv + min_chunk - 1) / min_chunk;
   if (warps > max_warps) warps = max_warps;
-  a.chunk = (a.B + warps - 1) / warps;
-  warps = (a.B + a.chunk - 1) / a.chunk;
+  a.chunk = (Bv + warps - 1) / warps;
+  warps = (Bv + a.chunk - 1) / a.chunk;
   const int64_t grid = (warps + wpc - 1) / wpc;
   // tuning knob: DYNODE_DEBUG_SMEM=<bytes> of unused dynamic shared memory per CTA lowers the number of
   // resident CTAs (occupancy experiments, profiles/r1/occupancy.md); 0 in production

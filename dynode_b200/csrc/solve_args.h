@@ -7,7 +7,8 @@
 
 namespace dynode {
 
-constexpr int kPMax = 2;            // max tangent directions carried per pass (more -> several passes)
+constexpr int kPMax = 2;            // max tangent directions carried per work item (more -> several groups)
+constexpr int kMaxWrt = 64;         // max tangent directions per call
 // Directions per pass chosen so that (1+P) * 8 * NE doubles stay in registers without spilling:
 // SIR lanes hold 3 elements (P=2 -> 72 doubles), SEIRS/SEIRS_C lanes 4-5 elements (P=1 -> 80).
 constexpr int tangent_chunk(int flow) { return flow == DYNODE_FLOW_SIR ? 2 : 1; }
@@ -46,9 +47,11 @@ struct SolveArgs {
   // discontinuity points (SolverParams.discontinuity_points -> jump_ts), sorted ascending, device memory
   const double* jump_ts;
   int32_t n_jump;
-  // sensitivities: this pass carries directions p0 .. p0+P-1 of P_total
-  int32_t P_total, p0;
-  int32_t wrt[kPMax];
+  // sensitivities: P_total directions ride the primal's steps in n_pass groups of P (the kernel's template
+  // chunk).  All groups run in ONE launch: work item v = trajectory * n_pass + group integrates trajectory
+  // v / n_pass carrying directions group*P .. group*P+P-1; group 0 also writes the primal outputs.
+  int32_t P_total, n_pass;
+  int32_t wrt[kMaxWrt];
   const double* dy0;  // [B][P_total][n]
   double* dys;        // [B][T][n_saved][P_total]
   // fused log-likelihood

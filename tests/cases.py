@@ -51,16 +51,16 @@ def make_case(name, B, seed=20260101):
                                 season_phase=phase, season_period=period), contact=None, y0=y0,
                     oracle=(O_SEIRS_SEASONAL, (1, 1, 1), np.hstack([beta, gamma, sigma, omega, amp, phase, period]), None),
                     t1=365)
-    if name in ("sir_age2", "sir_age4"):
-        A = 2 if name == "sir_age2" else 4
+    if name in ("sir_age2", "sir_age3", "sir_age4"):
+        A = int(name[-1])
         beta, gamma, _, _, _ = _rates(rng, B, 1, r0=(1.5, 3.0), inf=(4, 10))
         if A == 2:
             C = CONTACT2 / np.max(np.real(np.linalg.eigvals(CONTACT2)))
             demo = np.array([0.75, 0.25])
         else:
-            C = np.random.default_rng(5).uniform(0.1, 1.0, (4, 4))
+            C = np.random.default_rng(5 if A == 4 else 50 + A).uniform(0.1, 1.0, (A, A))
             C = C / np.max(np.real(np.linalg.eigvals(C)))
-            demo = np.array([0.4, 0.3, 0.2, 0.1])
+            demo = np.array([0.4, 0.3, 0.2, 0.1]) if A == 4 else np.array([0.5, 0.3, 0.2])
         y0 = np.concatenate([1000 * 0.99 * demo, 1000 * 0.01 * demo, np.zeros(A)])
         return dict(model=FlowModel(_lib.FLOW_SIR, 0, A, 1), params=dict(beta=beta, gamma=gamma), contact=C,
                     y0=y0, oracle=(O_SIR_AGE, (A, 1, 1), np.hstack([beta, gamma]), C), t1=100)
@@ -74,16 +74,22 @@ def make_case(name, B, seed=20260101):
         K = CM.reshape(6, 6).T  # engine layout: contact[target][source]
         return dict(model=FlowModel(_lib.FLOW_SIR, 0, 6, 1), params=dict(beta=beta, gamma=gamma), contact=K,
                     y0=y0, oracle=(O_SIR_AGE_RISK, (3, 2, 1), np.hstack([beta, gamma]), CM), t1=150)
-    if name in ("seirs_multi_a2s3", "seirs_multi_g6s3"):
-        S = 3
-        G = 2 if name == "seirs_multi_a2s3" else 6
+    if name.startswith("seirs_multi_"):
+        import re
+        m = re.fullmatch(r"seirs_multi_[ag](\d+)s(\d+)", name)
+        G, S = int(m.group(1)), int(m.group(2))
         beta, gamma, sigma, omega, r0 = _rates(rng, B, S)
         if G == 2:
             C = CONTACT2
             demo = np.array([0.75, 0.25])
-        else:
+        elif G == 6:
             C = np.kron(AGE3, RISK2)
             demo = (np.array([0.7, 0.2, 0.1])[:, None] * np.array([[0.5, 0.5]] * 3)).ravel()
+        else:
+            C = np.random.default_rng(100 + G).uniform(0.1, 1.0, (G, G))
+            C = C / np.max(np.real(np.linalg.eigvals(C)))
+            demo = np.arange(G, 0, -1.0)
+            demo = demo / demo.sum()
         dom = r0 / r0.sum(1, keepdims=True)  # initial infections split by r0 (multi-strain example :152-167)
         s_0 = np.broadcast_to(1000 * 0.99 * demo, (B, G))
         i_0 = 1000 * 0.01 * demo[None, :, None] * dom[:, None, :]
@@ -97,3 +103,6 @@ def make_case(name, B, seed=20260101):
 
 ALL_CASES = ("sir_1bin", "sir_density", "seirs_1bin", "seirs_seasonal", "sir_age2", "sir_age4",
              "sir_age_risk32", "seirs_multi_a2s3", "seirs_multi_g6s3")
+# further compiled members of the families (csrc/instances.def 9-17)
+EXTRA_CASES = ("sir_age3", "seirs_multi_g1s1", "seirs_multi_g1s2", "seirs_multi_g1s3", "seirs_multi_g2s2",
+               "seirs_multi_g3s2", "seirs_multi_g4s2", "seirs_multi_g3s3", "seirs_multi_g4s3")

@@ -4,7 +4,7 @@ identical accepted/rejected step counts (the canary for step-sequence parity, SU
 import numpy as np
 import pytest
 
-from tests.cases import ALL_CASES, make_case
+from tests.cases import ALL_CASES, EXTRA_CASES, make_case
 
 pytestmark = pytest.mark.gpu
 
@@ -36,7 +36,7 @@ def _assert_close(got, ref, rtol=RTOL, atol_scale=ATOL_SCALE):
     assert not bad.any(), f"max rel err {np.nanmax(np.abs(got - ref) / (np.abs(ref) + atol_scale * scale)):.3e}"
 
 
-@pytest.mark.parametrize("name", ALL_CASES)
+@pytest.mark.parametrize("name", ALL_CASES + EXTRA_CASES)
 def test_saved_trajectories_match_oracle(name):
     B = 257  # ragged: not a multiple of trajectories-per-warp/CTA
     case = make_case(name, B)
