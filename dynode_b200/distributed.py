@@ -112,6 +112,34 @@ def run_sharded(local_solve: Callable[[int, int, torch.Tensor], None], B_total: 
     return buf.all_gather() if gather else buf.local
 
 
+def gather_draws(local: dict, group=None) -> dict:
+    """All-gather a dict of per-rank draws (posterior samples / posterior-predictive trajectories,
+    {site: [n_local, ...]}) along the leading axis; every rank may hold a different number of rows.
+    Uses the same padded in-place buffer as the trajectory gather (NCCL all_gather_into_tensor on CUDA)."""
+    rank, ws = world()
+    if ws == 1:
+        return dict(local)
+    out = {}
+    for name in sorted(local):
+        x = local[name].contiguous()
+        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+        counts = [torch.zeros_like(n) for _ in range(ws)]
+        dist.all_gather(counts, n, group=group)
+        counts = [int(c.item()) for c in counts]
+        m = max(counts)
+        full = torch.zeros((ws * m, *x.shape[1:]), dtype=x.dtype, device=x.device)
+        full[rank * m:rank * m + x.shape[0]] = x
+        mine = full[rank * m:(rank + 1) * m]
+        if x.is_cuda:
+            dist.all_gather_into_tensor(full, mine, group=group)
+        else:
+            parts = [torch.empty_like(mine) for _ in range(ws)]
+            dist.all_gather(parts, mine.clone(), group=group)
+            full = torch.cat(parts, 0)
+        out[name] = torch.cat([full[r * m:r * m + c] for r, c in enumerate(counts)], 0)
+    return out
+
+
 def all_reduce_flags(n_failed: int, device=None, group=None) -> int:
     """Sum of per-rank failure counts (e.g. trajectories that hit max_steps)."""
     rank, ws = world()

@@ -67,6 +67,12 @@ def _worker(rank, ws, port, B, q):
         lo, hi = D.shard_bounds(B, ws, rank)
         ok &= torch.equal(local, _rows(lo, hi, T, ns))
         ok &= D.all_reduce_flags(rank + 1) == ws * (ws + 1) // 2
+        # posterior draws / posterior-predictive rows, a different number per rank
+        mine = {"r0": torch.full((3 + rank,), float(rank)), "inc": torch.full((3 + rank, 4, 2), float(rank))}
+        got = D.gather_draws(mine)
+        ok &= got["r0"].shape == (7,) and got["inc"].shape == (7, 4, 2)
+        ok &= torch.equal(got["r0"], torch.tensor([0.0] * 3 + [1.0] * 4))
+        ok &= bool((got["inc"][:3] == 0).all() and (got["inc"][3:] == 1).all())
         ok &= D.world() == (rank, ws)
         q.put((rank, bool(ok)))
     finally:
