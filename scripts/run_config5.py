@@ -41,6 +41,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))  # build the communicator before anything is timed
     chains = args.chains // world
     obs = m5.synthetic_incidence(args.tf).to(dev)
     cfg = m5.get_config(infer=True)
