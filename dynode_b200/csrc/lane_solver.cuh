@@ -642,10 +642,16 @@ struct LaneSolver {
               } else {
                 // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
                 // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
+                // the observed compartment is picked through an index the compiler cannot see: written as
+                // `if (e == obs_comp) v = dense(e)` the unrolled chain was turned into one dynamically
+                // indexed read, which put y, f and Q (55 duals) in local memory
                 D v = make_dual<P>(0.0);
 #pragma unroll
-                for (int e = 0; e < NE; ++e)
-                  if (e == a.obs_comp) v = dense(e, th, hthw, hth2);
+                for (int e = 0; e < NE; ++e) {
+                  int ee = e;
+                  asm volatile("" : "+r"(ee));
+                  if (ee == a.obs_comp) v = dense(e, th, hthw, hth2);  // warp-uniform branch
+                }
                 if (save_i > 0 && obs_owner) {
                   D inc = v - obs_prev;
                   const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
@@ -711,7 +717,11 @@ constexpr int min_blocks(int flow, int p) {
 #ifdef DYN_MINBLOCKS
   return DYN_MINBLOCKS;
 #else
+#ifdef DYN_MINBLOCKS_TANGENT
+  return p > 0 ? DYN_MINBLOCKS_TANGENT : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8);
+#else
   return p > 0 ? 1 : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8);
+#endif
 #endif
 }
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
