@@ -17,11 +17,13 @@ FLOW_SIR, FLOW_SEIRS, FLOW_SEIRS_C = 0, 1, 2
 FLAG_SEASONAL, FLAG_DENSITY_DEP = 1, 2
 P_BETA, P_GAMMA, P_SIGMA, P_OMEGA, P_SEASON_AMP, P_SEASON_PHASE = range(6)
 STAT_RESULT, STAT_ACCEPTED, STAT_REJECTED, STAT_STEPS = range(4)
+RESULT_OK, RESULT_MAX_STEPS, RESULT_ADJOINT_CAPACITY = range(3)
 
 EXPORTED_SYMBOLS = (
     "dynode_version", "dynode_last_error", "dynode_state_size", "dynode_num_compartments",
     "dynode_saved_size", "dynode_is_supported", "dynode_solve_f64", "dynode_solve_sens_f64",
-    "dynode_poisson_loglik_grad_f64", "dynode_probe_dfma", "dynode_probe_hbm_write",
+    "dynode_poisson_loglik_grad_f64", "dynode_poisson_loglik_adjoint_f64", "dynode_probe_dfma",
+    "dynode_probe_hbm_write",
     "dynode_nuts_round_pre", "dynode_nuts_round_post",
 )
 
@@ -101,6 +103,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_poisson_loglik_grad_f64.restype = ctypes.c_int
     L.dynode_poisson_loglik_grad_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, i32, vp, dbl, i32,
                                                  ctypes.POINTER(i32), vp, vp, vp, vp, vp]
+    L.dynode_poisson_loglik_adjoint_f64.restype = ctypes.c_int
+    L.dynode_poisson_loglik_adjoint_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, i32, vp, dbl, vp, vp, vp, vp,
+                                                    vp, i32, vp, vp]
     NP = ctypes.POINTER(NutsState)
     L.dynode_nuts_round_pre.restype = ctypes.c_int
     L.dynode_nuts_round_pre.argtypes = [NP, vp, vp, vp]

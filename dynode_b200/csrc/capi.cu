@@ -32,10 +32,12 @@ int fail_msg(const char* fmt, ...) {
 }
 
 typedef cudaError_t (*LaunchFn)(const SolveArgs&, cudaStream_t);
+typedef cudaError_t (*AdjointFn)(const AdjointArgs&, cudaStream_t);
 
 struct Instance {
   int flow, flags, g, s, chunk;
   LaunchFn save0, saveP, lik0, likP, saveJ;
+  AdjointFn adjoint;
 };
 
 #define X(IDX, FLOW, FLAGS, G, S)                                                        \
@@ -44,7 +46,8 @@ struct Instance {
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_SAVE>,               \
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK>,                               \
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK>,             \
-   &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_SAVE_JUMPS>},
+   &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_SAVE_JUMPS>,                           \
+   &launch_adjoint_solver<FLOW, FLAGS, G, S>},
 static const Instance kInstances[] = {
 #include "instances.def"
 };
@@ -249,6 +252,36 @@ int dynode_poisson_loglik_grad_f64(const DynodeModelDesc* model, const DynodeSol
   a.lp = lp;
   a.grad = grad;
   return run_passes(inst, a, n_wrt, wrt, /*loglik=*/true, (cudaStream_t)stream);
+}
+
+int dynode_poisson_loglik_adjoint_f64(const DynodeModelDesc* model, const DynodeSolverDesc* solver, int64_t B,
+                                      DynodeArray y0, const DynodeParams* params, const double* save_ts,
+                                      int32_t T, int32_t obs_comp, const double* obs, double lp_const,
+                                      double* lp, double* grad, double* grad_y0, int32_t* stats, double* ckpt,
+                                      int32_t cap, double* vsave, void* stream) {
+  const Instance* inst = nullptr;
+  if (int rc = check_common(model, solver, B, y0, params, save_ts, T, &inst)) return rc;
+  if (obs_comp < 0 || obs_comp >= ncomp(model->flow)) return fail("obs_comp out of range");
+  if (!obs || !lp || !grad || !stats) return fail("obs/lp/grad/stats must not be null");
+  if (!ckpt || !vsave || cap < 1) return fail("the adjoint needs checkpoint scratch (ckpt, vsave, cap >= 1)");
+  if (T < 2) return fail("need at least two save times to form increments");
+  if (solver->n_jump > 0) return fail("unsupported: discontinuity points together with the adjoint");
+  AdjointArgs a;
+  fill_common(a.s, solver, B, y0, params, save_ts, T);
+  a.s.stats = stats;
+  a.s.obs_comp = obs_comp;
+  a.s.obs = obs;
+  a.s.lp_const = lp_const;
+  a.s.lp = lp;
+  a.grad = grad;
+  a.grad_y0 = grad_y0;
+  a.ckpt = ckpt;
+  a.vsave = vsave;
+  a.cap = cap;
+  if (B == 0) return 0;
+  const cudaError_t e = inst->adjoint(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int64_t dynode_probe_dfma(double* sink, int32_t iters, void* stream) {

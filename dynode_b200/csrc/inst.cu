@@ -1,5 +1,5 @@
 // inst.cu -- explicit instantiation of the kernels of ONE flow-family instance (-DDYN_INST=k).
-#include "lane_solver.cuh"
+#include "adjoint_solver.cuh"
 
 #ifndef DYN_INST
 #error "compile with -DDYN_INST=<index from instances.def>"
@@ -19,5 +19,7 @@ template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_c
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_SAVE_JUMPS>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
+
+template cudaError_t launch_adjoint_solver<I::flow, I::flags, I::g, I::s>(const AdjointArgs&, cudaStream_t);
 
 }  // namespace dynode

@@ -62,6 +62,18 @@ struct SolveArgs {
   double* grad;  // [B][P_total]
 };
 
+// Discrete-adjoint log-likelihood kernel (adjoint_solver.cuh)
+struct AdjointArgs {
+  SolveArgs s;        // B, y0, prm, save_ts, T, t0, t1, rtol, atol, max_steps, obs_comp, obs, lp_const, lp, stats
+  double* grad;       // [B][4*S + 2]: d lp / d (beta_s, gamma_s, sigma_s, omega_s, season_amp, season_phase)
+  double* grad_y0;    // [B][n] or NULL
+  double* ckpt;       // scratch [B][cap][n + 2]: per accepted step (tprev, tnext, y_k)
+  double* vsave;      // scratch [B][T][m]: observed compartment at the save times, then its cotangent
+  int32_t cap;        // accepted steps that fit the scratch
+};
+template <int FLOW, int FLAGS, int G, int S>
+cudaError_t launch_adjoint_solver(const AdjointArgs& a, cudaStream_t stream);
+
 // Defined in lane_solver.cuh, explicitly instantiated per model in inst.cu (see instances.def).
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
 cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream);

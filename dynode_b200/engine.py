@@ -236,3 +236,46 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
         d0.data_ptr() if d0 is not None else None, lp.data_ptr(), grad.data_ptr(), stats.data_ptr(),
         ctypes.c_void_p(_lib.current_stream_ptr())))
     return lp, (grad[:, :P] if P else None), stats
+
+
+_SCRATCH: Dict[tuple, object] = {}
+
+
+def _scratch(torch, dev, name: str, numel: int):
+    """Grow-only device scratch (checkpoints of the adjoint): reused across calls, so a NUTS run allocates
+    it once and a CUDA-graph capture sees a stable address."""
+    key = (dev.index, name)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < numel:
+        t = torch.empty(int(numel), dtype=torch.float64, device=dev)
+        _SCRATCH[key] = t
+    return t
+
+
+def poisson_loglik_adjoint(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions, save_ts,
+                           obs_comp: int, obs, lp_const: float = 0.0, with_y0_grad: bool = False,
+                           B: Optional[int] = None, cap: int = 512):
+    """Fused solve + Poisson-incidence log-likelihood + gradient w.r.t. ALL rates (and y0) by the discrete
+    adjoint: returns (lp[B], grad[B, 4*S+2] ordered (beta_s, gamma_s, sigma_s, omega_s, amp, phase),
+    grad_y0[B, n] or None, stats[B, 4]).  `cap` bounds the accepted steps per trajectory that fit the
+    checkpoint scratch (stats result == 2 and NaN outputs beyond it)."""
+    b = _Bound(model, y0, params, contact, save_ts, B, opts)
+    torch = b.torch
+    m = model.compartment_sizes()[obs_comp]
+    obs_t = _dev_f64(torch, obs, b.dev)
+    if obs_t.numel() != (b.T - 1) * m:
+        raise ValueError(f"obs must be [{b.T - 1}][{m}], got {tuple(obs_t.shape)}")
+    S, n = model.n_strains, model.state_size
+    lp = torch.empty((b.B,), dtype=torch.float64, device=b.dev)
+    grad = torch.empty((b.B, 4 * S + 2), dtype=torch.float64, device=b.dev)
+    g0 = torch.empty((b.B, n), dtype=torch.float64, device=b.dev) if with_y0_grad else None
+    stats = torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
+    ckpt = _scratch(torch, b.dev, "ckpt", b.B * cap * (n + 2))
+    vsave = _scratch(torch, b.dev, "vsave", b.B * b.T * m)
+    md, sd = model.desc(), opts.desc(b.save_dt)
+    _lib.check(_lib.load().dynode_poisson_loglik_adjoint_f64(
+        ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T,
+        int(obs_comp), obs_t.data_ptr(), float(lp_const), lp.data_ptr(), grad.data_ptr(),
+        g0.data_ptr() if g0 is not None else None, stats.data_ptr(), ckpt.data_ptr(), int(cap), vsave.data_ptr(),
+        ctypes.c_void_p(_lib.current_stream_ptr())))
+    return lp, grad, g0, stats

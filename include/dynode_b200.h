@@ -96,7 +96,7 @@ enum { DYNODE_P_BETA = 0, DYNODE_P_GAMMA = 1, DYNODE_P_SIGMA = 2, DYNODE_P_OMEGA
 
 /* stats row per trajectory */
 enum { DYNODE_STAT_RESULT = 0, DYNODE_STAT_ACCEPTED = 1, DYNODE_STAT_REJECTED = 2, DYNODE_STAT_STEPS = 3 };
-enum { DYNODE_RESULT_OK = 0, DYNODE_RESULT_MAX_STEPS = 1 };
+enum { DYNODE_RESULT_OK = 0, DYNODE_RESULT_MAX_STEPS = 1, DYNODE_RESULT_ADJOINT_CAPACITY = 2 };
 
 int dynode_version(void);
 const char* dynode_last_error(void);
@@ -139,6 +139,21 @@ int dynode_poisson_loglik_grad_f64(const DynodeModelDesc* model, const DynodeSol
                                    int32_t T, int32_t obs_comp, const double* obs, double lp_const,
                                    int32_t n_wrt, const int32_t* wrt, const double* dy0, double* lp,
                                    double* grad, int32_t* stats, void* stream);
+
+/* Same log-likelihood with its gradient w.r.t. EVERY rate and (optionally) the initial state from one
+ * reverse sweep over the accepted steps -- the discrete adjoint of the frozen-step scheme, i.e. what the
+ * reference's reverse-mode pass through diffeqsolve yields (odes.py:133-144 with diffrax's default
+ * RecursiveCheckpointAdjoint).  Cost ~4.5 solves whatever the number of parameters.
+ *   grad     [B][4*S + 2]   d lp / d (beta_s, gamma_s, sigma_s, omega_s, season_amp, season_phase)
+ *   grad_y0  [B][n] or NULL d lp / d y0
+ *   ckpt     scratch [B][cap][n + 2]  (tprev, tnext, y_k) of every accepted step; a trajectory that accepts
+ *            more than `cap` steps reports DYNODE_RESULT_ADJOINT_CAPACITY and NaN outputs
+ *   vsave    scratch [B][T][m] */
+int dynode_poisson_loglik_adjoint_f64(const DynodeModelDesc* model, const DynodeSolverDesc* solver, int64_t B,
+                                      DynodeArray y0, const DynodeParams* params, const double* save_ts,
+                                      int32_t T, int32_t obs_comp, const double* obs, double lp_const,
+                                      double* lp, double* grad, double* grad_y0, int32_t* stats, double* ckpt,
+                                      int32_t cap, double* vsave, void* stream);
 
 /* Bench / roofline helpers: dependency-free FP64 FMA loop (returns flops done per launch) and a
  * streaming write, both enqueued on `stream`. */

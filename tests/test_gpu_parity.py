@@ -181,3 +181,58 @@ def test_discontinuity_points_match_oracle(name):
     _assert_close(ys, ref)
     ys0, _, st0 = _run_engine(case, t1)
     assert not np.array_equal(st, st0)
+
+
+@pytest.mark.parametrize("name,obs_comp", [("sir_age2", 2), ("seirs_multi_a2s3", 4), ("seirs_seasonal", 3),
+                                           ("seirs_multi_g6s3", 4), ("sir_density", 0), ("seirs_multi_g3s2", 2)])
+def test_discrete_adjoint_equals_forward_sensitivities(name, obs_comp):
+    """dynode_poisson_loglik_adjoint_f64 (one reverse sweep, all parameters + y0) against
+    dynode_poisson_loglik_grad_f64 (forward tangents, one direction at a time): same lp, same gradient."""
+    import torch
+    from dynode_b200 import _lib
+    from dynode_b200.engine import SolverOptions, poisson_loglik_adjoint, poisson_loglik_grad
+    from oracle import oracle as orc
+    B = 41
+    case = make_case(name, B)
+    model = case["model"]
+    S, n = model.n_strains, model.state_size
+    t1 = 90
+    fam, dims, theta, shared = case["oracle"]
+    sizes = model.compartment_sizes()
+    lo = sum(sizes[:obs_comp])
+    idx = list(range(lo, lo + sizes[obs_comp]))
+    truth, _, _ = orc.solve(fam, dims, case["y0"][:1] if np.ndim(case["y0"]) == 2 else case["y0"], theta[:1], shared,
+                            t1=t1, save_idx=idx)
+    obs = np.abs(np.diff(truth[0], axis=0)) + 0.05
+    ts = np.linspace(0.0, t1, t1 + 1)
+    kinds = [_lib.P_BETA, _lib.P_GAMMA] + ([_lib.P_SIGMA, _lib.P_OMEGA] if model.flow != _lib.FLOW_SIR else [])
+    wrt = [_lib.wrt_id(k, s) for k in kinds for s in range(S)]
+    cols = [k * S + s for k in kinds for s in range(S)]
+    if model.flags & _lib.FLAG_SEASONAL:
+        wrt += [_lib.wrt_id(_lib.P_SEASON_AMP, 0), _lib.wrt_id(_lib.P_SEASON_PHASE, 0)]
+        cols += [4 * S, 4 * S + 1]
+    y0 = np.broadcast_to(case["y0"], (B, n)).copy()
+    # forward mode, including the initial-state directions
+    dy0 = np.zeros((B, len(wrt) + n, n))
+    dy0[:, len(wrt):, :] = np.eye(n)
+    lp_f, g_f, st_f = poisson_loglik_grad(model, y0, case["params"], case["contact"], SolverOptions(t1=t1), ts,
+                                          obs_comp, obs, 1.5, wrt=wrt + [-1] * n, dy0=dy0)
+    lp_a, g_a, g0_a, st_a = poisson_loglik_adjoint(model, y0, case["params"], case["contact"], SolverOptions(t1=t1),
+                                                   ts, obs_comp, obs, 1.5, with_y0_grad=True)
+    torch.cuda.synchronize()
+    assert torch.equal(st_f, st_a) and int((st_a[:, 0] != 0).sum()) == 0
+    assert torch.allclose(lp_a, lp_f, rtol=1e-12)
+    gf = g_f.cpu().numpy()
+    ga = g_a.cpu().numpy()[:, cols]
+    scale = np.abs(gf[:, :len(wrt)]).max(axis=0, keepdims=True) + 1e-300
+    assert np.all(np.abs(ga - gf[:, :len(wrt)]) <= 1e-8 * np.abs(gf[:, :len(wrt)]) + 1e-9 * scale)
+    g0f = gf[:, len(wrt):]
+    g0a = g0_a.cpu().numpy()
+    assert np.all(np.abs(g0a - g0f) <= 1e-8 * np.abs(g0f) + 1e-9 * np.abs(g0f).max())
+    # parameters the flow does not have get a zero gradient
+    others = [c for c in range(4 * S + 2) if c not in cols]
+    assert np.all(g_a.cpu().numpy()[:, others] == 0.0)
+    # checkpoint capacity exceeded -> flagged, NaN, no crash
+    lp_c, g_c, _, st_c = poisson_loglik_adjoint(model, y0, case["params"], case["contact"], SolverOptions(t1=t1),
+                                                ts, obs_comp, obs, 0.0, cap=3)
+    assert bool((st_c[:, 0] == 2).all()) and bool(torch.isnan(lp_c).all()) and bool(torch.isnan(g_c).all())
