@@ -234,6 +234,23 @@ def nuts_leg(args, dev, world, barrier):
         e1.record()
         barrier()
         ms5 = e0.elapsed_time(e1) / 3
+        def k5a():
+            return engine.poisson_loglik_adjoint(case5["model"], y05, prm5, c5, o5, ts5, 4, obs5, 0.0, B=B5, cap=256)
+
+        for _ in range(2):
+            k5a()
+        barrier()
+        e0.record()
+        for _ in range(3):
+            lpa, ga, _, sta = k5a()
+        e1.record()
+        barrier()
+        ms5a = e0.elapsed_time(e1) / 3
+        out["kernel_config5_adjoint"] = {
+            "value": world * B5 / (ms5a * 1e-3), "draws_per_gpu": B5, "ms_per_launch": ms5a,
+            "directions": "all 12 rates (+ y0 on request) from one reverse sweep",
+            "max_abs_diff_lp_vs_forward": float((lpa - lp5).abs().max()),
+            "max_rel_diff_grad_vs_forward": float(((ga[:, :6] - g5).abs() / (g5.abs() + 1e-300)).max())}
         out["kernel_config5"] = {"value": world * B5 / (ms5 * 1e-3), "draws_per_gpu": B5, "ms_per_launch": ms5,
                                  "directions": 6, "tangent_groups_in_one_launch": 6,
                                  "config": "C5 age(3) x risk(2) x strain(3) SEIRS + C (n=78), 120 d, Poisson on diff(C)"}

@@ -207,6 +207,48 @@ class EnsembleSolve(torch.autograd.Function):
         return (ys, stats, dys), (0, 0, 0)
 
 
+def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions) -> bool:
+    """Forward sensitivities cost (1 + chunk) solves per group of `chunk` directions; the discrete adjoint
+    ~4.5 solves in total (measured: profiles/r1/adjoint_vs_forward.md).  DYNODE_B200_ADJOINT=0/1 forces one."""
+    import os
+    force = os.environ.get("DYNODE_B200_ADJOINT")
+    if force is not None:
+        return force == "1" and n_dir > 0
+    if n_dir == 0 or len(opts.jump_ts) > 0:
+        return False
+    chunk = 2 if model.flow == _lib.FLOW_SIR else 1
+    groups = -(-n_dir // chunk)
+    return groups * (1 + chunk) > ADJOINT_COST
+
+
+ADJOINT_COST = 5.0  # solves-equivalent of one adjoint evaluation (forward + reverse sweep)
+
+
+def adjoint_capacity() -> int:
+    import os
+    return int(os.environ.get("DYNODE_B200_ADJOINT_CAP", "512"))
+
+
+_ADJ_COLS = {}
+
+
+def _adjoint_columns(cfg: SolveConfig, device) -> torch.Tensor:
+    """Columns of the adjoint's [4*S + 2] gradient row that correspond to cfg.wrt_cols (cached on device)."""
+    key = (device.index, cfg.layout, cfg.wrt_cols, cfg.model.n_strains)
+    t = _ADJ_COLS.get(key)
+    if t is None:
+        S = cfg.model.n_strains
+        base = {"beta": 0, "gamma": S, "sigma": 2 * S, "omega": 3 * S, "season_amp": 4 * S, "season_phase": 4 * S + 1}
+        cols = []
+        for col in cfg.wrt_cols:
+            for kind, first, width in cfg.layout:
+                if first <= col < first + width:
+                    cols.append(base[kind] + (col - first))
+        t = torch.tensor(cols, dtype=torch.long, device=device)
+        _ADJ_COLS[key] = t
+    return t
+
+
 class PoissonLoglik(torch.autograd.Function):
     """(y0 [B|1, n], theta [B|1, K]) -> (lp [B], stats [B, 4]); gradient from the same launch."""
 
@@ -216,6 +258,16 @@ class PoissonLoglik(torch.autograd.Function):
         if cfg.y0_grad and y0c.shape[0] != B:
             y0c = y0c.expand(B, y0c.shape[1]).contiguous()
         pl = cfg.payload
+        n_dir = len(cfg.wrt_cols) + (cfg.model.state_size if cfg.y0_grad else 0)
+        if use_adjoint(cfg.model, n_dir, cfg.opts()):
+            # one reverse sweep gives d lp / d (every rate, y0); pick the columns that were asked for
+            lp, g_all, g_y0, stats = engine.poisson_loglik_adjoint(
+                cfg.model, y0c, _kernel_params(cfg, th), pl.contact, cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs,
+                pl.lp_const, with_y0_grad=cfg.y0_grad, B=B, cap=adjoint_capacity())
+            grad = g_all.index_select(1, _adjoint_columns(cfg, th.device))
+            if cfg.y0_grad:
+                grad = torch.cat([grad, g_y0], dim=1)
+            return lp, stats, grad
         lp, grad, stats = engine.poisson_loglik_grad(cfg.model, y0c, _kernel_params(cfg, th), pl.contact,
                                                      cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs, pl.lp_const,
                                                      wrt=cfg.wrt_ids(), dy0=_seeds(cfg, B, th.device), B=B)
