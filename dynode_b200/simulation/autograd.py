@@ -207,9 +207,14 @@ class EnsembleSolve(torch.autograd.Function):
         return (ys, stats, dys), (0, 0, 0)
 
 
-def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions) -> bool:
-    """Forward sensitivities cost (1 + chunk) solves per group of `chunk` directions; the discrete adjoint
-    ~4.5 solves in total (measured: profiles/r1/adjoint_vs_forward.md).  DYNODE_B200_ADJOINT=0/1 forces one."""
+def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions, B: int = 1 << 30) -> bool:
+    """Forward sensitivities or the discrete adjoint for the fused log-likelihood gradient?
+
+    Measured on B200 (profiles/r1/adjoint_vs_forward.md), in units of one primal solve: the adjoint costs
+    ~3.2 whatever the number of directions; forward mode ~1.45 per direction (4/5-element lanes, one direction
+    per group) or ~1.9 per pair of directions (SIR lanes).  But the forward groups are independent work items of
+    one launch, so while they do not fill the GPU (few NUTS chains) their latency is that of ONE group and they
+    win up to ~8 groups.  DYNODE_B200_ADJOINT=0/1 forces a choice."""
     import os
     force = os.environ.get("DYNODE_B200_ADJOINT")
     if force is not None:
@@ -218,10 +223,15 @@ def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions)
         return False
     chunk = 2 if model.flow == _lib.FLOW_SIR else 1
     groups = -(-n_dir // chunk)
-    return groups * (1 + chunk) > ADJOINT_COST
+    slots = max(1, 32 // (model.n_groups * model.n_strains))
+    warps = -(-B // slots) * groups
+    if warps <= RESIDENT_WARPS:  # latency regime
+        return groups > 8
+    return groups * (1.9 if chunk == 2 else 1.45) > ADJOINT_COST
 
 
-ADJOINT_COST = 5.0  # solves-equivalent of one adjoint evaluation (forward + reverse sweep)
+ADJOINT_COST = 3.2      # primal-solve equivalents of one adjoint evaluation (forward + reverse sweep)
+RESIDENT_WARPS = 1184   # 148 SMs x 8 warps of the 255-register tangent / adjoint kernels
 
 
 def adjoint_capacity() -> int:
@@ -259,7 +269,7 @@ class PoissonLoglik(torch.autograd.Function):
             y0c = y0c.expand(B, y0c.shape[1]).contiguous()
         pl = cfg.payload
         n_dir = len(cfg.wrt_cols) + (cfg.model.state_size if cfg.y0_grad else 0)
-        if use_adjoint(cfg.model, n_dir, cfg.opts()):
+        if use_adjoint(cfg.model, n_dir, cfg.opts(), B):
             # one reverse sweep gives d lp / d (every rate, y0); pick the columns that were asked for
             lp, g_all, g_y0, stats = engine.poisson_loglik_adjoint(
                 cfg.model, y0c, _kernel_params(cfg, th), pl.contact, cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs,
