@@ -134,8 +134,45 @@ struct LaneSolver {
   }
 
   // ---- right-hand side of the flow family in lane layout -------------
+  // sin / cos of the seasonal angle 2*pi*t/period + phase (seirs_seasonal_forcing.py:34-37)
+  static DYN_DI void season_angle(double t, const Prm& p, double& sn, double& cs) {
+    const double w = ((2.0 * CUDART_PI) * t) / p.period;
+    sincos(p.phase.v + w, &sn, &cs);
+  }
+  // sin / cos of a small increment |d| <= 0.5 by Taylor series in d^2 (remainder < 1e-18): 16 FMAs instead of
+  // a libm sincos (~75 instructions, a third of them 64-bit constant moves); used with the angle-addition
+  // formulas for the stage times inside a step, the base angle being evaluated exactly once per step
+  static DYN_DI void sincos_small(double d, double& sd, double& cd) {
+    const double z = d * d;
+    double ps = -1.0 / 1307674368000.0;
+    ps = fma(ps, z, 1.0 / 6227020800.0);
+    ps = fma(ps, z, -1.0 / 39916800.0);
+    ps = fma(ps, z, 1.0 / 362880.0);
+    ps = fma(ps, z, -1.0 / 5040.0);
+    ps = fma(ps, z, 1.0 / 120.0);
+    ps = fma(ps, z, -1.0 / 6.0);
+    sd = fma(d * z, ps, d);
+    double pc = 1.0 / 20922789888000.0;
+    pc = fma(pc, z, -1.0 / 87178291200.0);
+    pc = fma(pc, z, 1.0 / 479001600.0);
+    pc = fma(pc, z, -1.0 / 3628800.0);
+    pc = fma(pc, z, 1.0 / 40320.0);
+    pc = fma(pc, z, -1.0 / 720.0);
+    pc = fma(pc, z, 1.0 / 24.0);
+    pc = fma(pc, z, -0.5);
+    cd = fma(z, pc, 1.0);
+  }
+
   static DYN_DI void rhs(double t, const D (&y)[NE], D (&dy)[NE], const Geo& c, const double (&K)[G],
                          const Prm& p, const D& invN) {
+    double sn = 0.0, cs = 1.0;
+    if constexpr (SEASONAL) season_angle(t, p, sn, cs);
+    rhs_sc(sn, cs, y, dy, c, K, p, invN);
+  }
+
+  // the right-hand side with the seasonal sine / cosine already known
+  static DYN_DI void rhs_sc(double sn, double cs, const D (&y)[NE], D (&dy)[NE], const Geo& c,
+                            const double (&K)[G], const Prm& p, const D& invN) {
     D prop;
     if constexpr (DENSITY) {
       prop = y[II];  // tests/test_simulation/test_odes.py:23  s_to_i = beta*s*i
@@ -154,16 +191,11 @@ struct LaneSolver {
     D beta_t = p.beta;
     if constexpr (SEASONAL) {
       // beta*(1 + amp*sin(2*pi*t/period + phase))   (seirs_seasonal_forcing.py:34-37)
-      const double w = ((2.0 * CUDART_PI) * t) / p.period;
-      D arg = p.phase;
-      arg.v += w;
-      double sn, cs;
-      sincos(arg.v, &sn, &cs);
       D seas;
       seas.v = fma(p.amp.v, sn, 1.0);
       if constexpr (P > 0) {
 #pragma unroll
-        for (int k = 0; k < P; ++k) seas.d[k] = fma(p.amp.d[k], sn, p.amp.v * cs * arg.d[k]);
+        for (int k = 0; k < P; ++k) seas.d[k] = fma(p.amp.d[k], sn, p.amp.v * cs * p.phase.d[k]);
       }
       beta_t = p.beta * seas;
     }
@@ -280,6 +312,7 @@ struct LaneSolver {
     double tprev = t1, tnext = t1;
     int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
     bool active = false;
+    double sn0 = 0.0, cs0 = 1.0;  // seasonal sine / cosine at tprev of my slot (exact, libm)
     bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
     double* out_s = a.ys;  // running output pointers of the full-save fast path
     double* out_c = a.ys;
@@ -404,6 +437,7 @@ struct LaneSolver {
             p0s = cand_p0;
             wp = a.write_primal && cand_p0 == 0;
             tprev = a.t0;
+            if constexpr (SEASONAL) season_angle(a.t0, pn, sn0, cs0);
             if constexpr (JUMPS) tn = clip_to_jumps(a, a.t0, tn, made_jump);
             tnext = fmin(tn, t1);
             n_acc = n_rej = n_steps = 0;
@@ -495,32 +529,64 @@ struct LaneSolver {
 #pragma unroll
         for (int b = 0; b < G; ++b) Kl[b] = Kr[b];
       }
-      auto stage_rhs = [&](double t, D (&out)[NE]) { rhs(t, ys, out, c, Kl, pl, invN); };
+      // Seasonal angles of the step: the angle at tnext exactly (libm, shared by the two c = 1 stages and
+      // -- through FSAL -- the next step's first stage), the four inner stage times by angle addition from
+      // the exact angle at tprev with Taylor sin/cos of the increment 2*pi*c_i*h/period (<= 0.5 rad, else libm)
+      double sn1 = 0.0, cs1 = 1.0, wstep = 0.0;
+      bool small_step = true;
+      if constexpr (SEASONAL) {
+        season_angle(tnext, pl, sn1, cs1);
+        wstep = ((2.0 * CUDART_PI) * h) / pl.period;
+        small_step = !__any_sync(0xffffffffu, fabs(wstep) > 0.5);
+      }
+      auto stage_rhs = [&](double t, double ci, D (&out)[NE]) {  // inner stage at t = tprev + ci*h
+        if constexpr (SEASONAL) {
+          double sn, cs;
+          if (small_step) {
+            double sd, cd;
+            sincos_small(ci * wstep, sd, cd);
+            sn = fma(sn0, cd, cs0 * sd);
+            cs = fma(cs0, cd, -(sn0 * sd));
+          } else {
+            season_angle(t, pl, sn, cs);
+          }
+          rhs_sc(sn, cs, ys, out, c, Kl, pl, invN);
+        } else {
+          rhs(t, ys, out, c, Kl, pl, invN);
+        }
+      };
+      auto end_rhs = [&](D (&out)[NE]) {  // the two stages at t = tnext
+        if constexpr (SEASONAL) {
+          rhs_sc(sn1, cs1, ys, out, c, Kl, pl, invN);
+        } else {
+          rhs(tnext, ys, out, c, Kl, pl, invN);
+        }
+      };
       // ---- Tsit5 stages 2..7 (6 new RHS evaluations; stage 7 = y1 (SSAL) and next f0 (FSAL))
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, T5_a21 * f[0][e], y[e]);
-      stage_rhs(fma(T5_c2, h, tprev), f[1]);
+      stage_rhs(fma(T5_c2, h, tprev), T5_c2, f[1]);
 #pragma unroll
       for (int e = 0; e < NE; ++e) ys[e] = dfma(h, dfma(T5_a32, f[1][e], T5_a31 * f[0][e]), y[e]);
-      stage_rhs(fma(T5_c3, h, tprev), f[2]);
+      stage_rhs(fma(T5_c3, h, tprev), T5_c3, f[2]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a43, f[2][e], dfma(T5_a42, f[1][e], T5_a41 * f[0][e])), y[e]);
-      stage_rhs(fma(T5_c4, h, tprev), f[3]);
+      stage_rhs(fma(T5_c4, h, tprev), T5_c4, f[3]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a54, f[3][e], dfma(T5_a53, f[2][e], dfma(T5_a52, f[1][e], T5_a51 * f[0][e]))), y[e]);
-      stage_rhs(fma(T5_c5, h, tprev), f[4]);
+      stage_rhs(fma(T5_c5, h, tprev), T5_c5, f[4]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a65, f[4][e], dfma(T5_a64, f[3][e], dfma(T5_a63, f[2][e],
                      dfma(T5_a62, f[1][e], T5_a61 * f[0][e])))), y[e]);
-      stage_rhs(tnext, f[5]);
+      end_rhs(f[5]);
 #pragma unroll
       for (int e = 0; e < NE; ++e)
         ys[e] = dfma(h, dfma(T5_a76, f[5][e], dfma(T5_a75, f[4][e], dfma(T5_a74, f[3][e], dfma(T5_a73, f[2][e],
                      dfma(T5_a72, f[1][e], T5_a71 * f[0][e]))))), y[e]);
-      stage_rhs(tnext, f[6]);  // ys is y1
+      end_rhs(f[6]);  // ys is y1
 
       // ---- dense-output coefficients, formed unconditionally right after the last stage so their
       // independent FMAs overlap the latency-bound error-norm / controller chain below.
@@ -678,6 +744,7 @@ struct LaneSolver {
           ++n_acc;
 #pragma unroll
           for (int e = 0; e < NE; ++e) { y[e] = ys[e]; f[0][e] = f[6][e]; }
+          if constexpr (SEASONAL) { sn0 = sn1; cs0 = cs1; }
         } else {
           ++n_rej;
         }
