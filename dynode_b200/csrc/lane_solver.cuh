@@ -653,12 +653,20 @@ struct LaneSolver {
       if (__any_sync(0xffffffffu, ts_next <= tnext)) {
         const double inv_h = rcp_fast((tnext == tprev) ? 1.0 : h);
         const double hw = h * kDense[0][0];
+        // offloaded kernels bring Q back into registers ONCE per step (the stage derivatives f1..f5 are
+        // dead by now); read inside the save loop it was re-fetched after every global store (12 LDS per pass,
+        // 9 passes per step for the 32-slot warps: profiles/r1/ncu_full_c3_lane_solver.md)
+        D Qs[3][NE];
+        if constexpr (OFFLOAD) {
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int e = 0; e < NE; ++e) Qs[m][e] = make_dual<P>(my[(OFF_Q + m * NE + e) * kThreads]);
+        }
         auto dense = [&](int e, double th, double hthw, double hth2) -> D {
           D q0, q1, q2;
           if constexpr (OFFLOAD) {
-            q0 = make_dual<P>(my[(OFF_Q + 0 * NE + e) * kThreads]);
-            q1 = make_dual<P>(my[(OFF_Q + 1 * NE + e) * kThreads]);
-            q2 = make_dual<P>(my[(OFF_Q + 2 * NE + e) * kThreads]);
+            q0 = Qs[0][e]; q1 = Qs[1][e]; q2 = Qs[2][e];
           } else {
             q0 = Q[0][e]; q1 = Q[1][e]; q2 = Q[2][e];
           }
