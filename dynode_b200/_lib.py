@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "dynode_saved_size", "dynode_is_supported", "dynode_solve_f64", "dynode_solve_sens_f64",
     "dynode_poisson_loglik_grad_f64", "dynode_poisson_loglik_adjoint_f64", "dynode_probe_dfma",
     "dynode_probe_hbm_write",
-    "dynode_nuts_round_pre", "dynode_nuts_round_post",
+    "dynode_nuts_round_pre", "dynode_nuts_round_post", "dynode_seip_state_size", "dynode_seip_solve_f64",
 )
 
 
@@ -55,6 +55,15 @@ class Params(ctypes.Structure):
     _fields_ = [("beta", Array), ("gamma", Array), ("sigma", Array), ("omega", Array),
                 ("season_amp", Array), ("season_phase", Array), ("season_period", Array),
                 ("contact", ctypes.c_void_p)]
+
+
+class SeipDesc(ctypes.Structure):
+    _fields_ = [("n_ages", ctypes.c_int32), ("n_strains", ctypes.c_int32), ("n_wane", ctypes.c_int32)]
+
+
+class SeipParams(ctypes.Structure):
+    _fields_ = [("beta", Array), ("sigma", Array), ("gamma", Array), ("omega", Array),
+                ("contact", ctypes.c_void_p), ("pop", ctypes.c_void_p), ("immunity", ctypes.c_void_p)]
 
 
 _NUTS_PTRS = (
@@ -106,6 +115,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_poisson_loglik_adjoint_f64.restype = ctypes.c_int
     L.dynode_poisson_loglik_adjoint_f64.argtypes = [MP, SP, i64, Array, PP, vp, i32, i32, vp, dbl, vp, vp, vp, vp,
                                                     vp, i32, vp, vp]
+    L.dynode_seip_state_size.restype = ctypes.c_int
+    L.dynode_seip_state_size.argtypes = [ctypes.POINTER(SeipDesc)]
+    L.dynode_seip_solve_f64.restype = ctypes.c_int
+    L.dynode_seip_solve_f64.argtypes = [ctypes.POINTER(SeipDesc), SP, i64, Array, ctypes.POINTER(SeipParams), vp, i32,
+                                        vp, vp, vp]
     NP = ctypes.POINTER(NutsState)
     L.dynode_nuts_round_pre.restype = ctypes.c_int
     L.dynode_nuts_round_pre.argtypes = [NP, vp, vp, vp]

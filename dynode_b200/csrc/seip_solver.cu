@@ -1,0 +1,352 @@
+// seip_solver.cu -- one thread block per trajectory for the immune-history / waning family
+// (include/dynode_b200_seip.h).  State, stage state and the 7 stage derivatives live in shared memory
+// (9*n doubles), each thread owns the elements e = tid, tid + blockDim, ...; the infectious totals per
+// (age, strain), the force of infection through the contact matrix and the RMS error norm are block-wide
+// steps separated by __syncthreads.  The integrator is the same restatement of
+// diffeqsolve(Tsit5, PIDController(rtol, atol), SaveAt(ts)) as lane_solver.cuh (reference
+// src/dynode/simulation/odes.py:107-144); the right-hand side follows
+// oracle/dynode_oracle.cpp FAM_SEIP term by term, in the same summation order.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/dynode_b200.h"
+#include "../../include/dynode_b200_seip.h"
+#include "tsit5.cuh"
+
+namespace dynode {
+
+int fail_msg(const char* fmt, ...);  // capi.cu
+
+namespace {
+
+constexpr int kSeipThreads = 128;
+
+struct SeipArgs {
+  int A, K, W, H, n;
+  int64_t B;
+  DynodeArray y0, beta, sigma, gamma, omega;
+  const double* contact;
+  const double* pop;
+  const double* imm;
+  double t0, t1, rtol, atol, const_dt, save_dt;
+  const double* save_ts;
+  int T;
+  int max_steps;
+  double* ys;
+  int32_t* stats;
+};
+
+// element -> (compartment, age, history, w or k), packed: comp in bits 30-31, a in 20-29, j in 10-19, x in 0-9
+__device__ __forceinline__ unsigned pack_meta(int comp, int a, int j, int x) {
+  return ((unsigned)comp << 30) | ((unsigned)a << 20) | ((unsigned)j << 10) | (unsigned)x;
+}
+
+struct Smem {
+  double *y, *ys, *f[7];
+  double *itot, *foi, *beta, *sigma, *gamma, *omega, *contact, *pop, *imm, *red;
+  unsigned* meta;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  // sum over the block, returned to every thread (4 warps)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();  // red[] may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  double t = red[0];
+  for (int k = 1; k < kSeipThreads / 32; ++k) t += red[k];
+  return t;
+}
+
+// dx = f(x): all threads call it; x and dx are shared-memory arrays of n doubles
+__device__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, double* dx) {
+  const int A = a.A, K = a.K, W = a.W, H = a.H;
+  const double* xS = x;
+  const double* xE = x + A * H * W;
+  const double* xI = xE + A * H * K;
+  for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
+    const int ag = q / K, k = q - ag * K;
+    double acc = xI[(ag * H + 0) * K + k];
+    for (int j = 1; j < H; ++j) acc += xI[(ag * H + j) * K + k];
+    sm.itot[q] = acc;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
+    const int ag = q / K, k = q - ag * K;
+    double acc = sm.contact[ag * A + 0] * (sm.itot[0 * K + k] / sm.pop[0]);
+    for (int b = 1; b < A; ++b) acc += sm.contact[ag * A + b] * (sm.itot[b * K + k] / sm.pop[b]);
+    sm.foi[q] = sm.beta[k] * acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < a.n; e += blockDim.x) {
+    const unsigned m = sm.meta[e];
+    const int comp = m >> 30, ag = (m >> 20) & 1023, j = (m >> 10) & 1023, xw = m & 1023;
+    double d;
+    if (comp == 0) {  // S[ag][j][w]
+      const int w = xw;
+      const double s = xS[e];
+      double out = 0.0;
+      for (int k = 0; k < K; ++k) out += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * s;
+      d = -out;
+      if (w > 0) d += sm.omega[w - 1] * xS[e - 1];
+      if (w < W - 1) d -= sm.omega[w] * s;
+      if (w == 0)
+        for (int k = 0; k < K; ++k)
+          if ((j >> k) & 1)
+            d += sm.gamma[k] * (xI[(ag * H + j) * K + k] + xI[(ag * H + (j ^ (1 << k))) * K + k]);
+    } else {  // E / I / C [ag][j][k]
+      const int k = xw;
+      const int q = (ag * H + j) * K + k;
+      if (comp == 2) {
+        d = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
+      } else {
+        double expo = 0.0;
+        for (int w = 0; w < W; ++w)
+          expo += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * xS[(ag * H + j) * W + w];
+        d = (comp == 1) ? expo - sm.sigma[k] * xE[q] : expo;
+      }
+    }
+    dx[e] = d;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArgs a) {
+  using namespace tsit5;
+  extern __shared__ double smem_raw[];
+  const int A = a.A, K = a.K, W = a.W, H = a.H, n = a.n;
+  Smem sm;
+  double* p = smem_raw;
+  sm.y = p; p += n;
+  sm.ys = p; p += n;
+  for (int i = 0; i < 7; ++i) { sm.f[i] = p; p += n; }
+  sm.itot = p; p += A * K;
+  sm.foi = p; p += A * K;
+  sm.beta = p; p += K;
+  sm.sigma = p; p += K;
+  sm.gamma = p; p += K;
+  sm.omega = p; p += W;
+  sm.contact = p; p += A * A;
+  sm.pop = p; p += A;
+  sm.imm = p; p += H * W * K;
+  sm.red = p; p += 8;
+  sm.meta = (unsigned*)p;
+
+  const int64_t traj = blockIdx.x;
+  const int tid = threadIdx.x;
+  // ---- stage the shared tables, this trajectory's rates and initial state, and the element map
+  for (int q = tid; q < K; q += blockDim.x) {
+    sm.beta[q] = a.beta.ptr[traj * a.beta.batch_stride + q];
+    sm.sigma[q] = a.sigma.ptr[traj * a.sigma.batch_stride + q];
+    sm.gamma[q] = a.gamma.ptr[traj * a.gamma.batch_stride + q];
+  }
+  for (int q = tid; q < W; q += blockDim.x) sm.omega[q] = a.omega.ptr[traj * a.omega.batch_stride + q];
+  for (int q = tid; q < A * A; q += blockDim.x) sm.contact[q] = a.contact[q];
+  for (int q = tid; q < A; q += blockDim.x) sm.pop[q] = a.pop[q];
+  for (int q = tid; q < H * W * K; q += blockDim.x) sm.imm[q] = a.imm[q];
+  const int nS = A * H * W, nX = A * H * K;
+  for (int e = tid; e < n; e += blockDim.x) {
+    sm.y[e] = a.y0.ptr[traj * a.y0.batch_stride + e];
+    if (e < nS) {
+      const int ag = e / (H * W), r = e - ag * H * W;
+      sm.meta[e] = pack_meta(0, ag, r / W, r % W);
+    } else {
+      const int comp = 1 + (e - nS) / nX, r0 = (e - nS) % nX;
+      const int ag = r0 / (H * K), r = r0 - ag * H * K;
+      sm.meta[e] = pack_meta(comp, ag, r / K, r % K);
+    }
+  }
+  __syncthreads();
+
+  const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
+  const double inv_n = 1.0 / (double)n;
+  auto save_time = [&](int k) -> double {
+    if (k >= a.T) return CUDART_INF;
+    if (a.save_dt > 0.0) return (k == a.T - 1) ? a.t1 : fma((double)k, a.save_dt, a.t0);
+    return a.save_ts[k];
+  };
+
+  // ---- FSAL f0 and the initial step (Hairer-Wanner, PIDController._select_initial_step)
+  seip_rhs(a, sm, sm.y, sm.f[0]);
+  double tprev = a.t0, tnext;
+  if (a.const_dt > 0.0) {
+    tnext = a.t0 + a.const_dt;
+  } else {
+    double p0 = 0.0, p1 = 0.0;
+    for (int e = tid; e < n; e += blockDim.x) {
+      const double sc = atol + fabs(sm.y[e]) * rtol;
+      const double u = sm.y[e] / sc, v = sm.f[0][e] / sc;
+      p0 += u * u;
+      p1 += v * v;
+    }
+    const double d0 = sqrt(block_sum(p0, sm.red) * inv_n);
+    const double d1 = sqrt(block_sum(p1, sm.red) * inv_n);
+    const bool small = (d0 < 1e-5) || (d1 < 1e-5);
+    const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
+    for (int e = tid; e < n; e += blockDim.x) sm.ys[e] = sm.y[e] + h0 * sm.f[0][e];
+    __syncthreads();
+    seip_rhs(a, sm, sm.ys, sm.f[1]);
+    double p2 = 0.0;
+    for (int e = tid; e < n; e += blockDim.x) {
+      const double sc = atol + fabs(sm.y[e]) * rtol;
+      const double u = (sm.f[1][e] - sm.f[0][e]) / sc;
+      p2 += u * u;
+    }
+    const double d2 = sqrt(block_sum(p2, sm.red) * inv_n) / h0;
+    const double md = fmax(d1, d2);
+    const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
+    tnext = a.t0 + fmin(100.0 * h0, h1);
+  }
+  tnext = fmin(tnext, t1);
+
+  // tableau rows a_{s+1, 1..s} inside kTab (tsit5.cuh TabIdx order)
+  const int row_base[6] = {I_a21, I_a31, I_a41, I_a51, I_a61, I_a71};
+  const int c_idx[4] = {I_c2, I_c3, I_c4, I_c5};
+  int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
+  double* const out = a.ys + traj * (int64_t)a.T * n;
+
+  while (tprev < t1 && n_steps < a.max_steps) {
+    const double h = tnext - tprev;
+    // ---- Tsit5 stages 2..7
+    for (int s = 1; s <= 6; ++s) {
+      const int base = row_base[s - 1];
+      for (int e = tid; e < n; e += blockDim.x) {
+        double acc = kTab[base] * sm.f[0][e];
+        for (int j = 1; j < s; ++j) acc = fma(kTab[base + j], sm.f[j][e], acc);
+        sm.ys[e] = fma(h, acc, sm.y[e]);
+      }
+      __syncthreads();
+      seip_rhs(a, sm, sm.ys, sm.f[s]);  // autonomous right-hand side: stage times c_idx[] are not needed
+    }
+    (void)c_idx;
+    // ---- embedded error, scaled RMS norm, I-controller
+    bool keep;
+    double dt_next;
+    if (a.const_dt > 0.0) {
+      keep = true;
+      dt_next = a.const_dt;
+    } else {
+      double part = 0.0;
+      for (int e = tid; e < n; e += blockDim.x) {
+        double er = kTab[I_e1] * sm.f[0][e];
+#pragma unroll
+        for (int i = 1; i < 7; ++i) er = fma(kTab[I_e1 + i], sm.f[i][e], er);
+        er *= h;
+        const double sc = fma(fmax(fabs(sm.y[e]), fabs(sm.ys[e])), rtol, atol);
+        const double r = er / sc;
+        part = fma(r, r, part);
+      }
+      const double err2 = block_sum(part, sm.red) * inv_n;
+      keep = err2 < 1.0;
+      dt_next = h * controller_factor_sq(err2, keep);
+    }
+    double ntprev = keep ? tnext : tprev;
+    double ntnext = ntprev + dt_next;
+    ntprev = fmin(ntprev, t1);
+    if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);
+    ++n_steps;
+    if (keep) {
+      ++n_acc;
+      // ---- SaveAt(ts): dense output for every ts[k] <= tnext; consecutive threads write consecutive elements
+      const double inv_h = 1.0 / ((tnext == tprev) ? 1.0 : h);
+      while (save_i < a.T && save_time(save_i) <= tnext) {
+        const double th = (save_time(save_i) - tprev) * inv_h;
+        double b[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          b[i] = th * fma(th, fma(th, fma(th, kDense[i][3], kDense[i][2]), kDense[i][1]), kDense[i][0]);
+        double* row = out + (int64_t)save_i * n;
+        for (int e = tid; e < n; e += blockDim.x) {
+          double acc = b[0] * sm.f[0][e];
+#pragma unroll
+          for (int i = 1; i < 7; ++i) acc = fma(b[i], sm.f[i][e], acc);
+          row[e] = fma(h, acc, sm.y[e]);
+        }
+        ++save_i;
+      }
+      __syncthreads();
+      for (int e = tid; e < n; e += blockDim.x) {
+        sm.y[e] = sm.ys[e];
+        sm.f[0][e] = sm.f[6][e];
+      }
+      __syncthreads();
+    } else {
+      ++n_rej;
+    }
+    tprev = ntprev;
+    tnext = ntnext;
+  }
+  // slots never reached keep diffrax's +inf fill
+  for (int k = save_i; k < a.T; ++k)
+    for (int e = tid; e < n; e += blockDim.x) out[(int64_t)k * n + e] = CUDART_INF;
+  if (tid == 0) {
+    int32_t* st = a.stats + traj * 4;
+    st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
+    st[DYNODE_STAT_ACCEPTED] = n_acc;
+    st[DYNODE_STAT_REJECTED] = n_rej;
+    st[DYNODE_STAT_STEPS] = n_steps;
+  }
+}
+
+size_t seip_smem_bytes(int A, int K, int W, int H, int n) {
+  const size_t doubles = (size_t)9 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * W * K + 8;
+  return doubles * sizeof(double) + (size_t)n * sizeof(unsigned);
+}
+
+}  // namespace
+}  // namespace dynode
+
+using namespace dynode;
+
+extern "C" {
+
+int dynode_seip_state_size(const DynodeSeipDesc* m) {
+  if (!m || m->n_ages < 1 || m->n_strains < 1 || m->n_strains > DYNODE_SEIP_MAX_STRAINS || m->n_wane < 1) return -1;
+  const int H = 1 << m->n_strains;
+  return m->n_ages * H * (m->n_wane + 3 * m->n_strains);
+}
+
+int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* sv, int64_t B, DynodeArray y0,
+                          const DynodeSeipParams* p, const double* save_ts, int32_t T, double* ys, int32_t* stats,
+                          void* stream) {
+  if (!model || !sv || !p) return fail_msg("null model/solver/params descriptor");
+  const int n = dynode_seip_state_size(model);
+  if (n < 0)
+    return fail_msg("unsupported ODE: SEIP dims ages=%d strains=%d wane=%d (1..%d strains); there is no CPU fallback",
+                    model->n_ages, model->n_strains, model->n_wane, DYNODE_SEIP_MAX_STRAINS);
+  if (n > DYNODE_SEIP_MAX_STATE || model->n_ages > 1023 || model->n_wane > 1023)
+    return fail_msg("unsupported ODE: SEIP state of %d doubles exceeds the %d a thread block can stage in shared "
+                    "memory; there is no CPU fallback", n, DYNODE_SEIP_MAX_STATE);
+  if (B < 0) return fail_msg("negative ensemble size");
+  if (!y0.ptr || !p->beta.ptr || !p->sigma.ptr || !p->gamma.ptr || !p->omega.ptr)
+    return fail_msg("y0/beta/sigma/gamma/omega are required");
+  if (!p->contact || !p->pop || !p->immunity) return fail_msg("contact/pop/immunity tables are required");
+  if (!save_ts || T <= 0 || !ys || !stats) return fail_msg("save_ts (T >= 1), ys and stats are required");
+  if (!(sv->t1 >= sv->t0)) return fail_msg("t1 must be >= t0");
+  if (!(sv->const_dt > 0.0) && !(sv->rtol > 0.0 && sv->atol > 0.0)) return fail_msg("rtol/atol must be positive");
+  if (sv->max_steps <= 0) return fail_msg("max_steps must be positive");
+  if (sv->n_jump > 0) return fail_msg("unsupported: discontinuity points in the SEIP kernel");
+  if (B == 0) return 0;
+  SeipArgs a;
+  a.A = model->n_ages; a.K = model->n_strains; a.W = model->n_wane; a.H = 1 << a.K; a.n = n;
+  a.B = B;
+  a.y0 = y0; a.beta = p->beta; a.sigma = p->sigma; a.gamma = p->gamma; a.omega = p->omega;
+  a.contact = p->contact; a.pop = p->pop; a.imm = p->immunity;
+  a.t0 = sv->t0; a.t1 = sv->t1; a.rtol = sv->rtol; a.atol = sv->atol; a.const_dt = sv->const_dt;
+  a.save_dt = sv->save_dt > 0.0 ? sv->save_dt : 0.0;
+  a.save_ts = save_ts; a.T = T;
+  a.max_steps = (int)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
+  a.ys = ys; a.stats = stats;
+  const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, n);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024)
+    e = cudaFuncSetAttribute(seip_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail_msg("shared memory request of %zu bytes refused: %s", smem, cudaGetErrorString(e));
+  seip_solver_kernel<<<(unsigned)B, kSeipThreads, smem, (cudaStream_t)stream>>>(a);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail_msg("kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+}  // extern "C"

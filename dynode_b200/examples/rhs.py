@@ -164,4 +164,36 @@ def seirs_multi_strain_ode(t: float, state: CompartmentState, p: SEIRS_MultiStra
     return (ds, de, di, dr, dc)
 
 
+# ------------------------------------------------------------------ reference ode_model.md:15-53 (prose model)
+@dataclass
+class SEIP_ODEParams(AbstractODEParams):
+    beta: Any  # (strains,)
+    sigma: Any  # (strains,)
+    gamma: Any  # (strains,)
+    omega: Any  # (wane,) waning rates, the last stage absorbs
+    contact_matrix: Any  # (age, age)
+    population: Any  # (age,)
+    immunity: Any  # (2^strains, wane, strains) protection in [0, 1]
+
+
+@flow_family("seip", sigma="sigma", omega="omega", contact="contact_matrix", population="population",
+             immunity="immunity")
+def seip_ode(t: float, state: CompartmentState, p: SEIP_ODEParams):
+    """S (age, hist, wane); E, I, C (age, hist, strain); hist = bit set of strains recovered from."""
+    s, e, i, c = state
+    K = e.shape[-1]
+    foi = p.beta * (p.contact_matrix @ (i.sum(1) / p.population[:, None]))  # (age, strain)
+    expo = foi[:, None, None, :] * (1.0 - p.immunity)[None] * s[..., None]  # (age, hist, wane, strain)
+    ds = -expo.sum(-1)
+    ds[..., 1:] += p.omega[:-1] * s[..., :-1]
+    ds[..., :-1] -= p.omega[:-1] * s[..., :-1]
+    for j in range(s.shape[1]):
+        for k in range(K):
+            if (j >> k) & 1:
+                ds[:, j, 0] += p.gamma[k] * (i[:, j, k] + i[:, j ^ (1 << k), k])
+    de = expo.sum(2) - p.sigma * e
+    di = p.sigma * e - p.gamma * i
+    return (ds, de, di, expo.sum(2))
+
+
 __all__ = [n for n in dir() if not n.startswith("_") and n not in ("SimpleNamespace",)]

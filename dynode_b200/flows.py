@@ -16,8 +16,10 @@ from typing import Callable, Dict, Optional, Tuple
 from . import _lib
 from ._lib import DynodeError
 
-_FLOWS = {"sir": _lib.FLOW_SIR, "seirs": _lib.FLOW_SEIRS, "seirs_c": _lib.FLOW_SEIRS_C}
-_COMPARTMENTS = {"sir": ("s", "i", "r"), "seirs": ("s", "e", "i", "r"), "seirs_c": ("s", "e", "i", "r", "c")}
+# "seip": the immune-history / waning family (CTA-per-trajectory kernel, include/dynode_b200_seip.h)
+_FLOWS = {"sir": _lib.FLOW_SIR, "seirs": _lib.FLOW_SEIRS, "seirs_c": _lib.FLOW_SEIRS_C, "seip": -1}
+_COMPARTMENTS = {"sir": ("s", "i", "r"), "seirs": ("s", "e", "i", "r"), "seirs_c": ("s", "e", "i", "r", "c"),
+                 "seip": ("s", "e", "i", "c")}
 
 
 class UnsupportedODEError(DynodeError):
@@ -54,7 +56,8 @@ class FlowSpec:
 def flow_family(flow: str, *, beta: str = "beta", gamma: str = "gamma", sigma: Optional[str] = None,
                 omega: Optional[str] = None, contact: Optional[str] = None,
                 contact_layout: str = "target_source", seasonal: Optional[Tuple[str, str, str]] = None,
-                density_dependent: bool = False) -> Callable:
+                density_dependent: bool = False, population: Optional[str] = None,
+                immunity: Optional[str] = None) -> Callable:
     """Register `ode(t, state, p)` as a member of the compiled flow family.
 
     flow: "sir" (s,i,r) | "seirs" (s,e,i,r) | "seirs_c" (s,e,i,r,c); the keyword arguments name the
@@ -76,6 +79,10 @@ def flow_family(flow: str, *, beta: str = "beta", gamma: str = "gamma", sigma: O
         fields["omega"] = omega
     if seasonal:
         fields["season_amp"], fields["season_phase"], fields["season_period"] = seasonal
+    if flow == "seip":
+        if not (contact and population and immunity):
+            raise ValueError("flow 'seip' needs contact=, population= and immunity= attribute names")
+        fields["population"], fields["immunity"] = population, immunity
     spec = FlowSpec(flow=flow, fields=fields, contact=contact, contact_layout=contact_layout,
                     seasonal=bool(seasonal), density_dependent=density_dependent)
 

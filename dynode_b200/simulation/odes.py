@@ -329,6 +329,9 @@ def simulate_ensemble(
 
 def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices, save_step,
          *, batch_size, state_batched, throw, out=None, host_chunk=2048) -> Solution:
+    if flow_spec_of(ode).flow == "seip":
+        return _run_seip(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,
+                         save_step, batch_size=batch_size, state_batched=state_batched, throw=throw)
     # unsupported ODEs / solver options fail loudly before anything touches the device
     spec, model, params, contact = _resolve(ode, initial_state, ode_parameters, batch_size, state_batched)
     opts = _solver_options(solver_parameters, duration_days)
@@ -382,6 +385,64 @@ def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, s
     ts = torch.as_tensor(saveat.times, dtype=torch.float64, device=out_dev)
     return Solution(t0=opts.t0, t1=opts.t1, ts=ts, ys=_split_ys(ys_view, model, mask, shapes, lead),
                     stats=stats_d, result=result)
+
+
+def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices, save_step, *,
+              batch_size, state_batched, throw) -> Solution:
+    """`simulate` / `simulate_ensemble` for the immune-history / waning family: one thread block per trajectory
+    (dynode_b200/seip.py).  Compartments (s, e, i, c) shaped (A, H, W), (A, H, K), (A, H, K), (A, H, K)."""
+    from .. import seip
+
+    spec = flow_spec_of(ode)
+    if len(initial_state) != 4:
+        raise UnsupportedODEError("flow 'seip' integrates compartments (s, e, i, c)")
+    shapes = [tuple(c.shape[1:] if state_batched else c.shape) for c in initial_state]
+    if len(shapes[0]) != 3 or len(shapes[1]) != 3 or shapes[1] != shapes[2] or shapes[1] != shapes[3] \
+            or shapes[0][:2] != shapes[1][:2] or shapes[0][1] != (1 << shapes[1][2]):
+        raise UnsupportedODEError("flow 'seip' needs s (ages, 2^strains, wane) and e, i, c (ages, 2^strains, strains)")
+    A, H, W = shapes[0]
+    K = shapes[1][2]
+    model = seip.SeipModel(A, K, W)
+    try:
+        model.check_supported()
+    except _lib.DynodeError as e:
+        raise UnsupportedODEError(str(e)) from None
+    opts = _solver_options(solver_parameters, duration_days)
+    if len(opts.jump_ts) > 0:
+        raise UnsupportedODEError("discontinuity_points are not implemented for the 'seip' kernel")
+    if sub_save_indices is not None:
+        raise UnsupportedODEError("sub_save_indices are not implemented for the 'seip' kernel")
+    _lib.require_cuda()
+    B = 1 if batch_size is None else batch_size
+    ensemble = batch_size is not None
+    if state_batched:
+        y0 = torch.cat([c.reshape(B, -1).to(torch.float64) for c in initial_state], dim=1)
+    else:
+        y0 = torch.cat([c.reshape(-1).to(torch.float64) for c in initial_state])
+    get = lambda k: torch.as_tensor(get_path(ode_parameters, spec.fields[k]), dtype=torch.float64)
+    params = {k: get(k) for k in ("beta", "sigma", "gamma", "omega")}
+    saveat = build_saveat(opts.t0, duration_days, save_step, None)
+    ys, stats = seip.solve_ensemble(model, y0, params, get_path(ode_parameters, spec.contact), get("population"),
+                                    get("immunity"), opts, saveat.times, B=B)
+    out_dev = initial_state[0].device
+    st = stats if out_dev.type == "cuda" else stats.cpu()
+    if throw and bool((stats[:, _lib.STAT_RESULT] != 0).any()):
+        raise RuntimeError(MAX_STEPS_MESSAGE)
+    if out_dev.type != "cuda":
+        ys = ys.cpu()
+    T = len(saveat.times)
+    lead = (B, T) if ensemble else (T,)
+    flat = ys if ensemble else ys[0]
+    outs, off = [], 0
+    for shp in shapes:
+        sz = int(np.prod(shp))
+        outs.append(flat[..., off:off + sz].reshape(*lead, *shp))
+        off += sz
+    pick = (lambda c: st[:, c]) if ensemble else (lambda c: st[0, c])
+    stats_d = {"num_steps": pick(_lib.STAT_STEPS), "num_accepted_steps": pick(_lib.STAT_ACCEPTED),
+               "num_rejected_steps": pick(_lib.STAT_REJECTED), "max_steps": int(solver_parameters.max_steps)}
+    return Solution(t0=opts.t0, t1=opts.t1, ts=torch.as_tensor(saveat.times, dtype=torch.float64, device=out_dev),
+                    ys=tuple(outs), stats=stats_d, result=pick(_lib.STAT_RESULT))
 
 
 def _host_pipeline(model, y0, params, contact, opts, save_ts, mask, B, T, ns, out, chunk, cuda):

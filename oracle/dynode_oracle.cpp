@@ -148,8 +148,15 @@ enum Family {
                              //   theta = [beta, gamma, sigma, omega, amp, phase, period]
   FAM_SIR_AGE = 4,           // examples/sir_age_stratified.py:127-142   theta=[beta,gamma], shared=C[A][A]
   FAM_SIR_AGE_RISK = 5,      // examples/sir_age_risk_stratified.py:157-173 shared=CM[A][R][A][R]
-  FAM_SEIRS_MULTISTRAIN = 6  // examples/seirs_multi_strain_age_stratified.py:213-243
+  FAM_SEIRS_MULTISTRAIN = 6, // examples/seirs_multi_strain_age_stratified.py:213-243
                              //   theta = [beta[S], gamma[S], sigma[S], omega[S]], shared = C[A][A]
+  FAM_SEIP = 7               // immune-history / waning family after reference ode_model.md:15-53,100-118,179-211
+                             //   (no reference implementation exists; the equations below are this repo's
+                             //   reading of the prose model, without the vaccination dimension):
+                             //   dims A ages, R = W waning stages, S = K strains, H = 2^K immune histories
+                             //   state  S[A][H][W], E[A][H][K], I[A][H][K], C[A][H][K]
+                             //   theta  [beta[K], sigma[K], gamma[K], omega[W]]  (omega[W-1] unused: last stage absorbs)
+                             //   shared [contact[A][A] (target, source), pop[A], immunity[H][W][K] in [0, 1]]
 };
 
 struct Dims { int A, R, S; };
@@ -163,6 +170,7 @@ inline int state_size(int fam, Dims d) {
     case FAM_SIR_AGE: return 3 * d.A;
     case FAM_SIR_AGE_RISK: return 3 * d.A * d.R;
     case FAM_SEIRS_MULTISTRAIN: return d.A + 4 * d.A * d.S;
+    case FAM_SEIP: return d.A * (1 << d.S) * (d.R + 3 * d.S);
   }
   return -1;
 }
@@ -172,6 +180,7 @@ inline int theta_size(int fam, Dims d) {
     case FAM_SEIRS_1BIN: return 4;
     case FAM_SEIRS_SEASONAL: return 7;
     case FAM_SEIRS_MULTISTRAIN: return 4 * d.S;
+    case FAM_SEIP: return 3 * d.S + d.R;
   }
   return -1;
 }
@@ -277,6 +286,58 @@ void rhs(int fam, Dims dm, double t, const T* y, const T* th, const double* sh, 
           dc[q] = fois[q] * s[a];
         }
       }
+    } break;
+    case FAM_SEIP: {
+      // force of infection per (age, strain) through the contact matrix; a susceptible cell (age a, immune
+      // history j, waning stage w) is exposed to strain k at rate foi[a][k] * (1 - immunity[j][w][k]);
+      // exposure keeps the history j while infected; recovery moves to history eta(j, k) = j | 2^k
+      // (ode_model.md:100-118), waning stage 0; waning is a chain w -> w+1 at rate omega[w].
+      const int A = dm.A, W = dm.R, K = dm.S, H = 1 << K;
+      const T* Sx = y; const T* E = y + A * H * W; const T* I = E + A * H * K;
+      const T* beta = th; const T* sigma = th + K; const T* gamma = th + 2 * K; const T* omega = th + 3 * K;
+      const double* contact = sh; const double* pop = sh + A * A; const double* imm = pop + A;
+      T itot[MAXG * MAXS], foi[MAXG * MAXS];
+      for (int a = 0; a < A; ++a)
+        for (int k = 0; k < K; ++k) {
+          T acc = I[(a * H + 0) * K + k];
+          for (int j = 1; j < H; ++j) acc = acc + I[(a * H + j) * K + k];
+          itot[a * K + k] = acc;
+        }
+      for (int a = 0; a < A; ++a)
+        for (int k = 0; k < K; ++k) {
+          T acc = contact[a * A + 0] * (itot[0 * K + k] / T(pop[0]));
+          for (int b = 1; b < A; ++b) acc = acc + contact[a * A + b] * (itot[b * K + k] / T(pop[b]));
+          foi[a * K + k] = beta[k] * acc;
+        }
+      T* dS = dy; T* dE = dy + A * H * W; T* dI = dE + A * H * K; T* dC = dI + A * H * K;
+      for (int a = 0; a < A; ++a)
+        for (int j = 0; j < H; ++j) {
+          T expo[MAXS];
+          for (int k = 0; k < K; ++k) expo[k] = T(0.0);
+          for (int w = 0; w < W; ++w) {
+            const T s = Sx[(a * H + j) * W + w];
+            T out = T(0.0);
+            for (int k = 0; k < K; ++k) {
+              T x = foi[a * K + k] * (1.0 - imm[(j * W + w) * K + k]) * s;
+              expo[k] = expo[k] + x;
+              out = out + x;
+            }
+            T d = -out;
+            if (w > 0) d = d + omega[w - 1] * Sx[(a * H + j) * W + w - 1];
+            if (w < W - 1) d = d - omega[w] * s;
+            if (w == 0)
+              for (int k = 0; k < K; ++k)
+                if ((j >> k) & 1)
+                  d = d + gamma[k] * (I[(a * H + j) * K + k] + I[(a * H + (j ^ (1 << k))) * K + k]);
+            dS[(a * H + j) * W + w] = d;
+          }
+          for (int k = 0; k < K; ++k) {
+            const int q = (a * H + j) * K + k;
+            dE[q] = expo[k] - sigma[k] * E[q];
+            dI[q] = sigma[k] * E[q] - gamma[k] * I[q];
+            dC[q] = expo[k];
+          }
+        }
     } break;
   }
 }
@@ -508,7 +569,7 @@ int oracle_solve(int fam, int A, int R, int S, int64_t B, const double* y0, int6
                  const int32_t* wrt, const double* dy0, double* ys, double* dys, int32_t* stats,
                  int nthreads, const double* jump_ts, int n_jump) {
   Dims dm{A, R, S};
-  if (state_size(fam, dm) < 0 || A * R > MAXG || S > MAXS) return 1;
+  if (state_size(fam, dm) < 0 || (fam != FAM_SEIP && A * R > MAXG) || A > MAXG || S > MAXS) return 1;
   SolveCfg c{t0, t1, rtol, atol, const_dt, max_steps, save_ts, T, save_idx, n_saved, jump_ts, n_jump};
 #define ORC_CASE(PP) case PP: return solve_batch<PP>(fam, dm, c, B, y0, y0_bs, theta, th_bs, shared, \
                                                     wrt, dy0, ys, dys, stats, nthreads);

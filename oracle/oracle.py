@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libdynode_oracle.so")
 
 # family ids (dynode_oracle.cpp enum Family)
-SIR_1BIN, SIR_DENSITY, SEIRS_1BIN, SEIRS_SEASONAL, SIR_AGE, SIR_AGE_RISK, SEIRS_MULTISTRAIN = range(7)
+SIR_1BIN, SIR_DENSITY, SEIRS_1BIN, SEIRS_SEASONAL, SIR_AGE, SIR_AGE_RISK, SEIRS_MULTISTRAIN, SEIP = range(8)
 
 _lib = None
 

@@ -106,3 +106,31 @@ ALL_CASES = ("sir_1bin", "sir_density", "seirs_1bin", "seirs_seasonal", "sir_age
 # further compiled members of the families (csrc/instances.def 9-17)
 EXTRA_CASES = ("sir_age3", "seirs_multi_g1s1", "seirs_multi_g1s2", "seirs_multi_g1s3", "seirs_multi_g2s2",
                "seirs_multi_g3s2", "seirs_multi_g4s2", "seirs_multi_g3s3", "seirs_multi_g4s3")
+
+
+def make_seip_case(B, A=3, K=2, W=3, seed=20260107, t1=200):
+    """Immune-history / waning family (oracle FAM_SEIP, include/dynode_b200_seip.h): per-draw rates, shared
+    contact / population / immunity tables, everyone susceptible-and-fully-waned except 1 % infectious."""
+    from dynode_b200.seip import SeipModel, immunity_table
+    rng = np.random.Generator(np.random.PCG64(seed))
+    H = 1 << K
+    r0 = rng.uniform(1.5, 3.0, (B, K))
+    inf = rng.uniform(4, 9, (B, K))
+    lat = rng.uniform(2, 4, (B, K))
+    wane = rng.uniform(20, 90, (B, W))
+    beta, sigma, gamma, omega = r0 / inf, 1 / lat, 1 / inf, 1 / wane
+    omega[:, -1] = 0.0
+    C = np.random.default_rng(200 + A).uniform(0.1, 1.0, (A, A))
+    C = C / np.max(np.real(np.linalg.eigvals(C)))
+    pop = 1000.0 * (np.arange(A, 0, -1.0) / np.arange(A, 0, -1.0).sum())
+    cross = np.full((K, K), 0.45) + 0.55 * np.eye(K)
+    imm = immunity_table(K, np.linspace(0.9, 0.2, W), cross)
+    S0 = np.zeros((A, H, W))
+    S0[:, 0, W - 1] = 0.99 * pop
+    I0 = np.zeros((A, H, K))
+    I0[:, 0, :] = 0.01 * pop[:, None] / K
+    y0 = np.concatenate([S0.ravel(), np.zeros(A * H * K), I0.ravel(), np.zeros(A * H * K)])
+    theta = np.hstack([beta, sigma, gamma, omega])
+    shared = np.concatenate([C.ravel(), pop, imm.ravel()])
+    return dict(model=SeipModel(A, K, W), params=dict(beta=beta, sigma=sigma, gamma=gamma, omega=omega), contact=C,
+                pop=pop, immunity=imm, y0=y0, oracle=(7, (A, W, K), theta, shared), t1=t1)

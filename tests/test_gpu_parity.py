@@ -238,3 +238,33 @@ def test_discrete_adjoint_equals_forward_sensitivities(name, obs_comp):
     lp_c, g_c, _, st_c = poisson_loglik_adjoint(model, y0, case["params"], case["contact"], SolverOptions(t1=t1),
                                                 ts, obs_comp, obs, 0.0, cap=3)
     assert bool((st_c[:, 0] == 2).all()) and bool(torch.isnan(lp_c).all()) and bool(torch.isnan(g_c).all())
+
+
+@pytest.mark.parametrize("A,K,W", [(3, 2, 3), (4, 3, 4), (1, 1, 2), (5, 2, 1), (2, 4, 3)])
+def test_seip_cta_per_trajectory_kernel_matches_oracle(A, K, W):
+    """CTA-per-trajectory kernel of the immune-history / waning family (include/dynode_b200_seip.h)."""
+    import torch
+    from dynode_b200 import seip
+    from dynode_b200.engine import SolverOptions
+    from tests.cases import make_seip_case
+    B = 37
+    case = make_seip_case(B, A=A, K=K, W=W, t1=150)
+    fam, dims, theta, shared = case["oracle"]
+    ts = np.linspace(0.0, 150.0, 151)
+    ys, st = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                 case["immunity"], SolverOptions(t1=150.0), ts)
+    torch.cuda.synchronize()
+    ref, _, rst = _run_oracle(case, 150)
+    assert np.array_equal(st.cpu().numpy(), rst)
+    _assert_close(ys.cpu().numpy(), ref)
+    assert np.array_equal(ys[:, 0, :].cpu().numpy(), np.broadcast_to(case["y0"], (B, ref.shape[2])))
+    # max_steps and a non-uniform grid
+    ts2 = np.array([0.0, 0.5, 7.25, 100.0, 150.0])
+    ys2, st2 = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                   case["immunity"], SolverOptions(t1=150.0, max_steps=9), ts2)
+    ref2, _, rst2 = _run_oracle(case, 150, save_ts=ts2, max_steps=9)
+    assert np.array_equal(st2.cpu().numpy(), rst2) and np.all(rst2[:, 0] == 1)
+    got2 = ys2.cpu().numpy()
+    assert np.array_equal(np.isinf(got2), np.isinf(ref2))
+    fin = np.isfinite(ref2)
+    _assert_close(got2[fin], ref2[fin])

@@ -185,3 +185,32 @@ def test_discontinuity_points_through_simulate():
                            jump_ts=[25.0, 60.0])
     assert np.allclose(torch.cat(sol.ys, dim=1).cpu().numpy(), ref[0], rtol=1e-9, atol=1e-9)
     assert int(sol.stats["num_accepted_steps"]) == st[0, 1]
+
+
+def test_seip_family_through_simulate():
+    """The immune-history / waning family behind the same drop-in `simulate` / `simulate_ensemble`."""
+    from oracle import oracle as orc
+    from tests.cases import make_seip_case
+    B = 5
+    case = make_seip_case(B, A=3, K=2, W=3)
+    A, W, K = 3, 3, 2
+    H = 4
+    nS, nX = A * H * W, A * H * K
+    y0 = t(case["y0"])
+    state = (y0[:nS].reshape(A, H, W), y0[nS:nS + nX].reshape(A, H, K), y0[nS + nX:nS + 2 * nX].reshape(A, H, K),
+             y0[nS + 2 * nX:].reshape(A, H, K))
+    prm = case["params"]
+    mk = lambda sl: ex.SEIP_ODEParams(beta=t(prm["beta"][sl]), sigma=t(prm["sigma"][sl]), gamma=t(prm["gamma"][sl]),
+                                      omega=t(prm["omega"][sl]), contact_matrix=t(case["contact"]),
+                                      population=t(case["pop"]), immunity=t(case["immunity"]))
+    sol = simulate(ex.seip_ode, 120, state, mk(0), SolverParams())
+    assert sol.ys[0].shape == (121, A, H, W) and sol.ys[3].shape == (121, A, H, K)
+    fam, dims, theta, shared = case["oracle"]
+    ref, _, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=120)
+    got = torch.cat([c.reshape(121, -1) for c in sol.ys], dim=1).cpu().numpy()
+    assert np.allclose(got, ref[0], rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert int(sol.stats["num_accepted_steps"]) == st[0, 1]
+    ens = simulate_ensemble(ex.seip_ode, 120, state, mk(slice(None)), SolverParams(), batch_size=B)
+    assert ens.ys[1].shape == (B, 121, A, H, K)
+    flat = torch.cat([c.reshape(B, 121, -1) for c in ens.ys], dim=2).cpu().numpy()
+    assert np.allclose(flat, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())

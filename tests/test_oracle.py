@@ -310,3 +310,44 @@ def test_oracle_matches_diffrax_golden():
             g = (w[None, :, :, None] * dys[:, :, 4:6, :]).sum((1, 2))
             assert np.allclose(g[:, 0], gold[f"{name}/grad_beta"][:, 0], rtol=1e-6)
             assert np.allclose(g[:, 1], gold[f"{name}/grad_gamma"][:, 0], rtol=1e-6)
+
+
+def test_seip_family_invariants_and_two_statements_of_the_rhs():
+    """Immune-history / waning family (after reference ode_model.md; no reference implementation exists): the
+    oracle's loop form equals the vectorised torch statement in dynode_b200/examples/rhs.py, people are
+    conserved, nothing goes negative, cumulative incidence only grows, histories only gain strains, and the
+    solve agrees with a tight DOP853 integration of the torch RHS."""
+    import torch
+    from scipy.integrate import solve_ivp
+    from dynode_b200.examples import rhs as ex
+    from tests.cases import make_seip_case
+    case = make_seip_case(2, A=3, K=2, W=3)
+    fam, dims, theta, shared = case["oracle"]
+    A, W, K = dims
+    H = 1 << K
+    nS, nX = A * H * W, A * H * K
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+
+    def torch_rhs(y, th):
+        state = (t(y[:nS]).reshape(A, H, W), t(y[nS:nS + nX]).reshape(A, H, K),
+                 t(y[nS + nX:nS + 2 * nX]).reshape(A, H, K), t(y[nS + 2 * nX:]).reshape(A, H, K))
+        p = ex.SEIP_ODEParams(beta=t(th[:K]), sigma=t(th[K:2 * K]), gamma=t(th[2 * K:3 * K]), omega=t(th[3 * K:]),
+                              contact_matrix=t(case["contact"]), population=t(case["pop"]), immunity=t(case["immunity"]))
+        return torch.cat([x.reshape(-1) for x in ex.seip_ode(0.0, state, p)]).numpy()
+
+    rng = np.random.default_rng(3)
+    yr = rng.uniform(0.1, 5.0, nS + 3 * nX)
+    assert np.allclose(orc.rhs(fam, dims, 0.0, yr, theta[0], shared), torch_rhs(yr, theta[0]), rtol=1e-13, atol=1e-13)
+    ys, _, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=200)
+    assert np.all(st[:, 0] == 0)
+    people = ys[:, :, :nS + 2 * nX].sum(2)
+    assert np.allclose(people, people[:, :1], rtol=0, atol=1e-8)
+    assert ys.min() > -1e-9
+    cum = ys[:, :, nS + 2 * nX:]
+    assert np.all(np.diff(cum, axis=1) > -1e-9)
+    S = ys[:, :, :nS].reshape(2, 201, A, H, W)
+    assert S[:, -1, :, 0].sum() < S[:, 0, :, 0].sum()  # the naive history empties
+    assert S[:, -1, :, H - 1].sum() > 0.0              # some people have seen every strain
+    truth = solve_ivp(lambda tt, y: torch_rhs(y, theta[0]), (0, 200), case["y0"], method="DOP853", rtol=1e-11,
+                      atol=1e-11, t_eval=np.arange(201.0)).y.T
+    assert np.max(np.abs(ys[0] - truth)) < 5e-3 * np.max(np.abs(truth))
