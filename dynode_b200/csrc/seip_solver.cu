@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "../../include/dynode_b200.h"
 #include "../../include/dynode_b200_seip.h"
 #include "tsit5.cuh"
@@ -60,15 +62,18 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// dx = f(x): all threads call it; x and dx are shared-memory arrays of n doubles
-__device__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, double* dx) {
-  const int A = a.A, K = a.K, W = a.W, H = a.H;
+// dx = f(x): all threads call it; x and dx are shared-memory arrays of n doubles.  KT / WT > 0 fix the number
+// of strains / waning stages at compile time (loops unrolled, index arithmetic folded); 0 = runtime value.
+template <int KT, int WT>
+__device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, double* dx) {
+  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H;
   const double* xS = x;
   const double* xE = x + A * H * W;
   const double* xI = xE + A * H * K;
   for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
     const int ag = q / K, k = q - ag * K;
     double acc = xI[(ag * H + 0) * K + k];
+#pragma unroll
     for (int j = 1; j < H; ++j) acc += xI[(ag * H + j) * K + k];
     sm.itot[q] = acc;
   }
@@ -88,11 +93,13 @@ __device__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, dou
       const int w = xw;
       const double s = xS[e];
       double out = 0.0;
+#pragma unroll
       for (int k = 0; k < K; ++k) out += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * s;
       d = -out;
       if (w > 0) d += sm.omega[w - 1] * xS[e - 1];
       if (w < W - 1) d -= sm.omega[w] * s;
       if (w == 0)
+#pragma unroll
         for (int k = 0; k < K; ++k)
           if ((j >> k) & 1)
             d += sm.gamma[k] * (xI[(ag * H + j) * K + k] + xI[(ag * H + (j ^ (1 << k))) * K + k]);
@@ -103,6 +110,7 @@ __device__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, dou
         d = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
       } else {
         double expo = 0.0;
+#pragma unroll
         for (int w = 0; w < W; ++w)
           expo += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * xS[(ag * H + j) * W + w];
         d = (comp == 1) ? expo - sm.sigma[k] * xE[q] : expo;
@@ -113,10 +121,11 @@ __device__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, dou
   __syncthreads();
 }
 
+template <int KT, int WT>
 __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArgs a) {
   using namespace tsit5;
   extern __shared__ double smem_raw[];
-  const int A = a.A, K = a.K, W = a.W, H = a.H, n = a.n;
+  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H, n = a.n;
   Smem sm;
   double* p = smem_raw;
   sm.y = p; p += n;
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   };
 
   // ---- FSAL f0 and the initial step (Hairer-Wanner, PIDController._select_initial_step)
-  seip_rhs(a, sm, sm.y, sm.f[0]);
+  seip_rhs<KT, WT>(a, sm, sm.y, sm.f[0]);
   double tprev = a.t0, tnext;
   if (a.const_dt > 0.0) {
     tnext = a.t0 + a.const_dt;
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
     for (int e = tid; e < n; e += blockDim.x) sm.ys[e] = sm.y[e] + h0 * sm.f[0][e];
     __syncthreads();
-    seip_rhs(a, sm, sm.ys, sm.f[1]);
+    seip_rhs<KT, WT>(a, sm, sm.ys, sm.f[1]);
     double p2 = 0.0;
     for (int e = tid; e < n; e += blockDim.x) {
       const double sc = atol + fabs(sm.y[e]) * rtol;
@@ -201,26 +210,30 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   }
   tnext = fmin(tnext, t1);
 
-  // tableau rows a_{s+1, 1..s} inside kTab (tsit5.cuh TabIdx order)
-  const int row_base[6] = {I_a21, I_a31, I_a41, I_a51, I_a61, I_a71};
-  const int c_idx[4] = {I_c2, I_c3, I_c4, I_c5};
   int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
   double* const out = a.ys + traj * (int64_t)a.T * n;
 
   while (tprev < t1 && n_steps < a.max_steps) {
     const double h = tnext - tprev;
-    // ---- Tsit5 stages 2..7
-    for (int s = 1; s <= 6; ++s) {
-      const int base = row_base[s - 1];
+    // ---- Tsit5 stages 2..7 (stage index at compile time: the tableau row and the f_j pointers are static)
+    auto stage = [&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      constexpr int base = s == 1 ? I_a21 : s == 2 ? I_a31 : s == 3 ? I_a41 : s == 4 ? I_a51 : s == 5 ? I_a61 : I_a71;
       for (int e = tid; e < n; e += blockDim.x) {
         double acc = kTab[base] * sm.f[0][e];
+#pragma unroll
         for (int j = 1; j < s; ++j) acc = fma(kTab[base + j], sm.f[j][e], acc);
         sm.ys[e] = fma(h, acc, sm.y[e]);
       }
       __syncthreads();
-      seip_rhs(a, sm, sm.ys, sm.f[s]);  // autonomous right-hand side: stage times c_idx[] are not needed
-    }
-    (void)c_idx;
+      seip_rhs<KT, WT>(a, sm, sm.ys, sm.f[s]);  // autonomous right-hand side: no stage times needed
+    };
+    stage(std::integral_constant<int, 1>{});
+    stage(std::integral_constant<int, 2>{});
+    stage(std::integral_constant<int, 3>{});
+    stage(std::integral_constant<int, 4>{});
+    stage(std::integral_constant<int, 5>{});
+    stage(std::integral_constant<int, 6>{});
     // ---- embedded error, scaled RMS norm, I-controller
     bool keep;
     double dt_next;
@@ -340,11 +353,18 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   a.max_steps = (int)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.ys = ys; a.stats = stats;
   const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, n);
+  // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
+  void (*kern)(const SeipArgs) = seip_solver_kernel<0, 0>;
+#define SEIP_CASE(KK, WW) if (a.K == KK && a.W == WW) kern = seip_solver_kernel<KK, WW>;
+  SEIP_CASE(1, 1) SEIP_CASE(1, 2) SEIP_CASE(1, 3) SEIP_CASE(1, 4)
+  SEIP_CASE(2, 1) SEIP_CASE(2, 2) SEIP_CASE(2, 3) SEIP_CASE(2, 4)
+  SEIP_CASE(3, 1) SEIP_CASE(3, 2) SEIP_CASE(3, 3) SEIP_CASE(3, 4)
+  SEIP_CASE(4, 1) SEIP_CASE(4, 2) SEIP_CASE(4, 3) SEIP_CASE(4, 4)
+#undef SEIP_CASE
   cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024)
-    e = cudaFuncSetAttribute(seip_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail_msg("shared memory request of %zu bytes refused: %s", smem, cudaGetErrorString(e));
-  seip_solver_kernel<<<(unsigned)B, kSeipThreads, smem, (cudaStream_t)stream>>>(a);
+  kern<<<(unsigned)B, kSeipThreads, smem, (cudaStream_t)stream>>>(a);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("kernel launch failed: %s", cudaGetErrorString(e));
 }
