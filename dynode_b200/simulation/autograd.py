@@ -221,6 +221,9 @@ def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions,
         return force == "1" and n_dir > 0
     if n_dir == 0 or len(opts.jump_ts) > 0:
         return False
+    # the adjoint checkpoints every accepted step: [B][cap][n + 2] doubles of scratch
+    if B * adjoint_capacity() * (model.state_size + 2) * 8 > ADJOINT_SCRATCH_LIMIT:
+        return False
     chunk = 2 if model.flow == _lib.FLOW_SIR else 1
     groups = -(-n_dir // chunk)
     slots = max(1, 32 // (model.n_groups * model.n_strains))
@@ -232,6 +235,7 @@ def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions,
 
 ADJOINT_COST = 3.2      # primal-solve equivalents of one adjoint evaluation (forward + reverse sweep)
 RESIDENT_WARPS = 1184   # 148 SMs x 8 warps of the 255-register tangent / adjoint kernels
+ADJOINT_SCRATCH_LIMIT = 16 << 30  # bytes of checkpoint scratch beyond which forward mode is used instead
 
 
 def adjoint_capacity() -> int:
