@@ -38,15 +38,9 @@ struct SeipArgs {
   int32_t* stats;
 };
 
-// element -> (compartment, age, history, w or k), packed: comp in bits 30-31, a in 20-29, j in 10-19, x in 0-9
-__device__ __forceinline__ unsigned pack_meta(int comp, int a, int j, int x) {
-  return ((unsigned)comp << 30) | ((unsigned)a << 20) | ((unsigned)j << 10) | (unsigned)x;
-}
-
 struct Smem {
   double *y, *ys, *f[7];
   double *itot, *foi, *beta, *sigma, *gamma, *omega, *contact, *pop, *imm, *red;
-  unsigned* meta;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -85,38 +79,50 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
     sm.foi[q] = sm.beta[k] * acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < a.n; e += blockDim.x) {
-    const unsigned m = sm.meta[e];
-    const int comp = m >> 30, ag = (m >> 20) & 1023, j = (m >> 10) & 1023, xw = m & 1023;
-    double d;
-    if (comp == 0) {  // S[ag][j][w]
-      const int w = xw;
-      const double s = xS[e];
+  // one thread per (age, history) cell group: the W x K exposure terms are formed once and feed dS (summed over
+  // strains), dE and dC (summed over waning stages) -- the loop body of oracle FAM_SEIP, same summation order
+  constexpr int KMAX = KT ? KT : DYNODE_SEIP_MAX_STRAINS;
+  double* dS = dx;
+  double* dE = dx + A * H * W;
+  double* dI = dE + A * H * K;
+  double* dC = dI + A * H * K;
+  for (int cell = threadIdx.x; cell < A * H; cell += blockDim.x) {
+    const int ag = cell / H, j = cell - ag * H;
+    double expo[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) expo[k] = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const double s = xS[cell * W + w];
       double out = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) out += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * s;
-      d = -out;
-      if (w > 0) d += sm.omega[w - 1] * xS[e - 1];
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const double xk = sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * s;
+          expo[k] += xk;
+          out += xk;
+        }
+      }
+      double d = -out;
+      if (w > 0) d += sm.omega[w - 1] * xS[cell * W + w - 1];
       if (w < W - 1) d -= sm.omega[w] * s;
-      if (w == 0)
+      if (w == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if ((j >> k) & 1)
-            d += sm.gamma[k] * (xI[(ag * H + j) * K + k] + xI[(ag * H + (j ^ (1 << k))) * K + k]);
-    } else {  // E / I / C [ag][j][k]
-      const int k = xw;
-      const int q = (ag * H + j) * K + k;
-      if (comp == 2) {
-        d = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
-      } else {
-        double expo = 0.0;
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K && ((j >> k) & 1))
+            d += sm.gamma[k] * (xI[cell * K + k] + xI[(ag * H + (j ^ (1 << k))) * K + k]);
+      }
+      dS[cell * W + w] = d;
+    }
 #pragma unroll
-        for (int w = 0; w < W; ++w)
-          expo += sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * xS[(ag * H + j) * W + w];
-        d = (comp == 1) ? expo - sm.sigma[k] * xE[q] : expo;
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const int q = cell * K + k;
+        dE[q] = expo[k] - sm.sigma[k] * xE[q];
+        dI[q] = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
+        dC[q] = expo[k];
       }
     }
-    dx[e] = d;
   }
   __syncthreads();
 }
@@ -141,7 +147,6 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   sm.pop = p; p += A;
   sm.imm = p; p += H * W * K;
   sm.red = p; p += 8;
-  sm.meta = (unsigned*)p;
 
   const int64_t traj = blockIdx.x;
   const int tid = threadIdx.x;
@@ -155,18 +160,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   for (int q = tid; q < A * A; q += blockDim.x) sm.contact[q] = a.contact[q];
   for (int q = tid; q < A; q += blockDim.x) sm.pop[q] = a.pop[q];
   for (int q = tid; q < H * W * K; q += blockDim.x) sm.imm[q] = a.imm[q];
-  const int nS = A * H * W, nX = A * H * K;
-  for (int e = tid; e < n; e += blockDim.x) {
-    sm.y[e] = a.y0.ptr[traj * a.y0.batch_stride + e];
-    if (e < nS) {
-      const int ag = e / (H * W), r = e - ag * H * W;
-      sm.meta[e] = pack_meta(0, ag, r / W, r % W);
-    } else {
-      const int comp = 1 + (e - nS) / nX, r0 = (e - nS) % nX;
-      const int ag = r0 / (H * K), r = r0 - ag * H * K;
-      sm.meta[e] = pack_meta(comp, ag, r / K, r % K);
-    }
-  }
+  for (int e = tid; e < n; e += blockDim.x) sm.y[e] = a.y0.ptr[traj * a.y0.batch_stride + e];
   __syncthreads();
 
   const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
@@ -305,7 +299,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 
 size_t seip_smem_bytes(int A, int K, int W, int H, int n) {
   const size_t doubles = (size_t)9 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * W * K + 8;
-  return doubles * sizeof(double) + (size_t)n * sizeof(unsigned);
+  return doubles * sizeof(double);
 }
 
 }  // namespace

@@ -278,4 +278,29 @@ def poisson_loglik_adjoint(model: FlowModel, y0, params: Dict[str, object], cont
         int(obs_comp), obs_t.data_ptr(), float(lp_const), lp.data_ptr(), grad.data_ptr(),
         g0.data_ptr() if g0 is not None else None, stats.data_ptr(), ckpt.data_ptr(), int(cap), vsave.data_ptr(),
         ctypes.c_void_p(_lib.current_stream_ptr())))
+    _overflow_counter(torch, b.dev).add_((stats[:, _lib.STAT_RESULT] == _lib.RESULT_ADJOINT_CAPACITY).sum())
     return lp, grad, g0, stats
+
+
+_OVERFLOW: Dict[int, object] = {}
+
+
+def _overflow_counter(torch, dev):
+    """Device counter of trajectories whose accepted steps did not fit the adjoint's checkpoint scratch since
+    the last `adjoint_overflows(reset=True)`; updated with stream-ordered tensor ops (graph-capturable), so a
+    sampler can check ONCE at the end instead of synchronising on every evaluation."""
+    t = _OVERFLOW.get(dev.index)
+    if t is None:
+        t = torch.zeros((), dtype=torch.int64, device=dev)
+        _OVERFLOW[dev.index] = t
+    return t
+
+
+def adjoint_overflows(reset: bool = False) -> int:
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = _overflow_counter(torch, dev)
+    n = int(t.item())
+    if reset:
+        t.zero_()
+    return n

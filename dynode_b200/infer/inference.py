@@ -83,7 +83,17 @@ class MCMC:
                       f"mean accept={float(e.stats['accept_prob'].mean()):.2f}  "
                       f"mean leapfrogs={float(e.stats['num_steps'].mean()):.1f}  graph={e.graph_used}")
 
+        if md.device.type == "cuda":
+            from .. import engine as _engine
+            _engine.adjoint_overflows(reset=True)
         z, extra, last = eng.run(z0, self.num_warmup, self.num_samples, progress)
+        if md.device.type == "cuda":
+            lost = _engine.adjoint_overflows(reset=True)
+            if lost:
+                raise RuntimeError(
+                    f"{lost} log-density evaluations accepted more Tsit5 steps than the discrete adjoint's "
+                    "checkpoint scratch holds and returned NaN; raise DYNODE_B200_ADJOINT_CAP (default 512) or "
+                    "set DYNODE_B200_ADJOINT=0 to use forward sensitivities")
         self._samples_z, self._extra, self.last_state = z, extra, last
         C, N, D = z.shape
         flat = md.constrain(z.reshape(C * N, D), with_deterministic=True)
