@@ -69,13 +69,13 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
     double acc = xI[(ag * H + 0) * K + k];
 #pragma unroll
     for (int j = 1; j < H; ++j) acc += xI[(ag * H + j) * K + k];
-    sm.itot[q] = acc;
+    sm.itot[q] = acc / sm.pop[ag];  // infectious fraction of age group ag for strain k (divided once, not per target)
   }
   __syncthreads();
   for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
     const int ag = q / K, k = q - ag * K;
-    double acc = sm.contact[ag * A + 0] * (sm.itot[0 * K + k] / sm.pop[0]);
-    for (int b = 1; b < A; ++b) acc += sm.contact[ag * A + b] * (sm.itot[b * K + k] / sm.pop[b]);
+    double acc = sm.contact[ag * A + 0] * sm.itot[0 * K + k];
+    for (int b = 1; b < A; ++b) acc += sm.contact[ag * A + b] * sm.itot[b * K + k];
     sm.foi[q] = sm.beta[k] * acc;
   }
   __syncthreads();
