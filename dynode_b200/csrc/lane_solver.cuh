@@ -52,9 +52,15 @@ struct LaneSolver {
   // tight); otherwise a warp integrates one generation of TPW trajectories.
   static constexpr bool JUMPS = MODE == MODE_SAVE_JUMPS;
   static constexpr bool IS_SAVE = MODE != MODE_LOGLIK;
-  static constexpr bool PERSIST = TPW >= 8;
+#ifndef DYN_PERSIST_MIN_TPW
+#define DYN_PERSIST_MIN_TPW 8
+#endif
+#ifndef DYN_REFILL_SMALL
+#define DYN_REFILL_SMALL 1
+#endif
+  static constexpr bool PERSIST = TPW >= DYN_PERSIST_MIN_TPW;
   // refill as soon as this many slots are idle (masked re-initialisation costs ~1.5 steps)
-  static constexpr int REFILL = TPW >= 8 ? TPW / 8 : 1;
+  static constexpr int REFILL = TPW >= 8 ? TPW / 8 : DYN_REFILL_SMALL;
   static_assert(L >= 1 && L <= 32, "a trajectory must fit one warp");
   using D = Dual<P>;
   // Shared-memory offload: the dense-output coefficients Q (3*NE doubles, written once per step, read only
