@@ -44,8 +44,7 @@ class ModelDesc(ctypes.Structure):
 class SolverDesc(ctypes.Structure):
     _fields_ = [("t0", ctypes.c_double), ("t1", ctypes.c_double), ("rtol", ctypes.c_double),
                 ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64),
-                ("save_dt", ctypes.c_double), ("jump_ts", ctypes.c_void_p), ("n_jump", ctypes.c_int32),
-                ("order", ctypes.c_void_p)]
+                ("save_dt", ctypes.c_double), ("jump_ts", ctypes.c_void_p), ("n_jump", ctypes.c_int32)]
 
 
 class Array(ctypes.Structure):

@@ -108,7 +108,6 @@ static void fill_common(SolveArgs& a, const DynodeSolverDesc* sv, int64_t B, Dyn
   a.save_dt = sv->save_dt > 0.0 ? sv->save_dt : 0.0;
   a.jump_ts = sv->n_jump > 0 ? sv->jump_ts : nullptr;
   a.n_jump = sv->n_jump > 0 ? sv->n_jump : 0;
-  a.order = sv->order;
   a.max_steps = (int32_t)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.write_primal = 1;
   a.n_pass = 1;

@@ -343,10 +343,8 @@ struct LaneSolver {
           const int64_t cand = next + rank;
           const bool take = slot_ok && !active && cand < chunk_end;
           next = (next + n_idle < chunk_end) ? next + n_idle : chunk_end;
-          const int64_t cand_slot = (a.n_pass == 1) ? cand : cand / a.n_pass;
-          const int cand_p0 = (a.n_pass == 1) ? 0 : (int)(cand - cand_slot * a.n_pass) * P;
-          // scheduling order (similar step counts share a warp); the trajectory keeps its own output rows
-          const int64_t cand_tr = (a.order && take) ? (int64_t)__ldg(a.order + cand_slot) : cand_slot;
+          const int64_t cand_tr = (a.n_pass == 1) ? cand : cand / a.n_pass;
+          const int cand_p0 = (a.n_pass == 1) ? 0 : (int)(cand - cand_tr * a.n_pass) * P;
           const int64_t tr = take ? cand_tr : traj;
           const int p0n = take ? cand_p0 : p0s;
           // ---- parameters and initial state of the new trajectory (masked lanes shadow their old one)

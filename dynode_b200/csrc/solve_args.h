@@ -47,7 +47,6 @@ struct SolveArgs {
   // discontinuity points (SolverParams.discontinuity_points -> jump_ts), sorted ascending, device memory
   const double* jump_ts;
   int32_t n_jump;
-  const int32_t* order;  // optional permutation: work slot i integrates trajectory order[i]
   // sensitivities: P_total directions ride the primal's steps in n_pass groups of P (the kernel's template
   // chunk).  All groups run in ONE launch: work item v = trajectory * n_pass + group integrates trajectory
   // v / n_pass carrying directions group*P .. group*P+P-1; group 0 also writes the primal outputs.

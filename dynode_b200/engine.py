@@ -67,7 +67,7 @@ class SolverOptions:
 
     def desc(self, save_dt: float = 0.0) -> _lib.SolverDesc:
         d = _lib.SolverDesc(float(self.t0), float(self.t1), float(self.rtol), float(self.atol),
-                            float(self.const_dt), int(self.max_steps), float(save_dt), None, 0, None)
+                            float(self.const_dt), int(self.max_steps), float(save_dt), None, 0)
         if len(self.jump_ts) > 0:
             dev_t = _jump_tensor(tuple(sorted(float(x) for x in self.jump_ts)))
             d.jump_ts, d.n_jump = dev_t.data_ptr(), int(dev_t.numel())
@@ -173,35 +173,9 @@ class _Bound:
         self.c_y0 = _as_array(self.y0, n, self.B, "y0")
 
 
-SORT_MIN_BATCH = 4096
-
-
-def schedule_order(b: "_Bound"):
-    """int32 permutation that puts draws of similar cost next to each other, or None.
-
-    The trajectories sharing a warp advance in lock-step until the slowest is done, and the number of Tsit5
-    steps a draw needs grows with its transfer rates (correlation 0.77-0.90 with sum(sigma + gamma) on the
-    BASELINE ensembles: profiles/r1/kernel_variants.md), so sorting by that proxy cuts the lock-step loss
-    (C4: 110 -> 106 steps per warp against a mean of 99.7).  Pure scheduling: results do not change."""
-    if b.B < SORT_MIN_BATCH:
-        return None
-    torch = b.torch
-    cost = None
-    for k in ("sigma", "gamma", "beta"):
-        t = b.p.get(k)
-        if t is not None and t.numel() >= b.B and t.numel() % b.B == 0:
-            c = t.reshape(b.B, -1).sum(1)
-            cost = c if cost is None else cost + c
-        if cost is not None and k == "gamma":
-            break
-    if cost is None:
-        return None
-    return torch.argsort(cost).to(torch.int32)
-
-
 def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions,
                    save_ts, save_mask: Optional[int] = None, wrt: Sequence[int] = (), dy0=None,
-                   out=None, stats_out=None, B: Optional[int] = None, sort_by_cost: bool = True):
+                   out=None, stats_out=None, B: Optional[int] = None):
     """One launch for the whole ensemble.  Returns (ys[B,T,n_saved], dys or None, stats[B,4]).
 
     Everything stays on the current CUDA device and stream; nothing synchronises.
@@ -221,9 +195,6 @@ def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opt
     stream = ctypes.c_void_p(_lib.current_stream_ptr())
     P = len(wrt)
     if P == 0:
-        order = schedule_order(b) if sort_by_cost else None
-        if order is not None:
-            sd.order = order.data_ptr()
         _lib.check(L.dynode_solve_f64(ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0,
                                       ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T, mask,
                                       ys.data_ptr(), stats.data_ptr(), stream))

@@ -67,11 +67,6 @@ typedef struct {
    * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none. */
   const double* jump_ts;
   int32_t n_jump;
-  /* Optional scheduling hint: a permutation of 0..B-1 in DEVICE memory; work slot i integrates trajectory
-   * order[i] (outputs stay at the trajectory's own index).  Adaptive step counts differ per draw and the
-   * trajectories that share a warp wait for the slowest, so callers sort by a stiffness proxy (the sum of the
-   * transfer rates).  Results do not depend on it.  NULL = natural order. */
-  const int32_t* order;
 } DynodeSolverDesc;
 
 /* An ensemble array: element (b, k) lives at ptr[b*batch_stride + k]; batch_stride == 0 shares

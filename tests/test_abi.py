@@ -70,7 +70,7 @@ def test_unsupported_model_fails_loudly_without_touching_the_gpu(lib):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SEIRS_C, 0, 5, 7)
     assert lib.dynode_is_supported(ctypes.byref(d)) == 0
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0, None)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)
@@ -94,7 +94,7 @@ def test_unsupported_model_fails_loudly_without_touching_the_gpu(lib):
 def test_argument_validation_messages(lib, mutate, needle):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SIR, 0, 1, 1)
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0, None)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)
@@ -109,7 +109,7 @@ def test_argument_validation_messages(lib, mutate, needle):
 def test_empty_ensemble_is_a_no_op(lib):
     from dynode_b200 import _lib
     d = _lib.ModelDesc(_lib.FLOW_SIR, 0, 1, 1)
-    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0, None)
+    sv = _lib.SolverDesc(0.0, 10.0, 1e-5, 1e-6, 0.0, 100, 0.0, None, 0)
     buf = (ctypes.c_double * 8)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     arr = _lib.Array(ptr.value, 0)
