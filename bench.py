@@ -103,23 +103,33 @@ def make_inputs(workload: str, B: int, seed: int):
     return make_case(WORKLOADS[workload][0], B, seed=seed)
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the
+    CPU arm: the thread count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_leg(workload: str, min_seconds: float, chunk: int, seed: int):
     """Time the CPU oracle (all host threads) on chunk-sized pieces of the workload until
     `min_seconds` of CPU wall time have been spent (the bounded sample of the cpu_baseline leg)."""
     from oracle import oracle as orc
     case = make_inputs(workload, chunk, seed)
     fam, dims, theta, shared = case["oracle"]
+    nthr = host_threads()
     orc.solve(fam, dims, case["y0"][:256] if np.ndim(case["y0"]) == 2 else case["y0"], theta[:256], shared,
-              t1=case["t1"])  # warm-up (thread pool, page faults)
+              t1=case["t1"], nthreads=nthr)  # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
     sample_chunks = 0
     while True:
-        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"], nthreads=nthr)
         sample_chunks += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds:
             break
-    return sample_chunks * chunk / dt, orc.num_threads(), dt, sample_chunks
+    return sample_chunks * chunk / dt, nthr, dt, sample_chunks
 
 
 def run_reference(args):
@@ -132,14 +142,14 @@ def run_reference(args):
     from oracle import oracle as orc
     case = make_inputs(args.workload, chunk, 20260101)
     fam, dims, theta, shared = case["oracle"]
+    cores = host_threads()
     for _ in range(max(1, min(args.warmup, 2))):
-        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"], nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"])
+        orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"], nthreads=cores)
     dt = time.perf_counter() - t0
     v = args.steps * chunk / dt
-    cores = orc.num_threads()
     sample = f"{chunk} draws of the same workload per step, {args.steps} steps, OpenMP over {cores} threads"
     line = {
         "impl": "reference", "metric": "solved trajectories/s", "value": v, "unit": "trajectories/s",
