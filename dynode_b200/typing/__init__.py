@@ -1,10 +1,12 @@
-"""Type aliases mirroring reference src/dynode/typing/typing.py:11-39 (torch replaces jax.Array)."""
+"""Types of the DynODE-compatible host API (reference src/dynode/typing/__init__.py)."""
 
 from .typing import (  # noqa: F401
+    Array,
     CompartmentGradients,
     CompartmentState,
+    CompartmentTimeseries,
     DynodeName,
-    ODE_Eqns,
     ObservedData,
+    ODE_Eqns,
     UnitIntervalFloat,
 )
