@@ -8,6 +8,8 @@ class SamplePlaceholderError(Exception):
 
 
 class PlaceholderSample(Distribution):
+    raises_on_sample = True
+
     def __init__(self):
         pass
 
@@ -15,7 +17,7 @@ class PlaceholderSample(Distribution):
         import torch
         return (torch.zeros((), dtype=torch.float64),)
 
-    def sample(self, _=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
         raise SamplePlaceholderError(
             "Attempted to sample a PosteriorSample parameter outside of a Predictive() context. This likely "
             "means you did not provide posterior samples to the context via Predictive() or substitute().")

@@ -247,7 +247,13 @@ class Distribution:
     def _normal(self, generator, sample_shape):
         return torch.randn(self.shape(sample_shape), dtype=_F64, device=self._device(), generator=generator)
 
-    def sample(self, generator: Optional[torch.Generator] = None, sample_shape=()):
+    def _generator(self, key):
+        """numpyro passes a PRNGKey as `key`; here it may also be a torch.Generator or None (global RNG)."""
+        if key is None or isinstance(key, torch.Generator):
+            return key
+        return key.generator(self._device())
+
+    def sample(self, key=None, sample_shape=()):
         raise NotImplementedError
 
     def log_prob(self, value):
@@ -272,7 +278,8 @@ class Normal(Distribution):
     def _params(self):
         return (self.loc, self.scale)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return self.loc + self.scale * self._normal(generator, sample_shape)
 
     def log_prob(self, value):
@@ -289,7 +296,8 @@ class LogNormal(Distribution):
     def _params(self):
         return (self.loc, self.scale)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return torch.exp(self.loc + self.scale * self._normal(generator, sample_shape))
 
     def log_prob(self, value):
@@ -307,7 +315,8 @@ class HalfNormal(Distribution):
     def _params(self):
         return (self.scale,)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return torch.abs(self.scale * self._normal(generator, sample_shape))
 
     def log_prob(self, value):
@@ -324,7 +333,8 @@ class Exponential(Distribution):
     def _params(self):
         return (self.rate,)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return -torch.log1p(-self._uniform(generator, sample_shape)) / self.rate
 
     def log_prob(self, value):
@@ -339,7 +349,8 @@ class Uniform(Distribution):
     def _params(self):
         return (self.low, self.high)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return self.low + (self.high - self.low) * self._uniform(generator, sample_shape)
 
     def log_prob(self, value):
@@ -357,7 +368,8 @@ class Gamma(Distribution):
     def _params(self):
         return (self.concentration, self.rate)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         a = self.concentration.expand(self.shape(sample_shape)).contiguous()
         g = torch._standard_gamma(a, generator=generator) if generator is not None else torch._standard_gamma(a)
         return g / self.rate
@@ -376,7 +388,8 @@ class Beta(Distribution):
     def _params(self):
         return (self.concentration1, self.concentration0)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         shp = self.shape(sample_shape)
         kw = {} if generator is None else {"generator": generator}
         ga = torch._standard_gamma(self.concentration1.expand(shp).contiguous(), **kw)
@@ -406,13 +419,18 @@ class TruncatedNormal(Distribution):
     def _params(self):
         return (self.loc, self.scale)
 
+    @property
+    def base_dist(self):
+        return Normal(self.loc, self.scale)
+
     def _cdf_bounds(self):
         zero, one = torch.zeros_like(self.loc), torch.ones_like(self.loc)
         a = zero if self.low is None else _std_normal_cdf((self.low - self.loc) / self.scale)
         b = one if self.high is None else _std_normal_cdf((self.high - self.loc) / self.scale)
         return a, b
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         a, b = self._cdf_bounds()
         u = self._uniform(generator, sample_shape)
         p = (a + u * (b - a)).clamp(1e-300, 1.0 - 1e-16)
@@ -439,7 +457,8 @@ class Poisson(Distribution):
     def _params(self):
         return (self.rate,)
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         r = self.rate.expand(self.shape(sample_shape))
         return torch.poisson(r, generator=generator) if generator is not None else torch.poisson(r)
 
@@ -462,7 +481,8 @@ class TransformedDistribution(Distribution):
     def _params(self):
         return self.base_dist._params()
 
-    def sample(self, generator=None, sample_shape=()):
+    def sample(self, key=None, sample_shape=()):
+        generator = self._generator(key)
         return self.transform(self.base_dist.sample(generator, sample_shape))
 
     def log_prob(self, value):

@@ -156,6 +156,8 @@ def _apply_stack(msg: Dict[str, Any]) -> Dict[str, Any]:
     if msg["type"] == "sample" and msg["value"] is None:
         key = msg["rng_key"]
         fn = msg["fn"]
+        if getattr(fn, "raises_on_sample", False):
+            fn.sample(None, msg["sample_shape"])  # PlaceholderSample: its own error, whatever the context
         if key is None and not _STACK:
             raise ValueError(
                 f"site `{msg['name']}`: sampling outside an inference context needs rng_key=PRNGKey(...)")
