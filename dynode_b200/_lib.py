@@ -44,7 +44,8 @@ class ModelDesc(ctypes.Structure):
 class SolverDesc(ctypes.Structure):
     _fields_ = [("t0", ctypes.c_double), ("t1", ctypes.c_double), ("rtol", ctypes.c_double),
                 ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64),
-                ("save_dt", ctypes.c_double), ("jump_ts", ctypes.c_void_p), ("n_jump", ctypes.c_int32)]
+                ("save_dt", ctypes.c_double), ("jump_ts", ctypes.c_void_p), ("n_jump", ctypes.c_int32),
+                ("only", ctypes.c_void_p)]
 
 
 class Array(ctypes.Structure):
@@ -66,8 +67,9 @@ class SeipParams(ctypes.Structure):
                 ("contact", ctypes.c_void_p), ("pop", ctypes.c_void_p), ("immunity", ctypes.c_void_p)]
 
 
+NUTS_ADAPT, NUTS_WELFORD, NUTS_SAMPLING, NUTS_END_SLOW, NUTS_END_WARMUP = 1, 2, 4, 8, 16  # DYNODE_NUTS_*
 _NUTS_PTRS = (
-    "z U g eps imm msqrt k nwin active need_tree f_adapt f_middle f_sampling energy0 "
+    "z U g eps imm msqrt k nwin active need_tree sched sched_n energy0 "
     "zL rL gL zR rR gR zP gP r_sum UP weight sum_acc depth nprop turning diverging "
     "s_n s_right s_turn s_div s_z s_r s_g s_zP s_gP s_rsum s_UP s_w s_acc r_ck rs_ck z_new r_half "
     "da_x da_xavg da_gavg da_t da_prox wf_n wf_mean wf_m2 out_z out_accept out_steps out_div out_energy "
@@ -78,6 +80,7 @@ class NutsState(ctypes.Structure):
     """DynodeNutsState of include/dynode_b200_nuts.h (field order is the header's)."""
 
     _fields_ = ([("C", ctypes.c_int32), ("D", ctypes.c_int32), ("max_depth", ctypes.c_int32), ("N", ctypes.c_int32),
+                 ("n_warmup", ctypes.c_int32), ("dense", ctypes.c_int32),
                  ("target_accept", ctypes.c_double)] + [(n, ctypes.c_void_p) for n in _NUTS_PTRS])
 
 

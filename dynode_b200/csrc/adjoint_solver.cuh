@@ -137,7 +137,7 @@ struct AdjointSolver {
     }
     const bool lead = c.s == 0;
     const int64_t traj = warp_global * TPW + tw;
-    const bool have = tw < TPW && traj < a.B;
+    const bool have = tw < TPW && traj < a.B && (a.only == nullptr || __ldg(a.only + traj) != 0);  // row mask
     if (!__any_sync(0xffffffffu, have)) return;
     const int64_t tr = have ? traj : 0;  // idle lanes shadow trajectory 0 (nothing of theirs is stored)
 

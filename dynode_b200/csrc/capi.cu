@@ -111,6 +111,7 @@ static void fill_common(SolveArgs& a, const DynodeSolverDesc* sv, int64_t B, Dyn
   a.max_steps = (int32_t)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.write_primal = 1;
   a.n_pass = 1;
+  a.only = sv->only;
   for (int k = 0; k < kMaxWrt; ++k) a.wrt[k] = -1;
 }
 

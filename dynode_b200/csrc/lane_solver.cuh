@@ -339,10 +339,19 @@ struct LaneSolver {
         const int n_idle = __popc(idle_heads);
         const bool any_active = __any_sync(0xffffffffu, active);
         if (next < chunk_end && n_idle > 0 && (n_idle >= REFILL || !any_active)) {
+          // candidates: the next 32 work items of the chunk minus the rows the caller masked out (a.only);
+          // the idle slot of rank r takes the (r+1)-th candidate
+          const int64_t ci = next + lane;
+          bool cok = ci < chunk_end;
+          if (a.only != nullptr && cok) cok = __ldg(a.only + ((a.n_pass == 1) ? ci : ci / a.n_pass)) != 0;
+          const unsigned cmask = __ballot_sync(0xffffffffu, cok);
           const int rank = __popc(idle_heads & ((1u << c.base) - 1u));  // idle slots below mine
-          const int64_t cand = next + rank;
-          const bool take = slot_ok && !active && cand < chunk_end;
-          next = (next + n_idle < chunk_end) ? next + n_idle : chunk_end;
+          const unsigned pos = __fns(cmask, 0u, rank + 1);              // 0xffffffff: no candidate left for me
+          const bool take = slot_ok && !active && pos < 32u;
+          const int64_t cand = next + (take ? (int64_t)pos : 0);
+          // consumed: everything up to the last candidate handed out, or all 32 scanned items
+          const unsigned used = (__popc(cmask) >= n_idle) ? __fns(cmask, 0u, n_idle) + 1u : 32u;
+          next = (next + used < chunk_end) ? next + used : chunk_end;
           const int64_t cand_tr = (a.n_pass == 1) ? cand : cand / a.n_pass;
           const int cand_p0 = (a.n_pass == 1) ? 0 : (int)(cand - cand_tr * a.n_pass) * P;
           const int64_t tr = take ? cand_tr : traj;
@@ -501,7 +510,10 @@ struct LaneSolver {
       if constexpr (PERSIST) refill();
       // a new trajectory whose horizon is empty (t0 == t1) or max_steps == 0 finishes in the commit
       // block below after one masked pass; nothing to do when no slot is active
-      if (!__any_sync(0xffffffffu, active)) break;
+      if (!__any_sync(0xffffffffu, active)) {
+        if (PERSIST && next < chunk_end) continue;  // every candidate of this pass was masked out: scan on
+        break;
+      }
       const bool stepping = active && (tprev < t1) && (n_steps < a.max_steps);
 
       const double h = tnext - tprev;

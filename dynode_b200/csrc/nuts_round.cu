@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   copy(s.g + o, s.gP + o, D);
   s.last_accept[c] = accept;
   s.last_steps[c] = (double)nprop;
-  if (*s.f_adapt) {  // dual averaging of the log step size (t0 = 10, kappa = 0.75, gamma = 0.05)
+  const int64_t k = s.k[c];
+  const int64_t nwin = *s.nwin;
+  const unsigned fl = s.sched[k < nwin ? k : nwin - 1];
+  if (fl & DYNODE_NUTS_ADAPT) {  // dual averaging of the log step size (t0 = 10, kappa = 0.75, gamma = 0.05)
     const double tt = s.da_t[c] + 1.0;
     const double gavg = (1.0 - 1.0 / (tt + 10.0)) * s.da_gavg[c] + (s.target_accept - accept) / (tt + 10.0);
     const double x = s.da_prox[c] - sqrt(tt) / 0.05 * gavg;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
     s.da_x[c] = x;
     s.eps[c] = exp(fmin(fmax(x, -700.0), 700.0));
   }
-  if (*s.f_middle) {  // Welford covariance of the positions
+  if (fl & DYNODE_NUTS_WELFORD) {  // Welford covariance of the positions
     const double n1 = s.wf_n[c] + 1.0;
     double* mean = s.wf_mean + o;
     double* m2 = s.wf_m2 + o * D;
@@ -248,9 +251,57 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
       for (int j = 0; j < D; ++j) m2[i * D + j] += d1.v[i] * (z.v[j] - mean[j]);
     s.wf_n[c] = n1;
   }
-  const int64_t k = s.k[c];
-  if (*s.f_sampling) {
-    const int64_t kk = k < s.N ? k : s.N - 1;
+  if (fl & DYNODE_NUTS_END_SLOW) {
+    // End of a slow window (Stan / numpyro warmup_adapter): the chain's own window-end update, so that no
+    // chain waits for another one.
+    if (fl & DYNODE_NUTS_WELFORD) {
+      const double n = s.sched_n[k < nwin ? k : nwin - 1];
+      double* m2 = s.wf_m2 + o * D;
+      if (n > 1.0) {
+        // inverse mass matrix <- (n/(n+5)) cov + 1e-3 (5/(n+5)) I ; msqrt <- L^-T with imm = L L^T
+        double* A = s.imm + o * D;
+        double* Ms = s.msqrt + o * D;
+        const double a = n / (n + 5.0), bshr = 1e-3 * (5.0 / (n + 5.0));
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            double v = a * (m2[i * D + j] / (n - 1.0));
+            if (i == j) v += bshr;
+            else if (!s.dense) v = 0.0;
+            A[i * D + j] = v;
+          }
+        // Cholesky A = L L^T with L held in the Welford buffer (reset below), L^-1 by forward substitution
+        // written transposed straight into msqrt: no per-thread scratch
+        double* Lm = m2;
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j <= i; ++j) {
+            double acc = A[i * D + j];
+            for (int q = 0; q < j; ++q) acc -= Lm[i * D + q] * Lm[j * D + q];
+            Lm[i * D + j] = (i == j) ? sqrt(acc) : acc / Lm[j * D + j];
+          }
+        for (int j = 0; j < D; ++j)  // column j of L^-1 = row j of msqrt
+          for (int i = 0; i < D; ++i) {
+            if (i < j) { Ms[j * D + i] = 0.0; continue; }
+            double acc = (i == j) ? 1.0 : 0.0;
+            for (int q = j; q < i; ++q) acc -= Lm[i * D + q] * Ms[j * D + q];
+            Ms[j * D + i] = acc / Lm[i * D + i];
+          }
+      }
+      s.wf_n[c] = 0.0;
+      for (int i = 0; i < D; ++i) s.wf_mean[o + i] = 0.0;
+      for (int i = 0; i < D * D; ++i) m2[i] = 0.0;
+    }
+    if (fl & DYNODE_NUTS_ADAPT) {  // restart dual averaging around 10 x the averaged step size
+      const double e = exp(fmin(fmax(s.da_xavg[c], -700.0), 700.0));
+      s.eps[c] = e;
+      s.da_prox[c] = log(10.0 * e);
+      s.da_x[c] = 0.0; s.da_xavg[c] = 0.0; s.da_gavg[c] = 0.0; s.da_t[c] = 0.0;
+    }
+  }
+  if ((fl & DYNODE_NUTS_END_WARMUP) && (fl & DYNODE_NUTS_ADAPT))  // final step size = averaged iterate
+    s.eps[c] = exp(fmin(fmax(s.da_xavg[c], -700.0), 700.0));
+  if (fl & DYNODE_NUTS_SAMPLING) {
+    int64_t kk = k - s.n_warmup;
+    kk = kk < 0 ? 0 : (kk < s.N ? kk : s.N - 1);
     store(s.out_z + ((int64_t)c * s.N + kk) * D, z, D);
     const int64_t q = (int64_t)c * s.N + kk;
     s.out_accept[q] = accept;
@@ -261,7 +312,7 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   }
   s.k[c] = k + 1;
   s.need_tree[c] = 1;
-  if (k + 1 >= *s.nwin) s.active[c] = 0;
+  if (k + 1 >= nwin) s.active[c] = 0;
 }
 
 int check(const DynodeNutsState* st) {

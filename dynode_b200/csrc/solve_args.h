@@ -60,6 +60,7 @@ struct SolveArgs {
   double lp_const;
   double* lp;    // [B]
   double* grad;  // [B][P_total]
+  const uint8_t* only;  // [B] or NULL: row mask (DynodeSolverDesc.only)
 };
 
 // Discrete-adjoint log-likelihood kernel (adjoint_solver.cuh)

@@ -77,6 +77,38 @@ class SolverOptions:
 
 _JUMP_CACHE: Dict[tuple, object] = {}
 
+# ---- row mask (DynodeSolverDesc.only) -----------------------------------------------------------------
+_ONLY = [None]
+
+
+class only_rows:
+    """Context: ensemble launches made inside it integrate only the rows b with mask[b] != 0 (uint8/bool CUDA
+    tensor of the ensemble size; launches of another size ignore it).  Rows left out cost nothing and come
+    back as zeros.  The many-chain NUTS wraps the model evaluation of a round in it with its "chain still
+    running" flags; inside a CUDA-graph capture the mask's address is what gets recorded, so the flags may
+    change between replays."""
+
+    def __init__(self, mask):
+        self.mask, self.prev = mask, None
+
+    def __enter__(self):
+        self.prev, _ONLY[0] = _ONLY[0], self.mask
+        return self
+
+    def __exit__(self, *exc):
+        _ONLY[0] = self.prev
+        return False
+
+
+def _row_mask(sd, B: int):
+    """Point sd.only at the active context mask when it matches this launch; tells the caller to zero-fill."""
+    m = _ONLY[0]
+    if m is None or not m.is_cuda or m.numel() != B or m.element_size() != 1 or not m.is_contiguous():
+        return False
+    sd.only = m.data_ptr()
+    return True
+
+
 
 def _jump_tensor(ts: tuple):
     torch = _lib.require_cuda()
@@ -194,12 +226,15 @@ def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opt
     md, sd = model.desc(), opts.desc(b.save_dt)
     stream = ctypes.c_void_p(_lib.current_stream_ptr())
     P = len(wrt)
+    masked = _row_mask(sd, b.B)
+    if masked:
+        ys.zero_(); stats.zero_()
     if P == 0:
         _lib.check(L.dynode_solve_f64(ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0,
                                       ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T, mask,
                                       ys.data_ptr(), stats.data_ptr(), stream))
         return ys, None, stats
-    dys = torch.empty((b.B, b.T, ns, P), dtype=torch.float64, device=b.dev)
+    dys = (torch.zeros if masked else torch.empty)((b.B, b.T, ns, P), dtype=torch.float64, device=b.dev)
     d0 = None
     if dy0 is not None:
         d0 = _dev_f64(torch, dy0, b.dev)
@@ -230,6 +265,8 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
     if dy0 is not None:
         d0 = _dev_f64(torch, dy0, b.dev)
     md, sd = model.desc(), opts.desc(b.save_dt)
+    if _row_mask(sd, b.B):
+        lp.zero_(); grad.zero_(); stats.zero_()
     _lib.check(_lib.load().dynode_poisson_loglik_grad_f64(
         ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(),
         b.T, int(obs_comp), obs_t.data_ptr(), float(lp_const), P, _lib.i32_array(list(wrt)),
@@ -273,6 +310,10 @@ def poisson_loglik_adjoint(model: FlowModel, y0, params: Dict[str, object], cont
     ckpt = _scratch(torch, b.dev, "ckpt", b.B * cap * (n + 2))
     vsave = _scratch(torch, b.dev, "vsave", b.B * b.T * m)
     md, sd = model.desc(), opts.desc(b.save_dt)
+    if _row_mask(sd, b.B):
+        lp.zero_(); grad.zero_(); stats.zero_()
+        if g0 is not None:
+            g0.zero_()
     _lib.check(_lib.load().dynode_poisson_loglik_adjoint_f64(
         ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T,
         int(obs_comp), obs_t.data_ptr(), float(lp_const), lp.data_ptr(), grad.data_ptr(),

@@ -12,11 +12,14 @@ re-organises it for the GPU:
     ensemble launch of the ODE kernel, plus masked tensor updates of the per-chain tree state;
   * chains are NOT held in lock-step per transition: a chain whose tree is complete commits its
     transition (sample, step-size and covariance updates) and starts its next tree in the very next
-    round.  Chains only wait for each other at the adaptation-window boundaries, so the number of rounds
-    is set by the mean tree size, not by the largest tree among the chains at every transition;
+    round, and -- the adaptation state being per chain, as in numpyro -- walks the whole warm-up + sampling
+    schedule at its own pace, doing its own window-end updates (shrunk Welford covariance -> inverse mass
+    matrix and its Cholesky factor, dual-averaging restart).  No chain ever waits for another one, so the
+    number of rounds is the largest per-chain TOTAL of leapfrogs, not a sum of per-window (or per-transition)
+    maxima: measured 2-4x fewer rounds than with window barriers (profiles/r1/nuts_async.md);
   * all state lives in persistent device buffers updated in place, so on CUDA the whole round -- model
     evaluation included -- is captured once into a CUDA graph and replayed (one graph launch per round,
-    one host sync every `sync_every` rounds to see whether the window is finished).
+    one host sync every `sync_every` rounds to see whether every chain is finished).
 """
 
 from __future__ import annotations
@@ -52,6 +55,31 @@ def build_adaptation_schedule(num_steps: int):
         window *= 2
     sched.append((end_win_start, num_steps - 1))
     return sched
+
+
+# per-transition schedule flags (DYNODE_NUTS_* of include/dynode_b200_nuts.h)
+ADAPT, WELFORD, SAMPLING, END_SLOW, END_WARMUP = 1, 2, 4, 8, 16
+
+
+def build_transition_schedule(num_warmup: int, num_samples: int, adapt_ss: bool, adapt_mm: bool):
+    """(flags uint8 [n], window length float64 [n]) for a chain's n = num_warmup + num_samples transitions:
+    what happens after each of them (see the flag definitions)."""
+    flags, wlen = [], []
+    windows = build_adaptation_schedule(num_warmup) if num_warmup > 0 else []
+    for w, (a, e) in enumerate(windows):
+        middle = 0 < w < len(windows) - 1
+        fl = (ADAPT if adapt_ss else 0) | (WELFORD if (middle and adapt_mm) else 0)
+        for t in range(a, e + 1):
+            f = fl
+            if t == e and middle:
+                f |= END_SLOW
+            if t == e and w == len(windows) - 1:
+                f |= END_WARMUP
+            flags.append(f)
+            wlen.append(float(e - a + 1))
+    flags += [SAMPLING] * num_samples
+    wlen += [float(max(1, num_samples))] * num_samples
+    return flags, wlen
 
 
 def _tree_index_tables(max_depth: int, device):
@@ -129,6 +157,19 @@ class BatchedNUTS:
         return ((v_l * rc).sum(-1) <= 0) | ((v_r * rc).sum(-1) <= 0)
 
     # ------------------------------------------------------------------ buffers
+    def set_schedule(self, flags, wlen, num_warmup: int):
+        """Install a per-transition schedule (flags / window lengths, see build_transition_schedule); all
+        chains restart at transition 0."""
+        b = self.b
+        n = max(1, len(flags))
+        b.sched = torch.tensor(list(flags) or [0], dtype=torch.uint8, device=b.dev)
+        b.sched_n = torch.tensor(list(wlen) or [1.0], dtype=b.dtype, device=b.dev)
+        b.n_warm = int(num_warmup)
+        b.nwin.fill_(len(flags))
+        b.k.zero_()
+        b.active.fill_(len(flags) > 0)
+        b.any_active.fill_(len(flags) > 0)
+
     def _allocate(self, z0: torch.Tensor, num_samples: int):
         C, D = z0.shape
         dev, dt, md = z0.device, z0.dtype, self.max_depth
@@ -155,7 +196,9 @@ class BatchedNUTS:
         b.da_x, b.da_xavg, b.da_gavg, b.da_t = f(C), f(C), f(C), f(C)
         b.da_prox = torch.log(10.0 * b.eps)
         b.wf_n, b.wf_mean, b.wf_m2 = f(C), f(C, D), f(C, D, D)
-        b.f_adapt, b.f_middle, b.f_sampling = bl(()), bl(()), bl(())
+        b.sched = torch.zeros(1, dtype=torch.uint8, device=dev)
+        b.sched_n = f(1) + 1.0
+        b.n_warm = 0
         N = max(1, num_samples)
         b.out_z = f(C, N, D)
         b.out_stats = {k: f(C, N) for k in ("accept_prob", "num_steps", "diverging", "potential_energy", "tree_depth")}
@@ -277,8 +320,10 @@ class BatchedNUTS:
         _put(b.g, fin, b.gP)
         _put(b.last_accept, fin, accept)
         _put(b.last_steps, fin, b.nprop.to(b.dtype))
+        kidx = b.k.clamp(max=b.sched.numel() - 1)
+        fl = b.sched[kidx].to(torch.int32)
         # dual averaging of log step size (warmup windows)
-        ad = fin & b.f_adapt
+        ad = fin & ((fl & ADAPT) != 0)
         tt = b.da_t + 1.0
         gavg = (1.0 - 1.0 / (tt + 10.0)) * b.da_gavg + (self.target - accept) / (tt + 10.0)
         x = b.da_prox - torch.sqrt(tt) / 0.05 * gavg
@@ -290,7 +335,7 @@ class BatchedNUTS:
         _put(b.da_xavg, ad, xavg)
         _put(b.eps, ad, torch.exp(x.clamp(-700.0, 700.0)))
         # Welford covariance of the positions (slow windows)
-        wf = fin & b.f_middle
+        wf = fin & ((fl & WELFORD) != 0)
         n1 = b.wf_n + 1.0
         d1 = b.z - b.wf_mean
         mean1 = b.wf_mean + d1 / n1[:, None]
@@ -298,9 +343,37 @@ class BatchedNUTS:
         _put(b.wf_m2, wf, b.wf_m2 + d1[:, :, None] * d2[:, None, :])
         _put(b.wf_mean, wf, mean1)
         _put(b.wf_n, wf, n1)
-        # store the draw (sampling window)
-        st = fin & b.f_sampling
-        kk = b.k.clamp(max=b.out_z.shape[1] - 1)
+        # end of a slow window: the chain's own mass-matrix update and dual-averaging restart
+        es = fin & ((fl & END_SLOW) != 0)
+        # (on CUDA this masked-tensor round -- the cross-check, not the product -- stays free of host syncs so
+        # that it can still be graph-captured: the update is then computed every round and masked)
+        if b.dev.type == "cuda" or bool(es.any()):
+            nn = b.sched_n[kidx]
+            mm = es & ((fl & WELFORD) != 0)
+            upd = mm & (nn > 1.0)
+            eye = torch.eye(D, dtype=b.dtype, device=b.dev)
+            cov = b.wf_m2 / (nn - 1.0).clamp(min=1.0)[:, None, None]
+            cov = (nn / (nn + 5.0))[:, None, None] * cov + (1e-3 * (5.0 / (nn + 5.0)))[:, None, None] * eye
+            if not self.dense:
+                cov = torch.diag_embed(torch.diagonal(cov, dim1=1, dim2=2))
+            _put(b.imm, upd, cov)
+            Lc = torch.linalg.cholesky_ex(b.imm, check_errors=False).L
+            msq = torch.linalg.solve_triangular(Lc.transpose(1, 2), eye.expand(C, D, D), upper=True)  # L^-T
+            _put(b.msqrt, upd, msq)
+            _put(b.wf_n, mm, 0.0)
+            _put(b.wf_mean, mm, 0.0)
+            _put(b.wf_m2, mm, 0.0)
+            ads = es & ((fl & ADAPT) != 0)
+            e_new = torch.exp(b.da_xavg.clamp(-700.0, 700.0))
+            _put(b.eps, ads, e_new)
+            _put(b.da_prox, ads, torch.log(10.0 * e_new))
+            for t_ in (b.da_x, b.da_xavg, b.da_gavg, b.da_t):
+                _put(t_, ads, 0.0)
+        ew = fin & ((fl & END_WARMUP) != 0) & ((fl & ADAPT) != 0)
+        _put(b.eps, ew, torch.exp(b.da_xavg.clamp(-700.0, 700.0)))
+        # store the draw (sampling phase)
+        st = fin & ((fl & SAMPLING) != 0)
+        kk = (b.k - b.n_warm).clamp(min=0, max=b.out_z.shape[1] - 1)
         cur = b.out_z[b.ar, kk]
         b.out_z[b.ar, kk] = torch.where(st[:, None], b.z, cur)
         for name, val in (("accept_prob", accept), ("num_steps", b.nprop.to(b.dtype)),
@@ -321,6 +394,7 @@ class BatchedNUTS:
         b = self.b
         st = _lib.NutsState()
         st.C, st.D, st.max_depth, st.N = b.C, b.D, self.max_depth, b.out_z.shape[1]
+        st.n_warmup, st.dense = int(b.n_warm), int(bool(self.dense))
         st.target_accept = self.target
         alias = {"out_accept": b.out_stats["accept_prob"], "out_steps": b.out_stats["num_steps"],
                  "out_div": b.out_stats["diverging"], "out_energy": b.out_stats["potential_energy"],
@@ -338,7 +412,10 @@ class BatchedNUTS:
         rnd_n, rnd_u = self._randn(b.C, b.D), self._rand(b.C, 3)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self._lib.check(L.dynode_nuts_round_pre(ctypes.byref(self._st), rnd_n.data_ptr(), rnd_u.data_ptr(), stream))
-        U_new, g_new = self.pg(b.z_new)
+        # finished chains cost nothing in the model's ensemble launches (engine.only_rows -> DynodeSolverDesc.only)
+        from .. import engine as _engine
+        with _engine.only_rows(b.active.view(torch.uint8)):
+            U_new, g_new = self.pg(b.z_new)
         U_new, g_new = U_new.contiguous(), g_new.contiguous()
         self._lib.check(L.dynode_nuts_round_post(ctypes.byref(self._st), U_new.data_ptr(), g_new.data_ptr(),
                                                  rnd_u.data_ptr(), stream))
@@ -388,27 +465,22 @@ class BatchedNUTS:
                           f"running rounds eagerly\n{where}")
 
     # ------------------------------------------------------------------ driver
-    def _refresh_mass_sqrt(self):
+    def _run_schedule(self, progress: Optional[Callable] = None):
+        """Rounds until every chain has walked the whole schedule (one host sync every `sync_every` rounds)."""
         b = self.b
-        L = torch.linalg.cholesky_ex(b.imm, check_errors=False).L
-        eye = torch.eye(b.D, dtype=b.dtype, device=b.dev).expand(b.C, b.D, b.D)
-        b.msqrt.copy_(torch.linalg.solve_triangular(L.transpose(1, 2), eye, upper=True))  # L^-T
-
-    def _run_window(self, length: int, adapt: bool, middle: bool, sampling: bool):
-        b = self.b
-        b.k.zero_()
-        b.nwin.fill_(length)
-        b.active.fill_(True)
-        b.f_adapt.fill_(adapt)
-        b.f_middle.fill_(middle)
-        b.f_sampling.fill_(sampling)
-        b.any_active.fill_(True)
+        step = max(1, int(b.nwin) // 10)
+        next_mark = step
         while True:
             for _ in range(self.sync_every):
                 self._round_fn()
                 self.rounds += 1
             if not bool(b.any_active):
                 break
+            if progress is not None:
+                kmin = int(b.k.min())  # the slowest chain's position in the schedule
+                if kmin >= next_mark:
+                    progress(kmin - 1, self)
+                    next_mark = (kmin // step + 1) * step
 
     def run(self, z0: torch.Tensor, num_warmup: int, num_samples: int, progress: Optional[Callable] = None):
         """Returns (samples z [C, num_samples, D], per-sample stats dict, final state namespace)."""
@@ -422,36 +494,11 @@ class BatchedNUTS:
         b.U.copy_(U)
         b.g.copy_(g)
         b.need_tree.fill_(True)
+        flags, wlen = build_transition_schedule(num_warmup, num_samples, self.adapt_ss, self.adapt_mm)
+        self.set_schedule(flags, wlen, num_warmup)
         self._prepare_round_fn()
-        schedule = build_adaptation_schedule(num_warmup) if num_warmup > 0 else []
-        done = 0
-        for w, (a, e) in enumerate(schedule):
-            middle = 0 < w < len(schedule) - 1
-            self._run_window(e - a + 1, adapt=self.adapt_ss, middle=middle and self.adapt_mm, sampling=False)
-            if middle:
-                if self.adapt_mm:
-                    n = float(e - a + 1)
-                    if n > 1:
-                        cov = b.wf_m2 / (n - 1.0)
-                        eye = torch.eye(b.D, dtype=b.dtype, device=b.dev)
-                        cov = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * eye
-                        if not self.dense:
-                            cov = torch.diag_embed(torch.diagonal(cov, dim1=1, dim2=2))
-                        b.imm.copy_(cov)
-                        self._refresh_mass_sqrt()
-                    b.wf_n.zero_(); b.wf_mean.zero_(); b.wf_m2.zero_()
-                if self.adapt_ss:
-                    b.eps.copy_(torch.exp(b.da_xavg.clamp(-700.0, 700.0)))
-                    b.da_prox.copy_(torch.log(10.0 * b.eps))
-                    for t in (b.da_x, b.da_xavg, b.da_gavg, b.da_t):
-                        t.zero_()
-            done = e + 1
-            if progress is not None:
-                progress(done - 1, self)
-        if schedule and self.adapt_ss:
-            b.eps.copy_(torch.exp(b.da_xavg.clamp(-700.0, 700.0)))  # final step size = averaged iterate
-        if num_samples > 0:
-            self._run_window(num_samples, adapt=False, middle=False, sampling=True)
+        if len(flags) > 0:
+            self._run_schedule(progress)
             if progress is not None:
                 progress(num_warmup + num_samples - 1, self)
         self.grad_evals = int(b.n_useful) + int(b.n_leap.sum())

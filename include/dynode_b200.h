@@ -67,6 +67,11 @@ typedef struct {
    * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none. */
   const double* jump_ts;
   int32_t n_jump;
+  /* Optional row mask: DEVICE [B] bytes.  When non-NULL, only trajectories with only[b] != 0 are integrated;
+   * nothing is computed or written for the others (their rows of every output keep what the caller put
+   * there).  A many-chain sampler passes its "chain is still running" flags, so finished chains cost nothing
+   * (dynode_b200/infer/nuts.py).  NULL = all B trajectories. */
+  const uint8_t* only;
 } DynodeSolverDesc;
 
 /* An ensemble array: element (b, k) lives at ptr[b*batch_stride + k]; batch_stride == 0 shares

@@ -9,7 +9,8 @@
  *     dynode_nuts_round_post  (second half of the leapfrog, multinomial sampling inside the subtree,
  *                              checkpointed U-turn tests, tree doubling, and -- when a chain's tree is
  *                              complete -- the transition commit: dual-averaging step size, Welford
- *                              covariance, storage of the draw)
+ *                              covariance, window-end mass-matrix update (per-thread Cholesky), storage of
+ *                              the draw)
  *
  * Both launches are stream-ordered, allocate nothing and keep no state outside the buffers the caller owns,
  * so a whole round (model included) can be captured in a CUDA graph.  All pointers are DEVICE pointers.
@@ -27,18 +28,31 @@ extern "C" {
 #define DYNODE_NUTS_MAX_DIM 16
 #define DYNODE_NUTS_MAX_DEPTH 12
 
+/* Per-transition schedule flags (st->sched[t] for the chain's t-th transition, warm-up first).  The adaptation
+ * state is per chain (numpyro semantics), so chains never wait for each other: every chain walks the schedule
+ * at its own pace and does its own window-end updates inside dynode_nuts_round_post. */
+#define DYNODE_NUTS_ADAPT 1u      /* dual averaging of the log step size after this transition */
+#define DYNODE_NUTS_WELFORD 2u    /* the position enters the Welford covariance (slow windows) */
+#define DYNODE_NUTS_SAMPLING 4u   /* the draw is stored at out_*[t - n_warmup] */
+#define DYNODE_NUTS_END_SLOW 8u   /* last transition of a slow window: inverse mass matrix <- shrunk covariance
+                                     (if WELFORD), dual averaging restarted around the averaged step size (if ADAPT) */
+#define DYNODE_NUTS_END_WARMUP 16u /* last warm-up transition: step size <- averaged iterate (if ADAPT) */
+
 typedef struct {
   int32_t C, D, max_depth, N; /* chains, dimension, numpyro max_tree_depth, draws kept per chain */
+  int32_t n_warmup;           /* transitions before the first stored draw */
+  int32_t dense;              /* 1: dense inverse mass matrix, 0: diagonal */
   double target_accept;       /* dual averaging target (0.8) */
   /* chain state */
   double *z, *U, *g;    /* [C][D], [C], [C][D]: position, potential energy, its gradient */
   double *eps;          /* [C] step size */
   double *imm, *msqrt;  /* [C][D][D] inverse mass matrix; factor with momentum = msqrt @ N(0, I) */
-  /* window bookkeeping (chains run asynchronously inside an adaptation window) */
-  int64_t *k;           /* [C] transitions completed in the current window */
-  const int64_t *nwin;  /* [1] transitions each chain has to make in this window */
+  /* schedule bookkeeping (chains run asynchronously through the whole warm-up + sampling schedule) */
+  int64_t *k;           /* [C] transitions completed */
+  const int64_t *nwin;  /* [1] transitions each chain has to make in total */
   uint8_t *active, *need_tree; /* [C] */
-  const uint8_t *f_adapt, *f_middle, *f_sampling; /* [1] flags of the current window */
+  const uint8_t *sched;   /* [*nwin] DYNODE_NUTS_* flags per transition */
+  const double *sched_n;  /* [*nwin] length of the adaptation window the transition belongs to */
   /* whole tree */
   double *energy0;                  /* [C] */
   double *zL, *rL, *gL, *zR, *rR, *gR, *zP, *gP, *r_sum; /* [C][D] */

@@ -18,9 +18,9 @@ for kernels in (False, True):
     e._allocate(torch.zeros(C, 3, dtype=torch.float64, device=dev), 30)
     e._g = e.gen
     U, g = e._eval(e.b.z); e.b.U.copy_(U); e.b.g.copy_(g); e.b.need_tree.fill_(True)
+    e.set_schedule([3] * 40, [40.0] * 40, 40)
     e._prepare_round_fn()
     b = e.b
-    b.k.zero_(); b.nwin.fill_(40); b.active.fill_(True); b.f_adapt.fill_(True); b.f_middle.fill_(True); b.f_sampling.fill_(False)
     engs.append(e)
 fields = ["z","U","g","eps","k","active","need_tree","energy0","zL","rL","gL","zR","rR","gR","zP","gP","r_sum","UP","weight","sum_acc","depth","nprop","turning","diverging","s_n","s_right","s_turn","s_div","s_z","s_r","s_g","s_zP","s_gP","s_rsum","s_UP","s_w","s_acc","da_x","da_xavg","da_gavg","da_t","wf_n","wf_mean","wf_m2"]
 bad_chains = set()

@@ -181,6 +181,7 @@ def test_cuda_nuts_round_equals_the_torch_round():
     lock-step from the same state with the same random numbers: every state field agrees round by round
     (compared over 120 rounds -- beyond a few hundred, rounding differences between cuBLAS bmm and the
     per-thread dot products are amplified by warm-up trajectories that run near the stability limit)."""
+    from dynode_b200.infer import nuts as N
     from dynode_b200.infer.nuts import BatchedNUTS
     dev = _dev()
     cov = torch.tensor([[1.0, 0.6, 0.0], [0.6, 2.0, -0.4], [0.0, -0.4, 0.5]], dtype=torch.float64, device=dev)
@@ -203,18 +204,18 @@ def test_cuda_nuts_round_equals_the_torch_round():
         e.b.U.copy_(U)
         e.b.g.copy_(g)
         e.b.need_tree.fill_(True)
+        # 12 transitions per chain, every kind of bookkeeping on each of them, a slow-window end (mass-matrix
+        # update by the chain's own thread + dual-averaging restart) after the 6th and the warm-up end after the 12th
+        fl = [N.ADAPT | N.WELFORD | N.SAMPLING] * 12
+        fl[5] |= N.END_SLOW
+        fl[11] |= N.END_WARMUP
+        e.set_schedule(fl, [6.0] * 12, 0)
         e._prepare_round_fn()
-        b = e.b
-        b.nwin.fill_(12)
-        b.active.fill_(True)
-        b.f_adapt.fill_(True)
-        b.f_middle.fill_(True)
-        b.f_sampling.fill_(True)
         engs.append(e)
     fields = ["z", "U", "g", "eps", "k", "active", "need_tree", "energy0", "zL", "rL", "gL", "zR", "rR", "gR", "zP",
               "gP", "r_sum", "UP", "weight", "sum_acc", "depth", "nprop", "turning", "diverging", "s_n", "s_right",
               "s_turn", "s_div", "s_z", "s_r", "s_g", "s_zP", "s_gP", "s_rsum", "s_UP", "s_w", "s_acc", "da_x",
-              "da_xavg", "da_gavg", "da_t", "wf_n", "wf_mean", "wf_m2", "out_z"]
+              "da_xavg", "da_gavg", "da_t", "da_prox", "wf_n", "wf_mean", "wf_m2", "imm", "msqrt", "out_z"]
     for rnd in range(120):
         for e in engs:
             e._round_fn()

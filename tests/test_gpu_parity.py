@@ -268,3 +268,46 @@ def test_seip_cta_per_trajectory_kernel_matches_oracle(A, K, W):
     assert np.array_equal(np.isinf(got2), np.isinf(ref2))
     fin = np.isfinite(ref2)
     _assert_close(got2[fin], ref2[fin])
+
+
+@pytest.mark.gpu
+def test_row_mask_leaves_masked_trajectories_out():
+    """DynodeSolverDesc.only: masked rows are neither computed nor written, the others are bit-identical to
+    the unmasked launch -- through the plain solve (one generation per warp), the persistent-slot fused
+    log-likelihood with tangents (candidates scanned by ballot) and the adjoint."""
+    import torch
+    from dynode_b200 import _lib, engine
+    from tests.cases import make_case
+
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    for name, B in (("seirs_multi_a2s3", 333), ("sir_age2", 1000), ("seirs_seasonal", 777)):
+        case = make_case(name, B)
+        model, t1 = case["model"], float(min(case["t1"], 120))
+        prm = {k: t(v) for k, v in case["params"].items()}
+        y0 = t(case["y0"])
+        contact = None if case["contact"] is None else t(case["contact"])
+        ts = np.linspace(0.0, t1, int(t1) + 1)
+        opts = engine.SolverOptions(t1=t1)
+        for frac in (0.5, 0.03, 0.0):
+            mask = (torch.rand(B, device=dev, generator=g) < frac)
+            ys0, _, st0 = engine.solve_ensemble(model, y0, prm, contact, opts, ts, B=B)
+            with engine.only_rows(mask.view(torch.uint8)):
+                ys1, _, st1 = engine.solve_ensemble(model, y0, prm, contact, opts, ts, B=B)
+            assert torch.equal(ys1[mask], ys0[mask]) and torch.equal(st1[mask], st0[mask])
+            assert not ys1[~mask].any() and not st1[~mask].any()
+            obs_comp = model.n_compartments - 1
+            m = model.compartment_sizes()[obs_comp]
+            obs = torch.rand(len(ts) - 1, m, dtype=torch.float64, device=dev, generator=g) + 0.1
+            wrt = [_lib.wrt_id(_lib.P_BETA, 0), _lib.wrt_id(_lib.P_GAMMA, 0)]
+            lp0, g0, s0 = engine.poisson_loglik_grad(model, y0, prm, contact, opts, ts, obs_comp, obs, wrt=wrt, B=B)
+            with engine.only_rows(mask.view(torch.uint8)):
+                lp1, g1, s1 = engine.poisson_loglik_grad(model, y0, prm, contact, opts, ts, obs_comp, obs, wrt=wrt, B=B)
+            assert torch.equal(lp1[mask], lp0[mask]) and torch.equal(g1[mask], g0[mask]) and torch.equal(s1[mask], s0[mask])
+            assert not lp1[~mask].any() and not g1[~mask].any()
+            la0, ga0, _, sa0 = engine.poisson_loglik_adjoint(model, y0, prm, contact, opts, ts, obs_comp, obs, B=B)
+            with engine.only_rows(mask.view(torch.uint8)):
+                la1, ga1, _, sa1 = engine.poisson_loglik_adjoint(model, y0, prm, contact, opts, ts, obs_comp, obs, B=B)
+            assert torch.equal(la1[mask], la0[mask]) and torch.equal(ga1[mask], ga0[mask])
+            assert not la1[~mask].any() and not ga1[~mask].any()
