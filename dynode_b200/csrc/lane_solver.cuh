@@ -225,6 +225,10 @@ struct LaneSolver {
   }
 
   static DYN_DI double sq(double x) { return x * x; }
+  // base + k rows of N doubles, written as byte arithmetic so that it folds into one IMAD.WIDE
+  static DYN_DI double* row_ptr(double* base, int k) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + (int64_t)k * (int64_t)(N * 8));
+  }
 
   // ClipStepSizeController(jump_ts): a step [t0, t1] that would contain a discontinuity point ends just
   // before it.  i0 = #{jump <= t0}, i1 = #{jump <= t1}; a jump lies in (t0, t1] iff
@@ -320,7 +324,7 @@ struct LaneSolver {
     bool active = false;
     double sn0 = 0.0, cs0 = 1.0;  // seasonal sine / cosine at tprev of my slot (exact, libm)
     bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
-    double* out_s = a.ys;  // running output pointers of the full-save fast path
+    double* out_s = a.ys;  // row 0 of my trajectory in ys (my S_g / my cell): the full-save fast path
     double* out_c = a.ys;
     D lp_acc = make_dual<P>(0.0), obs_prev = make_dual<P>(0.0);
 #pragma unroll
@@ -693,22 +697,33 @@ struct LaneSolver {
           return dfma(hth2, u, dfma(hthw, f[0][e], y[e]));
         };
         if (IS_SAVE && P == 0 && full_save) {
-          // fast path: every compartment saved -> compile-time offsets off two running pointers
-          while (true) {
-            const bool pend = ts_next <= tnext;
-            if (!__any_sync(0xffffffffu, pend)) break;
-            if (pend) {
-              const double th = (ts_next - tprev) * inv_h;
-              const double hthw = hw * th, hth2 = (h * th) * th;
-              const D v0 = dense(0, th, hthw, hth2);
-              if (lead) *out_s = v0.v;
+          // fast path: every compartment saved -> compile-time offsets off the trajectory's two row pointers.
+          // One pass of this loop is the unit the warp pays for every slot whenever ANY slot has a save
+          // pending (profiles/r1/lockstep_probe.md), so it is kept short: row address = base + save_i * N (one
+          // IMAD.WIDE each, no loop-carried pointers), pending-ness evaluated once per pass, and the
+          // uniform-grid / loaded-grid choice made outside the loop.
+          auto passes = [&](auto next_time) {
+            bool pend = ts_next <= tnext;
+            do {
+              if (pend) {
+                const double th = (ts_next - tprev) * inv_h;
+                const double hthw = hw * th, hth2 = (h * th) * th;
+                const D v0 = dense(0, th, hthw, hth2);
+                if (lead) *row_ptr(out_s, save_i) = v0.v;
+                double* const pc = row_ptr(out_c, save_i);
 #pragma unroll
-              for (int e = 1; e < NE; ++e) out_c[(e - 1) * G * S] = dense(e, th, hthw, hth2).v;
-              out_s += N;
-              out_c += N;
-              ++save_i;
-              ts_next = save_time(save_i);
-            }
+                for (int e = 1; e < NE; ++e) pc[(e - 1) * G * S] = dense(e, th, hthw, hth2).v;
+                ++save_i;
+                ts_next = next_time(save_i);
+              }
+              pend = ts_next <= tnext;
+            } while (__any_sync(0xffffffffu, pend));
+          };
+          if (a.save_dt > 0.0) {
+            // t0 + k*dt exceeds t1 >= tnext for k >= T, so "no save left" needs no case of its own
+            passes([&](int k) -> double { return (k == a.T - 1) ? t1 : fma((double)k, a.save_dt, a.t0); });
+          } else {
+            passes([&](int k) -> double { return (k < a.T) ? __ldg(a.save_ts + k) : CUDART_INF; });
           }
         } else {
           while (true) {
