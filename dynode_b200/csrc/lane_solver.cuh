@@ -559,7 +559,10 @@ struct LaneSolver {
       if constexpr (SEASONAL) {
         season_angle(tnext, pl, sn1, cs1);
         wstep = ((2.0 * CUDART_PI) * h) / pl.period;
-        small_step = !__any_sync(0xffffffffu, fabs(wstep) > 0.5);
+        // per lane, not per warp: a trajectory's arithmetic must not depend on which trajectories share its warp
+        // (a permutation or a different sharding of the ensemble has to reproduce it bit for bit); all lanes of
+        // one trajectory share h and the period, hence the decision
+        small_step = !(fabs(wstep) > 0.5);
       }
       auto stage_rhs = [&](double t, double ci, D (&out)[NE]) {  // inner stage at t = tprev + ci*h
         if constexpr (SEASONAL) {
