@@ -32,6 +32,14 @@
 
 namespace dynode {
 
+// Taylor coefficients of sin(d)/d - 1 and cos(d) - 1 in z = d^2, highest power first (sincos_small)
+static __constant__ double kSinTaylor[7] = {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0,
+                                            1.0 / 362880.0,         -1.0 / 5040.0,      1.0 / 120.0,
+                                            -1.0 / 6.0};
+static __constant__ double kCosTaylor[8] = {1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0,
+                                            -1.0 / 3628800.0,       1.0 / 40320.0,        -1.0 / 720.0,
+                                            1.0 / 24.0,             -0.5};
+
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
 struct LaneSolver {
   static constexpr bool HAS_E = FLOW != DYNODE_FLOW_SIR;
@@ -149,23 +157,16 @@ struct LaneSolver {
   // a libm sincos (~75 instructions, a third of them 64-bit constant moves); used with the angle-addition
   // formulas for the stage times inside a step, the base angle being evaluated exactly once per step
   static DYN_DI void sincos_small(double d, double& sd, double& cd) {
+    // coefficients from constant memory (kSinTaylor / kCosTaylor below): c[bank][offset] operands of DFMA; as
+    // literals they cost 24 UMOVs per call, 96 per step (SASS of the seasonal instance)
     const double z = d * d;
-    double ps = -1.0 / 1307674368000.0;
-    ps = fma(ps, z, 1.0 / 6227020800.0);
-    ps = fma(ps, z, -1.0 / 39916800.0);
-    ps = fma(ps, z, 1.0 / 362880.0);
-    ps = fma(ps, z, -1.0 / 5040.0);
-    ps = fma(ps, z, 1.0 / 120.0);
-    ps = fma(ps, z, -1.0 / 6.0);
+    double ps = kSinTaylor[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) ps = fma(ps, z, kSinTaylor[k]);
     sd = fma(d * z, ps, d);
-    double pc = 1.0 / 20922789888000.0;
-    pc = fma(pc, z, -1.0 / 87178291200.0);
-    pc = fma(pc, z, 1.0 / 479001600.0);
-    pc = fma(pc, z, -1.0 / 3628800.0);
-    pc = fma(pc, z, 1.0 / 40320.0);
-    pc = fma(pc, z, -1.0 / 720.0);
-    pc = fma(pc, z, 1.0 / 24.0);
-    pc = fma(pc, z, -0.5);
+    double pc = kCosTaylor[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) pc = fma(pc, z, kCosTaylor[k]);
     cd = fma(z, pc, 1.0);
   }
 
