@@ -150,7 +150,9 @@ struct LaneSolver {
   // ---- right-hand side of the flow family in lane layout -------------
   // sin / cos of the seasonal angle 2*pi*t/period + phase (seirs_seasonal_forcing.py:34-37)
   static DYN_DI void season_angle(double t, const Prm& p, double& sn, double& cs) {
-    const double w = ((2.0 * CUDART_PI) * t) / p.period;
+    // quotient by reciprocal + one correction (faithfully rounded; the IEEE division sequence costs ~4x as much and
+    // runs once or twice per step)
+    const double w = div_fast((2.0 * CUDART_PI) * t, p.period);
     sincos(p.phase.v + w, &sn, &cs);
   }
   // sin / cos of a small increment |d| <= 0.5 by Taylor series in d^2 (remainder < 1e-18): 16 FMAs instead of
@@ -559,7 +561,7 @@ struct LaneSolver {
       bool small_step = true;
       if constexpr (SEASONAL) {
         season_angle(tnext, pl, sn1, cs1);
-        wstep = ((2.0 * CUDART_PI) * h) / pl.period;
+        wstep = div_fast((2.0 * CUDART_PI) * h, pl.period);
         // per lane, not per warp: a trajectory's arithmetic must not depend on which trajectories share its warp
         // (a permutation or a different sharding of the ensemble has to reproduce it bit for bit); all lanes of
         // one trajectory share h and the period, hence the decision
