@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "dynode_poisson_loglik_grad_f64", "dynode_poisson_loglik_adjoint_f64", "dynode_probe_dfma",
     "dynode_probe_hbm_write",
     "dynode_nuts_round_pre", "dynode_nuts_round_post", "dynode_seip_state_size", "dynode_seip_solve_f64",
+    "dynode_bijector_f64", "dynode_bijector_vjp_f64",
 )
 
 
@@ -128,6 +129,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_nuts_round_pre.argtypes = [NP, vp, vp, vp]
     L.dynode_nuts_round_post.restype = ctypes.c_int
     L.dynode_nuts_round_post.argtypes = [NP, vp, vp, vp, vp]
+    dbl = ctypes.c_double
+    L.dynode_bijector_f64.restype = ctypes.c_int
+    L.dynode_bijector_f64.argtypes = [i32, i64, vp, dbl, dbl, vp, vp, vp]
+    L.dynode_bijector_vjp_f64.restype = ctypes.c_int
+    L.dynode_bijector_vjp_f64.argtypes = [i32, i64, vp, dbl, vp, vp, vp, vp]
     L.dynode_probe_dfma.restype = i64
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int

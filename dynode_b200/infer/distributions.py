@@ -213,6 +213,91 @@ def biject_to(support: Constraint) -> Transform:
     raise NotImplementedError(f"no bijector for support {support!r}")
 
 
+# ---- fused bijector + log-Jacobian on the device (include/dynode_b200_ppl.h) ---------------------------
+BIJ_INTERVAL, BIJ_GREATER_THAN, BIJ_LESS_THAN = 0, 1, 2
+
+
+class _FusedBijector(torch.autograd.Function):
+    """(z) -> (x, log|dx/dz|) for biject_to(interval / greater_than / less_than) in ONE elementwise kernel,
+    its vector-Jacobian product in another: `dynode_bijector_f64` / `dynode_bijector_vjp_f64`.  The same map
+    written with tensor operations is ~13 launches forward and ~12 backward per site, which at a few thousand
+    NUTS chains is most of a round."""
+
+    @staticmethod
+    def forward(z, kind: int, a: float, b: float):
+        import ctypes
+
+        from .. import _lib
+        zc = z.contiguous()
+        x, ladj = torch.empty_like(zc), torch.empty_like(zc)
+        _lib.check(_lib.load().dynode_bijector_f64(int(kind), zc.numel(), zc.data_ptr(), float(a), float(b),
+                                                   x.data_ptr(), ladj.data_ptr(),
+                                                   ctypes.c_void_p(_lib.current_stream_ptr())))
+        return x, ladj
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        z, kind, a, b = inputs
+        ctx.kind, ctx.b = int(kind), float(b)
+        ctx.save_for_backward(z)
+
+    @staticmethod
+    def backward(ctx, gx, gl):
+        import ctypes
+
+        from .. import _lib
+        (z,) = ctx.saved_tensors
+        zc, gxc, glc = z.contiguous(), gx.contiguous(), gl.contiguous()
+        gz = torch.empty_like(zc)
+        _lib.check(_lib.load().dynode_bijector_vjp_f64(ctx.kind, zc.numel(), zc.data_ptr(), ctx.b, gxc.data_ptr(),
+                                                       glc.data_ptr(), gz.data_ptr(),
+                                                       ctypes.c_void_p(_lib.current_stream_ptr())))
+        return gz, None, None, None
+
+    @staticmethod
+    def vmap(info, in_dims, z, kind, a, b):  # elementwise: the batch axis is just one more axis
+        x, ladj = _FusedBijector.apply(z.movedim(in_dims[0], 0), kind, a, b)
+        return (x, ladj), (0, 0)
+
+
+def _host_float(v) -> Optional[float]:
+    """A bound as a python float when it is a number or a 0-dim HOST tensor (no device sync), else None."""
+    if isinstance(v, (int, float)):
+        return float(v)
+    if isinstance(v, torch.Tensor) and v.device.type == "cpu" and v.numel() == 1 and not v.requires_grad \
+            and not torch._C._functorch.is_batchedtensor(v):
+        return float(v)
+    return None
+
+
+def constrain_with_ladj(support: Constraint, z: torch.Tensor):
+    """x = biject_to(support)(z) and log|dx/dz| (elementwise).  Latent sites on a CUDA device whose support has
+    constant bounds take the fused kernels; everything else the composed transforms."""
+    if z.is_cuda and z.dtype == _F64:
+        kind = a = b = None
+        if isinstance(support, _UnitInterval):
+            kind, a, b = BIJ_INTERVAL, 0.0, 1.0
+        elif isinstance(support, _Interval):
+            lo, hi = _host_float(support.lower_bound), _host_float(support.upper_bound)
+            if lo is not None and hi is not None:
+                kind, a, b = BIJ_INTERVAL, lo, hi - lo
+        elif isinstance(support, _Positive):
+            kind, a, b = BIJ_GREATER_THAN, 0.0, 1.0
+        elif isinstance(support, _GreaterThan):
+            lo = _host_float(support.lower_bound)
+            if lo is not None:
+                kind, a, b = BIJ_GREATER_THAN, lo, 1.0
+        elif isinstance(support, _LessThan):
+            hi = _host_float(support.upper_bound)
+            if hi is not None:
+                kind, a, b = BIJ_LESS_THAN, hi, 1.0
+        if kind is not None:
+            return _FusedBijector.apply(z, kind, a, b)
+    t = biject_to(support)
+    x = t(z)
+    return x, t.log_abs_det_jacobian(z, x)
+
+
 # ------------------------------------------------------------------------------ distributions
 def _std_normal_cdf(x):
     return 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))

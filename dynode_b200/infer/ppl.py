@@ -137,10 +137,9 @@ class log_density_handler(Messenger):
     def process_message(self, msg):
         if msg["type"] == "sample" and not msg["is_observed"] and msg["name"] in self.z:
             z = self.z[msg["name"]]
-            t = dist.biject_to(msg["fn"].support)
-            x = t(z)
+            x, ladj = dist.constrain_with_ladj(msg["fn"].support, z)
             msg["value"] = x
-            self.logp = self.logp + t.log_abs_det_jacobian(z, x).sum()
+            self.logp = self.logp + ladj.sum()
             self.constrained[msg["name"]] = x
 
     def postprocess_message(self, msg):

@@ -105,8 +105,10 @@ def test_mcmc_process_recovers_the_generating_parameters():
     proc.infer(config=cfg, tf=100, obs_data=obs)
     s = proc.get_samples()
     assert s["strains_0_r0"].shape == (6400,)
-    assert abs(float(s["strains_0_r0"].mean()) - 2.0) < 0.05
-    assert abs(float(s["strains_0_infectious_period"].mean()) - 7.0) < 0.3
+    # the posterior means of this model are 2.0454 and 7.197 (262144 chains, profiles/r1/nuts_async.md): the
+    # generating values 2 and 7 shifted by the priors; 64 chains x 100 draws scatter around them by ~0.01 / 0.05
+    assert abs(float(s["strains_0_r0"].mean()) - 2.045) < 0.03
+    assert abs(float(s["strains_0_infectious_period"].mean()) - 7.2) < 0.25
     summ = proc._inferer.summary()
     assert summ["strains_0_r0"]["r_hat"] < 1.05
     # general (trajectory-materialising) model through the same process, fewer chains
@@ -233,3 +235,35 @@ def test_cuda_nuts_round_equals_the_torch_round():
     assert eng.graph_used and eng.kernels_used
     x = z.reshape(-1, 3)
     assert torch.allclose(x.mean(0), mu, atol=0.05) and torch.allclose(torch.cov(x.T), cov, atol=0.08)
+
+
+def test_fused_bijector_equals_the_composed_transforms():
+    """dynode_bijector_f64 / _vjp_f64 (one launch each way) against biject_to(support) written with tensor
+    operations: value, log-Jacobian and the gradient of an arbitrary function of both, plain and under vmap."""
+    from dynode_b200.infer import distributions as D
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(3)
+    z0 = torch.randn(4097, dtype=torch.float64, device=dev, generator=g) * 6.0
+    z0[:4] = torch.tensor([-745.0, -40.0, 40.0, 700.0], dtype=torch.float64, device=dev)  # tails stay finite
+    w1, w2 = (torch.randn(4097, dtype=torch.float64, device=dev, generator=g) for _ in range(2))
+    for sup in (D.constraints.unit_interval, D.constraints.interval(2.0, 15.0), D.constraints.interval(1.5, 2.5),
+                D.constraints.positive, D.constraints.greater_than(-3.0), D.constraints.less_than(4.0)):
+        outs = []
+        for fused in (True, False):
+            z = z0.clone().requires_grad_(True)
+            if fused:
+                x, l = D.constrain_with_ladj(sup, z)
+            else:
+                t = D.biject_to(sup)
+                x = t(z)
+                l = t.log_abs_det_jacobian(z, x)
+            (gz,) = torch.autograd.grad((w1 * x).sum() + (w2 * l).sum(), z)
+            outs.append((x.detach(), l.detach(), gz))
+        for a, b in zip(*outs):
+            fin = torch.isfinite(b)
+            assert torch.equal(torch.isfinite(a), fin)
+            assert torch.allclose(a[fin], b[fin], rtol=1e-13, atol=1e-13), sup
+        # under vmap (how ModelDensity evaluates the model for all chains at once)
+        f = lambda zz: D.constrain_with_ladj(sup, zz)
+        xv, lv = torch.vmap(f)(z0)
+        assert torch.equal(xv, outs[0][0]) and torch.equal(lv, outs[0][1])
