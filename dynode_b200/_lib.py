@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = (
     "dynode_poisson_loglik_grad_f64", "dynode_poisson_loglik_adjoint_f64", "dynode_probe_dfma",
     "dynode_probe_hbm_write",
     "dynode_nuts_round_pre", "dynode_nuts_round_post", "dynode_seip_state_size", "dynode_seip_solve_f64",
-    "dynode_bijector_f64", "dynode_bijector_vjp_f64",
+    "dynode_bijector_f64", "dynode_bijector_vjp_f64", "dynode_site_logdensity_f64",
+    "dynode_site_logdensity_vjp_f64",
 )
 
 
@@ -47,6 +48,14 @@ class SolverDesc(ctypes.Structure):
                 ("atol", ctypes.c_double), ("const_dt", ctypes.c_double), ("max_steps", ctypes.c_int64),
                 ("save_dt", ctypes.c_double), ("jump_ts", ctypes.c_void_p), ("n_jump", ctypes.c_int32),
                 ("only", ctypes.c_void_p)]
+
+
+class SiteDesc(ctypes.Structure):
+    """DynodeSiteDesc of include/dynode_b200_ppl.h."""
+
+    _fields_ = [("bijector", ctypes.c_int32), ("family", ctypes.c_int32), ("a", ctypes.c_double),
+                ("b", ctypes.c_double), ("p0", ctypes.c_double), ("p1", ctypes.c_double), ("c", ctypes.c_double),
+                ("aff_loc", ctypes.c_double), ("aff_scale", ctypes.c_double)]
 
 
 class Array(ctypes.Structure):
@@ -134,6 +143,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_bijector_f64.argtypes = [i32, i64, vp, dbl, dbl, vp, vp, vp]
     L.dynode_bijector_vjp_f64.restype = ctypes.c_int
     L.dynode_bijector_vjp_f64.argtypes = [i32, i64, vp, dbl, vp, vp, vp, vp]
+    SD = ctypes.POINTER(SiteDesc)
+    L.dynode_site_logdensity_f64.restype = ctypes.c_int
+    L.dynode_site_logdensity_f64.argtypes = [SD, i64, vp, vp, vp, vp]
+    L.dynode_site_logdensity_vjp_f64.restype = ctypes.c_int
+    L.dynode_site_logdensity_vjp_f64.argtypes = [SD, i64, vp, vp, vp, vp, vp]
     L.dynode_probe_dfma.restype = i64
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int

@@ -22,20 +22,35 @@ __device__ __forceinline__ double sigmoid(double v) {
   return v >= 0.0 ? s : e * s;
 }
 
+// x, dx/dz, log|dx/dz| and its derivative for one element
+struct Bij { double x, dxdz, ladj, dladj; };
+__device__ __forceinline__ Bij bijector(int kind, double v, double a, double b, double logb) {
+  Bij r;
+  if (kind == DYNODE_BIJ_INTERVAL) {
+    const double s = sigmoid(v);
+    r.x = fma(b, s, a);
+    r.dxdz = b * s * (1.0 - s);
+    r.ladj = logb - softplus(v) - softplus(-v);
+    r.dladj = 1.0 - 2.0 * s;
+  } else if (kind == DYNODE_BIJ_REAL) {
+    r.x = v; r.dxdz = 1.0; r.ladj = 0.0; r.dladj = 0.0;
+  } else {
+    const double e = exp(v);
+    r.x = (kind == DYNODE_BIJ_GREATER_THAN) ? a + e : a - e;
+    r.dxdz = (kind == DYNODE_BIJ_GREATER_THAN) ? e : -e;
+    r.ladj = v;
+    r.dladj = 1.0;
+  }
+  return r;
+}
 __global__ void __launch_bounds__(256) bijector_kernel(int kind, int64_t n, const double* __restrict__ z, double a,
                                                         double b, double* __restrict__ x, double* __restrict__ ladj) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double logb = (kind == DYNODE_BIJ_INTERVAL) ? log(fabs(b)) : 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double v = z[i];
-    if (kind == DYNODE_BIJ_INTERVAL) {
-      x[i] = fma(b, sigmoid(v), a);
-      ladj[i] = logb - softplus(v) - softplus(-v);
-    } else {
-      const double e = exp(v);
-      x[i] = (kind == DYNODE_BIJ_GREATER_THAN) ? a + e : a - e;
-      ladj[i] = v;
-    }
+    const Bij r = bijector(kind, z[i], a, b, logb);
+    x[i] = r.x;
+    ladj[i] = r.ladj;
   }
 }
 
@@ -44,15 +59,54 @@ __global__ void __launch_bounds__(256) bijector_vjp_kernel(int kind, int64_t n, 
                                                             const double* __restrict__ gl, double* __restrict__ gz) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double v = z[i];
-    if (kind == DYNODE_BIJ_INTERVAL) {
-      const double s = sigmoid(v);
-      // dx/dz = b s (1 - s);  d/dz (-softplus(z) - softplus(-z)) = 1 - 2 s
-      gz[i] = fma(gx[i], b * s * (1.0 - s), gl[i] * (1.0 - 2.0 * s));
-    } else {
-      const double e = exp(v);
-      gz[i] = fma(gx[i], (kind == DYNODE_BIJ_GREATER_THAN) ? e : -e, gl[i]);
+    const Bij r = bijector(kind, z[i], 0.0, b, 0.0);
+    gz[i] = fma(gx[i], r.dxdz, gl[i] * r.dladj);
+  }
+}
+
+__device__ __forceinline__ double xlogy(double c, double y) { return c == 0.0 ? 0.0 : c * log(y); }
+// f_family(u) and its derivative
+__device__ __forceinline__ void family(int fam, double u, double p0, double p1, double& f, double& df) {
+  switch (fam) {
+    case DYNODE_FAM_NORMAL: { const double t = (u - p0) / p1; f = -0.5 * t * t; df = -t / p1; break; }
+    case DYNODE_FAM_UNIFORM: f = 0.0; df = 0.0; break;
+    case DYNODE_FAM_BETA:
+      f = xlogy(p0 - 1.0, u) + xlogy(p1 - 1.0, 1.0 - u);
+      df = (p0 - 1.0) / u - (p1 - 1.0) / (1.0 - u);
+      break;
+    case DYNODE_FAM_GAMMA: f = (p0 - 1.0) * log(u) - p1 * u; df = (p0 - 1.0) / u - p1; break;
+    case DYNODE_FAM_LOGNORMAL: {
+      const double lv = log(u), t = (lv - p0) / p1;
+      f = -0.5 * t * t - lv; df = -(t / p1 + 1.0) / u; break;
     }
+    case DYNODE_FAM_HALFNORMAL: { const double t = u / p0; f = -0.5 * t * t; df = -t / p0; break; }
+    default: f = -p0 * u; df = -p0; break;  // EXPONENTIAL
+  }
+}
+
+__global__ void __launch_bounds__(256) site_kernel(const DynodeSiteDesc s, int64_t n, const double* __restrict__ z,
+                                                    double* __restrict__ x, double* __restrict__ lp) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double logb = (s.bijector == DYNODE_BIJ_INTERVAL) ? log(fabs(s.b)) : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Bij r = bijector(s.bijector, z[i], s.a, s.b, logb);
+    double f, df;
+    family(s.family, (r.x - s.aff_loc) / s.aff_scale, s.p0, s.p1, f, df);
+    x[i] = r.x;
+    lp[i] = r.ladj + (f + s.c);
+  }
+}
+__global__ void __launch_bounds__(256) site_vjp_kernel(const DynodeSiteDesc s, int64_t n, const double* __restrict__ z,
+                                                        const double* __restrict__ gx, const double* __restrict__ glp,
+                                                        double* __restrict__ gz) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Bij r = bijector(s.bijector, z[i], s.a, s.b, 0.0);
+    double f, df;
+    family(s.family, (r.x - s.aff_loc) / s.aff_scale, s.p0, s.p1, f, df);
+    // a site pushed to the edge of its support (x == bound in floating point) has dx/dz == 0: no 0 * inf
+    const double chain = (r.dxdz == 0.0) ? 0.0 : (df / s.aff_scale) * r.dxdz;
+    gz[i] = fma(gx[i], r.dxdz, glp[i] * (r.dladj + chain));
   }
 }
 
@@ -70,7 +124,7 @@ extern "C" {
 
 int dynode_bijector_f64(int32_t kind, int64_t n, const double* z, double a, double b, double* x, double* ladj,
                         void* stream) {
-  if (kind < 0 || kind > DYNODE_BIJ_LESS_THAN) return fail_msg("unknown bijector kind %d", kind);
+  if (kind < 0 || kind > DYNODE_BIJ_REAL) return fail_msg("unknown bijector kind %d", kind);
   if (n < 0 || (n > 0 && (!z || !x || !ladj))) return fail_msg("bijector: null buffer");
   if (n == 0) return 0;
   bijector_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(kind, n, z, a, b, x, ladj);
@@ -80,12 +134,40 @@ int dynode_bijector_f64(int32_t kind, int64_t n, const double* z, double a, doub
 
 int dynode_bijector_vjp_f64(int32_t kind, int64_t n, const double* z, double b, const double* gx, const double* gl,
                             double* gz, void* stream) {
-  if (kind < 0 || kind > DYNODE_BIJ_LESS_THAN) return fail_msg("unknown bijector kind %d", kind);
+  if (kind < 0 || kind > DYNODE_BIJ_REAL) return fail_msg("unknown bijector kind %d", kind);
   if (n < 0 || (n > 0 && (!z || !gx || !gl || !gz))) return fail_msg("bijector vjp: null buffer");
   if (n == 0) return 0;
   bijector_vjp_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(kind, n, z, b, gx, gl, gz);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("bijector vjp launch failed: %s", cudaGetErrorString(e));
+}
+
+static int check_site(const DynodeSiteDesc* s) {
+  if (!s) return fail_msg("null site descriptor");
+  if (s->bijector < 0 || s->bijector > DYNODE_BIJ_REAL) return fail_msg("unknown bijector kind %d", s->bijector);
+  if (s->family < 0 || s->family > DYNODE_FAM_EXPONENTIAL) return fail_msg("unknown prior family %d", s->family);
+  if (!(s->aff_scale != 0.0)) return fail_msg("site: aff_scale must be non-zero");
+  return 0;
+}
+
+int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const double* z, double* x, double* lp,
+                               void* stream) {
+  if (int rc = check_site(site)) return rc;
+  if (n < 0 || (n > 0 && (!z || !x || !lp))) return fail_msg("site: null buffer");
+  if (n == 0) return 0;
+  site_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, x, lp);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail_msg("site launch failed: %s", cudaGetErrorString(e));
+}
+
+int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, const double* gx,
+                                   const double* glp, double* gz, void* stream) {
+  if (int rc = check_site(site)) return rc;
+  if (n < 0 || (n > 0 && (!z || !gx || !glp || !gz))) return fail_msg("site vjp: null buffer");
+  if (n == 0) return 0;
+  site_vjp_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, gx, glp, gz);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail_msg("site vjp launch failed: %s", cudaGetErrorString(e));
 }
 
 }  // extern "C"

@@ -214,7 +214,7 @@ def biject_to(support: Constraint) -> Transform:
 
 
 # ---- fused bijector + log-Jacobian on the device (include/dynode_b200_ppl.h) ---------------------------
-BIJ_INTERVAL, BIJ_GREATER_THAN, BIJ_LESS_THAN = 0, 1, 2
+BIJ_INTERVAL, BIJ_GREATER_THAN, BIJ_LESS_THAN, BIJ_REAL = 0, 1, 2, 3
 
 
 class _FusedBijector(torch.autograd.Function):
@@ -270,29 +270,135 @@ def _host_float(v) -> Optional[float]:
     return None
 
 
+FAM_NORMAL, FAM_UNIFORM, FAM_BETA, FAM_GAMMA, FAM_LOGNORMAL, FAM_HALFNORMAL, FAM_EXPONENTIAL = range(7)
+
+
+def _bijector_spec(support: Constraint):
+    """(kind, a, b) of the fused bijector for a support with constant bounds, else None."""
+    if isinstance(support, _Real):
+        return BIJ_REAL, 0.0, 1.0
+    if isinstance(support, _UnitInterval):
+        return BIJ_INTERVAL, 0.0, 1.0
+    if isinstance(support, _Interval):
+        lo, hi = _host_float(support.lower_bound), _host_float(support.upper_bound)
+        return None if lo is None or hi is None else (BIJ_INTERVAL, lo, hi - lo)
+    if isinstance(support, _Positive):
+        return BIJ_GREATER_THAN, 0.0, 1.0
+    if isinstance(support, _GreaterThan):
+        lo = _host_float(support.lower_bound)
+        return None if lo is None else (BIJ_GREATER_THAN, lo, 1.0)
+    if isinstance(support, _LessThan):
+        hi = _host_float(support.upper_bound)
+        return None if hi is None else (BIJ_LESS_THAN, hi, 1.0)
+    return None
+
+
+def _family_spec(fn):
+    """(family, p0, p1, c, aff_loc, aff_scale) for a prior whose parameters are constants (numbers / 0-dim host
+    tensors), with c = every x-independent term of its log_prob; None if the fused site kernel cannot state it."""
+    hf = _host_float
+    if isinstance(fn, TransformedDistribution) and isinstance(fn.transform, AffineTransform):
+        base, loc, sc = _family_spec(fn.base_dist), hf(fn.transform.loc), hf(fn.transform.scale)
+        if base is None or loc is None or sc is None or sc == 0.0 or base[4:] != (0.0, 1.0):
+            return None
+        return base[0], base[1], base[2], base[3] - math.log(abs(sc)), loc, sc
+    vals = [hf(v) for v in fn._params()] if type(fn) in (Normal, LogNormal, HalfNormal, Exponential, Uniform,
+                                                         Gamma, Beta, TruncatedNormal) else [None]
+    if any(v is None for v in vals):
+        return None
+    half_log_2pi = 0.5 * math.log(2.0 * math.pi)
+    if type(fn) is Normal:
+        return FAM_NORMAL, vals[0], vals[1], -math.log(vals[1]) - half_log_2pi, 0.0, 1.0
+    if type(fn) is TruncatedNormal:
+        lo = None if fn.low is None else hf(fn.low)
+        hi = None if fn.high is None else hf(fn.high)
+        if (fn.low is not None and lo is None) or (fn.high is not None and hi is None):
+            return None
+        a, b = fn._cdf_bounds()  # host scalars
+        return FAM_NORMAL, vals[0], vals[1], -math.log(vals[1]) - half_log_2pi - math.log(float(b - a)), 0.0, 1.0
+    if type(fn) is LogNormal:
+        return FAM_LOGNORMAL, vals[0], vals[1], -math.log(vals[1]) - half_log_2pi, 0.0, 1.0
+    if type(fn) is HalfNormal:
+        return FAM_HALFNORMAL, vals[0], 0.0, -math.log(vals[0]) + 0.5 * math.log(2.0 / math.pi), 0.0, 1.0
+    if type(fn) is Exponential:
+        return FAM_EXPONENTIAL, vals[0], 0.0, math.log(vals[0]), 0.0, 1.0
+    if type(fn) is Uniform:
+        return FAM_UNIFORM, 0.0, 0.0, -math.log(vals[1] - vals[0]), 0.0, 1.0
+    if type(fn) is Gamma:
+        return FAM_GAMMA, vals[0], vals[1], vals[0] * math.log(vals[1]) - math.lgamma(vals[0]), 0.0, 1.0
+    if type(fn) is Beta:
+        a, b = vals
+        return FAM_BETA, a, b, -(math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b)), 0.0, 1.0
+    return None
+
+
+class _FusedSite(torch.autograd.Function):
+    """z -> (x, log|dx/dz| + log p(x)) for a latent site whose prior has constant parameters: ONE elementwise
+    kernel forward and one backward (`dynode_site_logdensity_f64` / `_vjp_f64`) in place of the ~25 launches the
+    composed transforms and log_prob take each way."""
+
+    @staticmethod
+    def forward(z, spec):
+        import ctypes
+
+        from .. import _lib
+        zc = z.contiguous()
+        x, lp = torch.empty_like(zc), torch.empty_like(zc)
+        sd = _lib.SiteDesc(*spec)
+        _lib.check(_lib.load().dynode_site_logdensity_f64(ctypes.byref(sd), zc.numel(), zc.data_ptr(), x.data_ptr(),
+                                                          lp.data_ptr(), ctypes.c_void_p(_lib.current_stream_ptr())))
+        return x, lp
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        z, spec = inputs
+        ctx.spec = spec
+        ctx.save_for_backward(z)
+
+    @staticmethod
+    def backward(ctx, gx, glp):
+        import ctypes
+
+        from .. import _lib
+        (z,) = ctx.saved_tensors
+        zc, gxc, glc = z.contiguous(), gx.contiguous(), glp.contiguous()
+        gz = torch.empty_like(zc)
+        sd = _lib.SiteDesc(*ctx.spec)
+        _lib.check(_lib.load().dynode_site_logdensity_vjp_f64(ctypes.byref(sd), zc.numel(), zc.data_ptr(),
+                                                              gxc.data_ptr(), glc.data_ptr(), gz.data_ptr(),
+                                                              ctypes.c_void_p(_lib.current_stream_ptr())))
+        return gz, None
+
+    @staticmethod
+    def vmap(info, in_dims, z, spec):
+        x, lp = _FusedSite.apply(z.movedim(in_dims[0], 0), spec)
+        return (x, lp), (0, 0)
+
+
+def fused_site(fn, z: torch.Tensor):
+    """(x, log|dx/dz| + fn.log_prob(x)) from one kernel when `z` lives on a CUDA device and the prior `fn` has
+    constant parameters and a supported family; None otherwise (the caller composes transforms + log_prob)."""
+    if not (z.is_cuda and z.dtype == _F64):
+        return None
+    spec = getattr(fn, "_fused_site_spec", False)
+    if spec is False:
+        bij, fam = _bijector_spec(fn.support), _family_spec(fn)
+        spec = None if bij is None or fam is None else (bij[0], fam[0], bij[1], bij[2], fam[1], fam[2], fam[3],
+                                                        fam[4], fam[5])
+        try:
+            fn._fused_site_spec = spec  # the prior objects of a config are reused by every model call
+        except AttributeError:
+            pass
+    return None if spec is None else _FusedSite.apply(z, spec)
+
+
 def constrain_with_ladj(support: Constraint, z: torch.Tensor):
     """x = biject_to(support)(z) and log|dx/dz| (elementwise).  Latent sites on a CUDA device whose support has
     constant bounds take the fused kernels; everything else the composed transforms."""
     if z.is_cuda and z.dtype == _F64:
-        kind = a = b = None
-        if isinstance(support, _UnitInterval):
-            kind, a, b = BIJ_INTERVAL, 0.0, 1.0
-        elif isinstance(support, _Interval):
-            lo, hi = _host_float(support.lower_bound), _host_float(support.upper_bound)
-            if lo is not None and hi is not None:
-                kind, a, b = BIJ_INTERVAL, lo, hi - lo
-        elif isinstance(support, _Positive):
-            kind, a, b = BIJ_GREATER_THAN, 0.0, 1.0
-        elif isinstance(support, _GreaterThan):
-            lo = _host_float(support.lower_bound)
-            if lo is not None:
-                kind, a, b = BIJ_GREATER_THAN, lo, 1.0
-        elif isinstance(support, _LessThan):
-            hi = _host_float(support.upper_bound)
-            if hi is not None:
-                kind, a, b = BIJ_LESS_THAN, hi, 1.0
-        if kind is not None:
-            return _FusedBijector.apply(z, kind, a, b)
+        spec = _bijector_spec(support)
+        if spec is not None and spec[0] != BIJ_REAL:
+            return _FusedBijector.apply(z, *spec)
     t = biject_to(support)
     x = t(z)
     return x, t.log_abs_det_jacobian(z, x)

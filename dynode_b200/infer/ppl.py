@@ -137,14 +137,20 @@ class log_density_handler(Messenger):
     def process_message(self, msg):
         if msg["type"] == "sample" and not msg["is_observed"] and msg["name"] in self.z:
             z = self.z[msg["name"]]
-            x, ladj = dist.constrain_with_ladj(msg["fn"].support, z)
+            whole = dist.fused_site(msg["fn"], z)
+            if whole is not None:  # bijector + log-Jacobian + prior log-density from one kernel
+                x, lp = whole
+                msg["prior_done"] = True
+            else:
+                x, lp = dist.constrain_with_ladj(msg["fn"].support, z)
             msg["value"] = x
-            self.logp = self.logp + ladj.sum()
+            self.logp = self.logp + lp.sum()
             self.constrained[msg["name"]] = x
 
     def postprocess_message(self, msg):
         if msg["type"] == "sample":
-            self.logp = self.logp + msg["fn"].log_prob(msg["value"]).sum()
+            if not msg.get("prior_done", False):
+                self.logp = self.logp + msg["fn"].log_prob(msg["value"]).sum()
         elif msg["type"] == "factor":
             self.logp = self.logp + msg["value"].sum()
 
