@@ -145,9 +145,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_bijector_vjp_f64.argtypes = [i32, i64, vp, dbl, vp, vp, vp, vp]
     SD = ctypes.POINTER(SiteDesc)
     L.dynode_site_logdensity_f64.restype = ctypes.c_int
-    L.dynode_site_logdensity_f64.argtypes = [SD, i64, vp, vp, vp, vp]
+    L.dynode_site_logdensity_f64.argtypes = [SD, i64, vp, i64, vp, vp, vp]
     L.dynode_site_logdensity_vjp_f64.restype = ctypes.c_int
-    L.dynode_site_logdensity_vjp_f64.argtypes = [SD, i64, vp, vp, vp, vp, vp]
+    L.dynode_site_logdensity_vjp_f64.argtypes = [SD, i64, vp, i64, vp, vp, vp, vp]
     L.dynode_probe_dfma.restype = i64
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int

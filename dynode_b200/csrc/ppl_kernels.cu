@@ -85,11 +85,11 @@ __device__ __forceinline__ void family(int fam, double u, double p0, double p1, 
 }
 
 __global__ void __launch_bounds__(256) site_kernel(const DynodeSiteDesc s, int64_t n, const double* __restrict__ z,
-                                                    double* __restrict__ x, double* __restrict__ lp) {
+                                                    int64_t zs, double* __restrict__ x, double* __restrict__ lp) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double logb = (s.bijector == DYNODE_BIJ_INTERVAL) ? log(fabs(s.b)) : 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const Bij r = bijector(s.bijector, z[i], s.a, s.b, logb);
+    const Bij r = bijector(s.bijector, z[i * zs], s.a, s.b, logb);
     double f, df;
     family(s.family, (r.x - s.aff_loc) / s.aff_scale, s.p0, s.p1, f, df);
     x[i] = r.x;
@@ -97,11 +97,12 @@ __global__ void __launch_bounds__(256) site_kernel(const DynodeSiteDesc s, int64
   }
 }
 __global__ void __launch_bounds__(256) site_vjp_kernel(const DynodeSiteDesc s, int64_t n, const double* __restrict__ z,
-                                                        const double* __restrict__ gx, const double* __restrict__ glp,
+                                                        int64_t zs, const double* __restrict__ gx,
+                                                        const double* __restrict__ glp,
                                                         double* __restrict__ gz) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const Bij r = bijector(s.bijector, z[i], s.a, s.b, 0.0);
+    const Bij r = bijector(s.bijector, z[i * zs], s.a, s.b, 0.0);
     double f, df;
     family(s.family, (r.x - s.aff_loc) / s.aff_scale, s.p0, s.p1, f, df);
     // a site pushed to the edge of its support (x == bound in floating point) has dx/dz == 0: no 0 * inf
@@ -150,22 +151,22 @@ static int check_site(const DynodeSiteDesc* s) {
   return 0;
 }
 
-int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const double* z, double* x, double* lp,
-                               void* stream) {
+int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const double* z, int64_t z_stride, double* x,
+                               double* lp, void* stream) {
   if (int rc = check_site(site)) return rc;
   if (n < 0 || (n > 0 && (!z || !x || !lp))) return fail_msg("site: null buffer");
   if (n == 0) return 0;
-  site_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, x, lp);
+  site_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, z_stride, x, lp);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("site launch failed: %s", cudaGetErrorString(e));
 }
 
-int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, const double* gx,
-                                   const double* glp, double* gz, void* stream) {
+int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, int64_t z_stride,
+                                   const double* gx, const double* glp, double* gz, void* stream) {
   if (int rc = check_site(site)) return rc;
   if (n < 0 || (n > 0 && (!z || !gx || !glp || !gz))) return fail_msg("site vjp: null buffer");
   if (n == 0) return 0;
-  site_vjp_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, gx, glp, gz);
+  site_vjp_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*site, n, z, z_stride, gx, glp, gz);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("site vjp launch failed: %s", cudaGetErrorString(e));
 }

@@ -335,17 +335,25 @@ def _family_spec(fn):
 class _FusedSite(torch.autograd.Function):
     """z -> (x, log|dx/dz| + log p(x)) for a latent site whose prior has constant parameters: ONE elementwise
     kernel forward and one backward (`dynode_site_logdensity_f64` / `_vjp_f64`) in place of the ~25 launches the
-    composed transforms and log_prob take each way."""
+    composed transforms and log_prob take each way.  A 1-d `z` is read through its stride (a site is usually a
+    column of the sampler's [chains, D] array), so no gather copy is made either."""
+
+    @staticmethod
+    def _strided(z):
+        if z.dim() == 1 and z.numel() > 0 and z.stride(0) > 0:
+            return z, int(z.stride(0))
+        return z.contiguous(), 1
 
     @staticmethod
     def forward(z, spec):
         import ctypes
 
         from .. import _lib
-        zc = z.contiguous()
-        x, lp = torch.empty_like(zc), torch.empty_like(zc)
+        zc, zs = _FusedSite._strided(z)
+        x = torch.empty(z.shape, dtype=z.dtype, device=z.device)
+        lp = torch.empty(z.shape, dtype=z.dtype, device=z.device)
         sd = _lib.SiteDesc(*spec)
-        _lib.check(_lib.load().dynode_site_logdensity_f64(ctypes.byref(sd), zc.numel(), zc.data_ptr(), x.data_ptr(),
+        _lib.check(_lib.load().dynode_site_logdensity_f64(ctypes.byref(sd), z.numel(), zc.data_ptr(), zs, x.data_ptr(),
                                                           lp.data_ptr(), ctypes.c_void_p(_lib.current_stream_ptr())))
         return x, lp
 
@@ -361,10 +369,11 @@ class _FusedSite(torch.autograd.Function):
 
         from .. import _lib
         (z,) = ctx.saved_tensors
-        zc, gxc, glc = z.contiguous(), gx.contiguous(), glp.contiguous()
-        gz = torch.empty_like(zc)
+        zc, zs = _FusedSite._strided(z)
+        gxc, glc = gx.contiguous(), glp.contiguous()
+        gz = torch.empty(z.shape, dtype=z.dtype, device=z.device)
         sd = _lib.SiteDesc(*ctx.spec)
-        _lib.check(_lib.load().dynode_site_logdensity_vjp_f64(ctypes.byref(sd), zc.numel(), zc.data_ptr(),
+        _lib.check(_lib.load().dynode_site_logdensity_vjp_f64(ctypes.byref(sd), z.numel(), zc.data_ptr(), zs,
                                                               gxc.data_ptr(), glc.data_ptr(), gz.data_ptr(),
                                                               ctypes.c_void_p(_lib.current_stream_ptr())))
         return gz, None

@@ -122,6 +122,11 @@ class condition(Messenger):
             msg["is_observed"] = True
 
 
+def _total(x):
+    """Sum over a site's own axes; a scalar site (0-dim, also under vmap) needs no reduction launch."""
+    return x if isinstance(x, torch.Tensor) and x.dim() == 0 else x.sum()
+
+
 class log_density_handler(Messenger):
     """Evaluate the joint log-density at unconstrained latent values.
 
@@ -144,15 +149,15 @@ class log_density_handler(Messenger):
             else:
                 x, lp = dist.constrain_with_ladj(msg["fn"].support, z)
             msg["value"] = x
-            self.logp = self.logp + lp.sum()
+            self.logp = self.logp + _total(lp)
             self.constrained[msg["name"]] = x
 
     def postprocess_message(self, msg):
         if msg["type"] == "sample":
             if not msg.get("prior_done", False):
-                self.logp = self.logp + msg["fn"].log_prob(msg["value"]).sum()
+                self.logp = self.logp + _total(msg["fn"].log_prob(msg["value"]))
         elif msg["type"] == "factor":
-            self.logp = self.logp + msg["value"].sum()
+            self.logp = self.logp + _total(msg["value"])
 
 
 def _apply_stack(msg: Dict[str, Any]) -> Dict[str, Any]:

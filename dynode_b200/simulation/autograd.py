@@ -296,6 +296,7 @@ class PoissonLoglik(torch.autograd.Function):
         ctx.shapes = (y0.shape, theta.shape)
         ctx.save_for_backward(output[2])
         ctx.mark_non_differentiable(output[1], output[2])
+        ctx.set_materialize_grads(False)  # no zero-filled [B, 4] / [B, P] tensors for stats / grad every backward
 
     @staticmethod
     def backward(ctx, g_lp, _g_stats, _g_grad):
@@ -303,7 +304,7 @@ class PoissonLoglik(torch.autograd.Function):
         (grad,) = ctx.saved_tensors
         y0_shape, th_shape = ctx.shapes
         g_theta = g_y0 = None
-        if grad.numel() > 0:
+        if g_lp is not None and grad.numel() > 0:
             g = g_lp[:, None] * grad
             pw = len(cfg.wrt_cols)
             if pw and ctx.needs_input_grad[1]:

@@ -54,12 +54,12 @@ typedef struct {
   double aff_loc, aff_scale;
 } DynodeSiteDesc;
 
-/* x[i], lp[i] from z[i] */
-int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const double* z, double* x, double* lp,
-                               void* stream);
+/* x[i], lp[i] from z[i * z_stride]  (a site is usually a column of the sampler's [chains][D] position array) */
+int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const double* z, int64_t z_stride, double* x,
+                               double* lp, void* stream);
 /* gz[i] = gx[i] * dx/dz + glp[i] * d lp/dz */
-int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, const double* gx,
-                                   const double* glp, double* gz, void* stream);
+int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, int64_t z_stride,
+                                   const double* gx, const double* glp, double* gz, void* stream);
 
 #ifdef __cplusplus
 }
