@@ -79,7 +79,7 @@ class SeipParams(ctypes.Structure):
 
 NUTS_ADAPT, NUTS_WELFORD, NUTS_SAMPLING, NUTS_END_SLOW, NUTS_END_WARMUP = 1, 2, 4, 8, 16  # DYNODE_NUTS_*
 _NUTS_PTRS = (
-    "z U g eps imm msqrt k nwin active need_tree sched sched_n energy0 "
+    "z U g eps imm msqrt k nwin active need_tree searching fr_dir fr_last sched sched_n energy0 "
     "zL rL gL zR rR gR zP gP r_sum UP weight sum_acc depth nprop turning diverging "
     "s_n s_right s_turn s_div s_z s_r s_g s_zP s_gP s_rsum s_UP s_w s_acc r_ck rs_ck z_new r_half "
     "da_x da_xavg da_gavg da_t da_prox wf_n wf_mean wf_m2 out_z out_accept out_steps out_div out_energy "

@@ -72,7 +72,23 @@ __global__ void __launch_bounds__(128) nuts_pre_kernel(const DynodeNutsState s, 
   const int64_t o = (int64_t)c * D;
   const double* imm = s.imm + o * D;
   const bool act = s.active[c] != 0;
-  if (act && s.need_tree[c]) {
+  const bool probe = act && s.searching[c] != 0;
+  if (probe) {
+    // find_reasonable_step_size: fresh momentum, one leapfrog forward from the current state with eps * 2^dir
+    const int64_t dir = s.fr_dir[c];
+    const double e = s.eps[c] * (dir > 0 ? 2.0 : (dir < 0 ? 0.5 : 1.0));
+    s.eps[c] = e;
+    Vec xi, r0, v;
+    load(xi, rnd_n + o, D);
+    matvec(r0, s.msqrt + o * D, xi, D);
+    matvec(v, imm, r0, D);
+    s.energy0[c] = s.U[c] + 0.5 * dot(r0, v, D);
+    copy(s.s_z + o, s.z + o, D);
+    store(s.s_r + o, r0, D);
+    copy(s.s_g + o, s.g + o, D);
+    s.s_right[c] = 1;
+  }
+  if (act && !probe && s.need_tree[c]) {
     // fresh momentum r ~ N(0, M) and a one-node tree at the current state
     Vec xi, r0, v;
     load(xi, rnd_n + o, D);
@@ -88,7 +104,7 @@ __global__ void __launch_bounds__(128) nuts_pre_kernel(const DynodeNutsState s, 
     s.turning[c] = 0; s.diverging[c] = 0;
     s.need_tree[c] = 0;
   }
-  if (act && s.s_n[c] == 0) {
+  if (act && !probe && s.s_n[c] == 0) {
     // a new doubling: pick a direction and start from that edge of the tree
     const bool right = rnd_u[(int64_t)c * 3 + 0] < 0.5;
     s.s_right[c] = right;
@@ -127,6 +143,27 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   matvec(v, imm, r_new, D);
   double delta = U_new + 0.5 * dot(r_new, v, D) - s.energy0[c];
   if (isnan(delta)) delta = CUDART_INF;
+  if (s.searching[c]) {
+    // ---- a step-size probe (numpyro find_reasonable_step_size: _body_fn / _cond_fn)
+    const double de = U_new + 0.5 * dot(r_new, v, D) - s.energy0[c];  // NaN compares false: direction -1
+    const int64_t dir_used = s.fr_dir[c];
+    const int64_t dir_new = (log(0.8) < -de) ? 1 : -1;
+    const double e = s.eps[c];
+    const bool not_extreme = (e > 2.2250738585072014e-308 || dir_new >= 0) && (e < 1.7976931348623157e308 || dir_new <= 0);
+    const bool go_on = not_extreme && (dir_used == 0 || dir_new == dir_used);
+    s.n_leap[c] += 1;
+    if (go_on) {
+      s.fr_last[c] = dir_used;
+      s.fr_dir[c] = dir_new;
+    } else {  // the direction flipped: keep this step size, restart dual averaging around 10 x it
+      s.searching[c] = 0;
+      s.fr_dir[c] = 0; s.fr_last[c] = 0;
+      s.da_prox[c] = log(10.0 * e);
+      s.da_x[c] = 0.0; s.da_xavg[c] = 0.0; s.da_gavg[c] = 0.0; s.da_t[c] = 0.0;
+      s.need_tree[c] = 1;
+    }
+    return;
+  }
   const double leaf_w = -delta;
   const bool leaf_div = delta > kMaxDeltaEnergy;
   const double leaf_acc = fmin(exp(-delta), 1.0);
@@ -290,11 +327,9 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
       for (int i = 0; i < D; ++i) s.wf_mean[o + i] = 0.0;
       for (int i = 0; i < D * D; ++i) m2[i] = 0.0;
     }
-    if (fl & DYNODE_NUTS_ADAPT) {  // restart dual averaging around 10 x the averaged step size
-      const double e = exp(fmin(fmax(s.da_xavg[c], -700.0), 700.0));
-      s.eps[c] = e;
-      s.da_prox[c] = log(10.0 * e);
-      s.da_x[c] = 0.0; s.da_xavg[c] = 0.0; s.da_gavg[c] = 0.0; s.da_t[c] = 0.0;
+    if (fl & DYNODE_NUTS_ADAPT) {  // step-size search from the current step size (new metric), see the probe branch
+      s.searching[c] = 1;
+      s.fr_dir[c] = 0; s.fr_last[c] = 0;
     }
   }
   if ((fl & DYNODE_NUTS_END_WARMUP) && (fl & DYNODE_NUTS_ADAPT))  // final step size = averaged iterate

@@ -183,6 +183,7 @@ class BatchedNUTS:
         b.msqrt = b.imm.clone()
         b.k, b.nwin = l(C), l(())
         b.active, b.need_tree = bl(C), bl(C)
+        b.searching, b.fr_dir, b.fr_last = bl(C), l(C), l(C)  # find_reasonable_step_size probes
         b.energy0 = f(C)
         for name in ("zL", "rL", "gL", "zR", "rR", "gR", "zP", "gP", "r_sum", "s_z", "s_r", "s_g", "s_zP", "s_gP", "s_rsum"):
             setattr(b, name, f(C, D))
@@ -220,9 +221,21 @@ class BatchedNUTS:
         act = b.active.clone()  # chains that take part in this round
         rnd_n, rnd_u = self._randn(C, D), self._rand(C, 3)  # same draws, same roles as the CUDA round
 
+        # ---- step-size probes (numpyro find_reasonable_step_size): fresh momentum, one leapfrog forward from the
+        # current state with eps * 2^dir
+        probe = act & b.searching
+        r0 = torch.einsum("cij,cj->ci", b.msqrt, rnd_n)
+        fac = torch.where(b.fr_dir > 0, 2.0, 1.0) * torch.where(b.fr_dir < 0, 0.5, 1.0)
+        _put(b.eps, probe, b.eps * fac.to(b.dtype))
+        _put(b.energy0, probe, b.U + self._kinetic(imm, r0))
+        _put(b.s_z, probe, b.z)
+        _put(b.s_r, probe, r0)
+        _put(b.s_g, probe, b.g)
+        _put(b.s_right, probe, True)
+        act = act & ~probe  # what follows is tree building
+
         # ---- chains beginning a transition: fresh momentum r ~ N(0, M), one-node tree at the current state
         nt = act & b.need_tree
-        r0 = torch.einsum("cij,cj->ci", b.msqrt, rnd_n)
         _put(b.energy0, nt, b.U + self._kinetic(imm, r0))
         for dst, src in ((b.zL, b.z), (b.zR, b.z), (b.zP, b.z), (b.gL, b.g), (b.gR, b.g), (b.gP, b.g),
                          (b.rL, r0), (b.rR, r0), (b.r_sum, r0)):
@@ -251,6 +264,21 @@ class BatchedNUTS:
         U_new, g_new = self._eval(z_new)
         r_new = r_half - 0.5 * h * g_new
         delta = U_new + self._kinetic(imm, r_new) - b.energy0
+        # ---- outcome of the probes (_body_fn / _cond_fn of find_reasonable_step_size)
+        dir_new = torch.where(math.log(0.8) < -delta, 1, -1)  # NaN compares false: -1
+        tiny, big = 2.2250738585072014e-308, 1.7976931348623157e308
+        not_extreme = ((eps > tiny) | (dir_new >= 0)) & ((eps < big) | (dir_new <= 0))
+        go_on = probe & not_extreme & ((b.fr_dir == 0) | (dir_new == b.fr_dir))
+        stop = probe & ~go_on
+        _put(b.fr_last, go_on, b.fr_dir)
+        _put(b.fr_dir, go_on, dir_new)
+        _put(b.searching, stop, False)
+        _put(b.fr_dir, stop, 0)
+        _put(b.fr_last, stop, 0)
+        _put(b.da_prox, stop, torch.log(10.0 * eps))
+        for t_ in (b.da_x, b.da_xavg, b.da_gavg, b.da_t):
+            _put(t_, stop, 0.0)
+        _put(b.need_tree, stop, True)
         delta = torch.where(torch.isnan(delta), torch.full_like(delta, math.inf), delta)
         leaf_w = -delta
         leaf_div = delta > MAX_DELTA_ENERGY
@@ -363,12 +391,10 @@ class BatchedNUTS:
             _put(b.wf_n, mm, 0.0)
             _put(b.wf_mean, mm, 0.0)
             _put(b.wf_m2, mm, 0.0)
-            ads = es & ((fl & ADAPT) != 0)
-            e_new = torch.exp(b.da_xavg.clamp(-700.0, 700.0))
-            _put(b.eps, ads, e_new)
-            _put(b.da_prox, ads, torch.log(10.0 * e_new))
-            for t_ in (b.da_x, b.da_xavg, b.da_gavg, b.da_t):
-                _put(t_, ads, 0.0)
+            ads = es & ((fl & ADAPT) != 0)  # step-size search under the new metric, from the current step size
+            _put(b.searching, ads, True)
+            _put(b.fr_dir, ads, 0)
+            _put(b.fr_last, ads, 0)
         ew = fin & ((fl & END_WARMUP) != 0) & ((fl & ADAPT) != 0)
         _put(b.eps, ew, torch.exp(b.da_xavg.clamp(-700.0, 700.0)))
         # store the draw (sampling phase)
@@ -384,7 +410,7 @@ class BatchedNUTS:
         _put(b.k, fin, b.k + 1)
         _put(b.need_tree, fin, True)
         _put(b.active, fin & (b.k >= b.nwin), False)
-        b.n_useful += act.sum()
+        b.n_useful += act.sum() + probe.sum()
         b.any_active.copy_(b.active.any())
 
     # ------------------------------------------------------------------ the same round on the CUDA kernels
@@ -496,6 +522,8 @@ class BatchedNUTS:
         b.need_tree.fill_(True)
         flags, wlen = build_transition_schedule(num_warmup, num_samples, self.adapt_ss, self.adapt_mm)
         self.set_schedule(flags, wlen, num_warmup)
+        if self.adapt_ss:
+            b.searching.fill_(True)  # warmup_adapter.init: find_reasonable_step_size before the first transition
         self._prepare_round_fn()
         if len(flags) > 0:
             self._run_schedule(progress)

@@ -35,7 +35,8 @@ extern "C" {
 #define DYNODE_NUTS_WELFORD 2u    /* the position enters the Welford covariance (slow windows) */
 #define DYNODE_NUTS_SAMPLING 4u   /* the draw is stored at out_*[t - n_warmup] */
 #define DYNODE_NUTS_END_SLOW 8u   /* last transition of a slow window: inverse mass matrix <- shrunk covariance
-                                     (if WELFORD), dual averaging restarted around the averaged step size (if ADAPT) */
+                                     (if WELFORD); step-size search from the current step size, then dual averaging
+                                     restarted around 10 x the result (if ADAPT) -- numpyro _update_at_window_end */
 #define DYNODE_NUTS_END_WARMUP 16u /* last warm-up transition: step size <- averaged iterate (if ADAPT) */
 
 typedef struct {
@@ -51,6 +52,11 @@ typedef struct {
   int64_t *k;           /* [C] transitions completed */
   const int64_t *nwin;  /* [1] transitions each chain has to make in total */
   uint8_t *active, *need_tree; /* [C] */
+  /* numpyro's find_reasonable_step_size (run at the start of warm-up and at the end of every slow window): while
+   * `searching`, a round is one probe -- fresh momentum, ONE leapfrog from the current state with eps * 2^fr_dir --
+   * and the step size keeps doubling / halving until the direction "accept probability above 0.8?" flips. */
+  uint8_t *searching;        /* [C] */
+  int64_t *fr_dir, *fr_last; /* [C] direction of the next probe / of the one before (-1, 0, +1) */
   const uint8_t *sched;   /* [*nwin] DYNODE_NUTS_* flags per transition */
   const double *sched_n;  /* [*nwin] length of the adaptation window the transition belongs to */
   /* whole tree */

@@ -212,9 +212,10 @@ def test_cuda_nuts_round_equals_the_torch_round():
         fl[5] |= N.END_SLOW
         fl[11] |= N.END_WARMUP
         e.set_schedule(fl, [6.0] * 12, 0)
+        e.b.searching.fill_(True)  # step-size search before the first transition (and again after the 6th)
         e._prepare_round_fn()
         engs.append(e)
-    fields = ["z", "U", "g", "eps", "k", "active", "need_tree", "energy0", "zL", "rL", "gL", "zR", "rR", "gR", "zP",
+    fields = ["z", "U", "g", "eps", "k", "active", "need_tree", "searching", "fr_dir", "fr_last", "energy0", "zL", "rL", "gL", "zR", "rR", "gR", "zP",
               "gP", "r_sum", "UP", "weight", "sum_acc", "depth", "nprop", "turning", "diverging", "s_n", "s_right",
               "s_turn", "s_div", "s_z", "s_r", "s_g", "s_zP", "s_gP", "s_rsum", "s_UP", "s_w", "s_acc", "da_x",
               "da_xavg", "da_gavg", "da_t", "da_prox", "wf_n", "wf_mean", "wf_m2", "imm", "msqrt", "out_z"]
