@@ -32,6 +32,9 @@
 
 namespace dynode {
 
+// clamp of the Poisson rate and its logarithm (fused log-likelihood)
+static __constant__ double kLikC[2] = {1e-6, -13.815510557964274};
+
 // Taylor coefficients of sin(d)/d - 1 and cos(d) - 1 in z = d^2, highest power first (sincos_small)
 static __constant__ double kSinTaylor[7] = {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0,
                                             1.0 / 362880.0,         -1.0 / 5040.0,      1.0 / 120.0,
@@ -732,54 +735,62 @@ struct LaneSolver {
             passes([&](int k) -> double { return (k < a.T) ? __ldg(a.save_ts + k) : CUDART_INF; });
           }
         } else {
-          while (true) {
-            const bool pend = ts_next <= tnext;
-            if (!__any_sync(0xffffffffu, pend)) break;
-            if (pend) {
-              const double th = (ts_next - tprev) * inv_h;
-              const double hthw = hw * th, hth2 = (h * th) * th;
-              if constexpr (IS_SAVE) {
-                const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
+          // general path (partial save masks, tangents, the fused log-likelihood): same loop shape as above
+          auto passes = [&](auto next_time) {
+            bool pend = ts_next <= tnext;
+            do {
+              if (pend) {
+                const double th = (ts_next - tprev) * inv_h;
+                const double hthw = hw * th, hth2 = (h * th) * th;
+                if constexpr (IS_SAVE) {
+                  const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                  const D v = dense(e, th, hthw, hth2);
-                  if (off_save[e] >= 0) {
-                    if (wp) a.ys[row + off_save[e]] = v.v;
-                    if constexpr (P > 0) {
+                  for (int e = 0; e < NE; ++e) {
+                    const D v = dense(e, th, hthw, hth2);
+                    if (off_save[e] >= 0) {
+                      if (wp) a.ys[row + off_save[e]] = v.v;
+                      if constexpr (P > 0) {
 #pragma unroll
-                      for (int k = 0; k < P; ++k)
-                        if (p0s + k < a.P_total) a.dys[(row + off_save[e]) * a.P_total + p0s + k] = v.d[k];
+                        for (int k = 0; k < P; ++k)
+                          if (p0s + k < a.P_total) a.dys[(row + off_save[e]) * a.P_total + p0s + k] = v.d[k];
+                      }
                     }
                   }
-                }
-              } else {
-                // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
-                // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
-                // the observed compartment is picked through an index the compiler cannot see: written as
-                // `if (e == obs_comp) v = dense(e)` the unrolled chain was turned into one dynamically
-                // indexed read, which put y, f and Q (55 duals) in local memory
-                D v = make_dual<P>(0.0);
+                } else {
+                  // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
+                  // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
+                  // the observed compartment is picked through an index the compiler cannot see: written as
+                  // `if (e == obs_comp) v = dense(e)` the unrolled chain was turned into one dynamically
+                  // indexed read, which put y, f and Q (55 duals) in local memory
+                  D v = make_dual<P>(0.0);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                  int ee = e;
-                  asm volatile("" : "+r"(ee));
-                  if (ee == a.obs_comp) v = dense(e, th, hthw, hth2);  // warp-uniform branch
-                }
-                if (save_i > 0 && obs_owner) {
-                  D inc = v - obs_prev;
-                  const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
-                  if (inc.v > 1e-6) {
-                    const D lg = dual_log(inc);
-                    lp_acc = lp_acc + (o * lg - inc);
-                  } else {
-                    lp_acc.v += o * log(1e-6) - 1e-6;  // clamped: zero gradient (jnp.maximum)
+                  for (int e = 0; e < NE; ++e) {
+                    int ee = e;
+                    asm volatile("" : "+r"(ee));
+                    if (ee == a.obs_comp) v = dense(e, th, hthw, hth2);  // warp-uniform branch
                   }
+                  if (save_i > 0 && obs_owner) {
+                    D inc = v - obs_prev;
+                    const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
+                    if (inc.v > kLikC[0]) {
+                      const D lg = dual_log(inc);
+                      lp_acc = lp_acc + (o * lg - inc);
+                    } else {
+                      lp_acc.v += fma(o, kLikC[1], -kLikC[0]);  // clamped at 1e-6: zero gradient (jnp.maximum)
+                    }
+                  }
+                  obs_prev = v;
                 }
-                obs_prev = v;
+                ++save_i;
+                ts_next = next_time(save_i);
               }
-              ++save_i;
-              ts_next = save_time(save_i);
-            }
+              pend = ts_next <= tnext;
+            } while (__any_sync(0xffffffffu, pend));
+          };
+          if (a.save_dt > 0.0) {
+            passes([&](int k) -> double { return (k == a.T - 1) ? t1 : fma((double)k, a.save_dt, a.t0); });
+          } else {
+            passes([&](int k) -> double { return (k < a.T) ? __ldg(a.save_ts + k) : CUDART_INF; });
           }
         }
       }
