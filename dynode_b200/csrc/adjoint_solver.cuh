@@ -332,11 +332,11 @@ struct AdjointSolver {
         const double inc = cur - prev;
         const double o = __ldg(a.obs + (int64_t)(s2 - 1) * obs_m + obs_q);
         double wgt = 0.0;
-        if (inc > 1e-6) {
-          lp_part += o * log(inc) - inc;
-          wgt = o / inc - 1.0;
+        if (inc > kLikC[0]) {
+          lp_part += o * log_fast(inc) - inc;
+          wgt = div_fast(o, inc) - 1.0;
         } else {
-          lp_part += o * log(1e-6) - 1e-6;
+          lp_part += fma(o, kLikC[1], -kLikC[0]);
         }
         vs[(int64_t)(s2 - 1) * obs_m] = carry - wgt;
         carry = wgt;
