@@ -311,3 +311,29 @@ def test_row_mask_leaves_masked_trajectories_out():
                 la1, ga1, _, sa1 = engine.poisson_loglik_adjoint(model, y0, prm, contact, opts, ts, obs_comp, obs, B=B)
             assert torch.equal(la1[mask], la0[mask]) and torch.equal(ga1[mask], ga0[mask])
             assert not la1[~mask].any() and not ga1[~mask].any()
+
+
+@pytest.mark.parametrize("name", ["seirs_multi_a2s3", "seirs_seasonal", "sir_age2"])
+def test_tiny_ensembles_and_degenerate_grids(name):
+    """Ensemble sizes around the slot / warp granularity (1, 2, one short of and one past a warp's slots), a
+    save grid that is t0 alone, a two-point grid, two save times 1e-9 apart, and an empty horizon (t1 == t0:
+    nothing to integrate, zero steps) -- all against the oracle."""
+    for B in (1, 2, 4, 6, 31, 33):
+        case = make_case(name, B)
+        ys, _, st = _run_engine(case, 30.0)
+        ref, _, rst = _run_oracle(case, 30.0)
+        assert np.array_equal(st, rst)
+        _assert_close(ys, ref)
+    case = make_case(name, 37)
+    for grid in (np.array([0.0]), np.array([0.0, 12.5]), np.array([0.0, 3.0, 3.0 + 1e-9, 12.5])):
+        ys, _, st = _run_engine(case, 12.5, save_ts=grid)
+        ref, _, rst = _run_oracle(case, 12.5, save_ts=grid)
+        assert ys.shape == ref.shape == (37, len(grid), ref.shape[2])
+        assert np.array_equal(st, rst)
+        _assert_close(ys, ref)
+    # empty horizon: the loop body never runs (tprev < t1 is false from the start), so no save is reached and the
+    # output keeps diffrax's +inf fill -- whatever the restated loop does, kernel and oracle must agree
+    ys, _, st = _run_engine(case, 0.0, save_ts=np.array([0.0]))
+    ref, _, rst = _run_oracle(case, 0.0, save_ts=np.array([0.0]))
+    assert np.array_equal(st, rst) and np.all(st[:, 3] == 0)
+    assert np.array_equal(ys, ref)
