@@ -623,19 +623,33 @@ struct LaneSolver {
       // independent FMAs overlap the latency-bound error-norm / controller chain below.
       // Monomial form of the Tsit5 interpolant (tsit5.cuh kDense):
       //   y(th) = y + (h th w11) f1 + (h th^2) (Q2 + th (Q3 + th Q4)),  Q_m = sum_i w_im f_i
-      D Q[3][NE];
+      // The fused log-likelihood reads ONE compartment: its coefficients, y and f1 are gathered here through the
+      // warp-uniform branch chain (picked through an index the compiler cannot see -- written as a dynamically
+      // indexed read it put y, f and Q in local memory), so that neither the other compartments' 21 FMAs each
+      // (x (1 + P) with tangents) nor the chain itself are paid per step / per save pass.
+      D Q[3][IS_SAVE ? NE : 1];
+      D y_obs = make_dual<P>(0.0), f_obs = make_dual<P>(0.0);
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
+        bool wanted = true;
+        if constexpr (!IS_SAVE) {
+          int ee = e;
+          asm volatile("" : "+r"(ee));
+          wanted = ee == a.obs_comp;
+        }
+        if (wanted) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          D acc = kDense[0][m + 1] * f[0][e];
+          for (int m = 0; m < 3; ++m) {
+            D acc = kDense[0][m + 1] * f[0][e];
 #pragma unroll
-          for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
-          if constexpr (OFFLOAD) {
-            my[(OFF_Q + m * NE + e) * kThreads] = acc.v;
-          } else {
-            Q[m][e] = acc;
+            for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
+            if constexpr (OFFLOAD) {
+              my[(OFF_Q + m * NE + e) * kThreads] = acc.v;
+            } else {
+              Q[m][IS_SAVE ? e : 0] = acc;
+            }
           }
+          if constexpr (!IS_SAVE) { y_obs = y[e]; f_obs = f[0][e]; }
         }
       }
 
@@ -699,7 +713,7 @@ struct LaneSolver {
           if constexpr (OFFLOAD) {
             q0 = Qs[0][e]; q1 = Qs[1][e]; q2 = Qs[2][e];
           } else {
-            q0 = Q[0][e]; q1 = Q[1][e]; q2 = Q[2][e];
+            q0 = Q[0][IS_SAVE ? e : 0]; q1 = Q[1][IS_SAVE ? e : 0]; q2 = Q[2][IS_SAVE ? e : 0];
           }
           D u = dfma(th, q2, q1);
           u = dfma(th, u, q0);
@@ -759,16 +773,9 @@ struct LaneSolver {
                 } else {
                   // Poisson(max(diff(comp), 1e-6)).log_prob(obs) accumulated on the fly
                   // (examples/sir_infer_parameters.py:30-38); lgamma(obs+1) arrives in lp_const.
-                  // the observed compartment is picked through an index the compiler cannot see: written as
-                  // `if (e == obs_comp) v = dense(e)` the unrolled chain was turned into one dynamically
-                  // indexed read, which put y, f and Q (55 duals) in local memory
-                  D v = make_dual<P>(0.0);
-#pragma unroll
-                  for (int e = 0; e < NE; ++e) {
-                    int ee = e;
-                    asm volatile("" : "+r"(ee));
-                    if (ee == a.obs_comp) v = dense(e, th, hthw, hth2);  // warp-uniform branch
-                  }
+                  D u = dfma(th, Q[2][0], Q[1][0]);
+                  u = dfma(th, u, Q[0][0]);
+                  const D v = dfma(hth2, u, dfma(hthw, f_obs, y_obs));  // the observed compartment at ts_next
                   if (save_i > 0 && obs_owner) {
                     D inc = v - obs_prev;
                     const double o = __ldg(a.obs + (int64_t)(save_i - 1) * obs_m + obs_q);
