@@ -71,7 +71,9 @@ struct LaneSolver {
 #endif
   static constexpr bool PERSIST = TPW >= DYN_PERSIST_MIN_TPW;
   // refill as soon as this many slots are idle (masked re-initialisation costs ~1.5 steps)
-  static constexpr int REFILL = TPW >= 8 ? TPW / 8 : DYN_REFILL_SMALL;
+  // (measured on B200, DYNODE_REFILL sweep: a quarter of the slots beats an eighth by 5 % on the 16-slot fused
+  // log-likelihood of C2 -- 22-step trajectories, so refills are frequent -- and by 2 % on the 32-slot C3 solve)
+  static constexpr int REFILL = TPW >= 8 ? TPW / 4 : DYN_REFILL_SMALL;
   static_assert(L >= 1 && L <= 32, "a trajectory must fit one warp");
   using D = Dual<P>;
   // Shared-memory offload: the dense-output coefficients Q (3*NE doubles, written once per step, read only
@@ -348,7 +350,7 @@ struct LaneSolver {
         const unsigned idle_heads = __ballot_sync(0xffffffffu, head && !active);
         const int n_idle = __popc(idle_heads);
         const bool any_active = __any_sync(0xffffffffu, active);
-        if (next < chunk_end && n_idle > 0 && (n_idle >= REFILL || !any_active)) {
+        if (next < chunk_end && n_idle > 0 && (n_idle >= a.refill_min || !any_active)) {
           // candidates: the next 32 work items of the chunk minus the rows the caller masked out (a.only);
           // the idle slot of rank r takes the (r+1)-th candidate
           const int64_t ci = next + lane;
@@ -892,6 +894,9 @@ cudaError_t launch_lane_solver(const SolveArgs& a_in, cudaStream_t stream) {
   a.chunk = (Bv + warps - 1) / warps;
   warps = (Bv + a.chunk - 1) / a.chunk;
   const int64_t grid = (warps + wpc - 1) / wpc;
+  // tuning knob: DYNODE_REFILL=<n> overrides the refill threshold of the persistent-slot instances
+  static const int env_refill = [] { const char* v = getenv("DYNODE_REFILL"); return v ? atoi(v) : 0; }();
+  a.refill_min = env_refill > 0 ? (env_refill < LS::TPW ? env_refill : LS::TPW) : LS::REFILL;
   // tuning knob: DYNODE_DEBUG_SMEM=<bytes> of unused dynamic shared memory per CTA lowers the number of
   // resident CTAs (occupancy experiments, profiles/r1/occupancy.md); 0 in production
   static const int debug_smem = [] { const char* v = getenv("DYNODE_DEBUG_SMEM"); return v ? atoi(v) : 0; }();

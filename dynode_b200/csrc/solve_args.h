@@ -61,6 +61,7 @@ struct SolveArgs {
   double* lp;    // [B]
   double* grad;  // [B][P_total]
   const uint8_t* only;  // [B] or NULL: row mask (DynodeSolverDesc.only)
+  int32_t refill_min;   // persistent-slot instances: refill once this many slots of a warp are idle (launcher)
 };
 
 // Discrete-adjoint log-likelihood kernel (adjoint_solver.cuh)
