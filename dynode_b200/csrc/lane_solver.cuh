@@ -416,32 +416,54 @@ struct LaneSolver {
           if (a.const_dt > 0.0) {
             tn = a.t0 + a.const_dt;  // ConstantStepSize (odes.py:115-118)
           } else {
-            // Hairer-Wanner initial step (PIDController._select_initial_step)
+            // Hairer-Wanner initial step (PIDController._select_initial_step).  It runs masked
+            // inside the step loop of the persistent-slot instances, for the whole warp at every refill, so it is
+            // kept short: one reciprocal per scale instead of three IEEE divisions, quotients by reciprocal +
+            // correction, and the probe RHS on the primal alone (the result is under stop_gradient).
             double p0 = 0.0, p1 = 0.0;
-            double scale[NE];
+            double inv_scale[NE];
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
-              scale[e] = fma(fabs(yn[e].v), rtol, atol);
+              inv_scale[e] = rcp_fast(fma(fabs(yn[e].v), rtol, atol));
               const double w = (e == 0 && !lead) ? 0.0 : 1.0;
-              p0 += w * sq(yn[e].v / scale[e]);
-              p1 += w * sq(fn[e].v / scale[e]);
+              p0 += w * sq(yn[e].v * inv_scale[e]);
+              p1 += w * sq(fn[e].v * inv_scale[e]);
             }
             const double d0 = sqrt(traj_sum(p0, c) * inv_n);
             const double d1 = sqrt(traj_sum(p1, c) * inv_n);
             const bool small = (d0 < 1e-5) || (d1 < 1e-5);
-            const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
+            const double h0 = small ? 1e-6 : 0.01 * div_fast(d0, small ? 1.0 : d1);
+            double df[NE];  // f(t0 + h0, y0 + h0 f0) - f0, primal
+            if constexpr (P == 0) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, fn[e], yn[e]);
-            rhs(a.t0 + h0, ys, f1, c, Kl, pn, invN0);
+              for (int e = 0; e < NE; ++e) ys[e] = dfma(h0, fn[e], yn[e]);
+              rhs(a.t0 + h0, ys, f1, c, Kl, pn, invN0);
+#pragma unroll
+              for (int e = 0; e < NE; ++e) df[e] = f1[e].v - fn[e].v;
+            } else {
+              using L0 = LaneSolver<FLOW, FLAGS, G, S, 0, MODE>;
+              typename L0::Geo c0;
+              c0.base = c.base; c0.sbase = c.sbase; c0.g = c.g; c0.s = c.s;
+              typename L0::Prm q0;
+              q0.beta.v = pn.beta.v; q0.gamma.v = pn.gamma.v; q0.sigma.v = pn.sigma.v; q0.omega.v = pn.omega.v;
+              q0.amp.v = pn.amp.v; q0.phase.v = pn.phase.v; q0.period = pn.period;
+              Dual<0> yv[NE], fv[NE], iN;
+              iN.v = invN0.v;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) yv[e].v = fma(h0, fn[e].v, yn[e].v);
+              L0::rhs(a.t0 + h0, yv, fv, c0, Kl, q0, iN);
+#pragma unroll
+              for (int e = 0; e < NE; ++e) df[e] = fv[e].v - fn[e].v;
+            }
             double p2 = 0.0;
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
               const double w = (e == 0 && !lead) ? 0.0 : 1.0;
-              p2 += w * sq((f1[e].v - fn[e].v) / scale[e]);
+              p2 += w * sq(df[e] * inv_scale[e]);
             }
-            const double d2 = sqrt(traj_sum(p2, c) * inv_n) / h0;
+            const double d2 = div_fast(sqrt(traj_sum(p2, c) * inv_n), h0);
             const double md = fmax(d1, d2);
-            const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
+            const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(div_fast(0.01, md), 0.2);
             tn = a.t0 + fmin(100.0 * h0, h1);
           }
           if (take) {
