@@ -36,7 +36,7 @@ typedef cudaError_t (*AdjointFn)(const AdjointArgs&, cudaStream_t);
 
 struct Instance {
   int flow, flags, g, s, chunk;
-  LaunchFn save0, saveP, lik0, likP, saveJ;
+  LaunchFn save0, saveP, lik0, likP, saveJ, saveJP, likJ0, likJP;
   AdjointFn adjoint;
 };
 
@@ -47,6 +47,9 @@ struct Instance {
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK>,                               \
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK>,             \
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_SAVE_JUMPS>,                           \
+   &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_SAVE_JUMPS>,         \
+   &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK_JUMPS>,                         \
+   &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK_JUMPS>,       \
    &launch_adjoint_solver<FLOW, FLAGS, G, S>},
 static const Instance kInstances[] = {
 #include "instances.def"
@@ -130,12 +133,11 @@ static int run_passes(const Instance* inst, SolveArgs& a, int32_t n_wrt, const i
                       cudaStream_t stream) {
   if (a.B == 0) return 0;
   cudaError_t e;
-  if (a.n_jump > 0 && (n_wrt > 0 || loglik))
-    return fail("unsupported: discontinuity points together with sensitivities / the fused log-likelihood");
+  const bool jumps = a.n_jump > 0;
   if (n_wrt == 0) {
     a.P_total = 0;
     a.n_pass = 1;
-    e = (loglik ? inst->lik0 : (a.n_jump > 0 ? inst->saveJ : inst->save0))(a, stream);
+    e = (loglik ? (jumps ? inst->likJ0 : inst->lik0) : (jumps ? inst->saveJ : inst->save0))(a, stream);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
   }
@@ -146,7 +148,7 @@ static int run_passes(const Instance* inst, SolveArgs& a, int32_t n_wrt, const i
   a.n_pass = (n_wrt + inst->chunk - 1) / inst->chunk;
   for (int k = 0; k < kMaxWrt; ++k) a.wrt[k] = k < n_wrt ? wrt[k] : -1;
   a.write_primal = 1;
-  e = (loglik ? inst->likP : inst->saveP)(a, stream);
+  e = (loglik ? (jumps ? inst->likJP : inst->likP) : (jumps ? inst->saveJP : inst->saveP))(a, stream);
   if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
 }

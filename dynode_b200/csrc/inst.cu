@@ -17,6 +17,9 @@ using I = Inst<DYN_INST>;
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_SAVE>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_SAVE>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_SAVE_JUMPS>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_SAVE_JUMPS>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_LOGLIK_JUMPS>(const SolveArgs&, cudaStream_t);
+template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_LOGLIK_JUMPS>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
 

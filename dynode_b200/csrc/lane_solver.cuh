@@ -61,8 +61,8 @@ struct LaneSolver {
   // Persistent slots pay off only where many slots share a warp (measured on B200, profiles/
   // r1_tuning.md: +11% for 32 slots, -8% for the 5-slot multi-strain case whose step counts are
   // tight); otherwise a warp integrates one generation of TPW trajectories.
-  static constexpr bool JUMPS = MODE == MODE_SAVE_JUMPS;
-  static constexpr bool IS_SAVE = MODE != MODE_LOGLIK;
+  static constexpr bool JUMPS = MODE == MODE_SAVE_JUMPS || MODE == MODE_LOGLIK_JUMPS;
+  static constexpr bool IS_SAVE = MODE == MODE_SAVE || MODE == MODE_SAVE_JUMPS;
 #ifndef DYN_PERSIST_MIN_TPW
 #define DYN_PERSIST_MIN_TPW 8
 #endif
@@ -82,6 +82,9 @@ struct LaneSolver {
   // SEIRS lanes (seasonal C3 workload), -3 % for the 5-element SEIRS+C lane even though it then fits 16
   // instead of 12 warps per SM -- so it is on for FLOW_SEIRS only (DYN_SMEM_OFFLOAD: -1 auto, 0 off, 1 all).
   static constexpr bool OFFLOAD = P == 0 && (DYN_SMEM_OFFLOAD == 1 || (DYN_SMEM_OFFLOAD < 0 && FLOW == DYNODE_FLOW_SEIRS));
+  // the dense-output coefficients are offloaded only where whole rows are saved: the fused log-likelihood keeps the
+  // observed compartment's three coefficients in registers
+  static constexpr bool OFFLOAD_Q = OFFLOAD && IS_SAVE;
   static constexpr int OFF_Q = 0, OFF_PRM = 3 * NE, OFF_K = OFF_PRM + 4, OFF_SEAS = OFF_K + G;
   static constexpr int NOFF = OFFLOAD ? OFF_SEAS + (SEASONAL ? 3 : 0) : 1;
   // volatile: the rates are loop-invariant, and the whole point is that they are NOT kept in registers
@@ -667,7 +670,7 @@ struct LaneSolver {
             D acc = kDense[0][m + 1] * f[0][e];
 #pragma unroll
             for (int i = 1; i < 7; ++i) acc = dfma(kDense[i][m + 1], f[i][e], acc);
-            if constexpr (OFFLOAD) {
+            if constexpr (OFFLOAD_Q) {
               my[(OFF_Q + m * NE + e) * kThreads] = acc.v;
             } else {
               Q[m][IS_SAVE ? e : 0] = acc;
@@ -726,7 +729,7 @@ struct LaneSolver {
         // dead by now); read inside the save loop it was re-fetched after every global store (12 LDS per pass,
         // 9 passes per step for the 32-slot warps: profiles/r1/ncu_full_c3_lane_solver.md)
         D Qs[3][NE];
-        if constexpr (OFFLOAD) {
+        if constexpr (OFFLOAD_Q) {
 #pragma unroll
           for (int m = 0; m < 3; ++m)
 #pragma unroll
@@ -734,7 +737,7 @@ struct LaneSolver {
         }
         auto dense = [&](int e, double th, double hthw, double hth2) -> D {
           D q0, q1, q2;
-          if constexpr (OFFLOAD) {
+          if constexpr (OFFLOAD_Q) {
             q0 = Qs[0][e]; q1 = Qs[1][e]; q2 = Qs[2][e];
           } else {
             q0 = Q[0][IS_SAVE ? e : 0]; q1 = Q[1][IS_SAVE ? e : 0]; q2 = Q[2][IS_SAVE ? e : 0];

@@ -18,7 +18,8 @@ constexpr int tangent_chunk(int flow) { return flow == DYNODE_FLOW_SIR ? 2 : 1; 
 constexpr int kThreads = DYN_THREADS;  // warps per CTA = kThreads / 32
 constexpr int MODE_SAVE = 0;        // write saved trajectories (+ tangents)
 constexpr int MODE_LOGLIK = 1;      // fused Poisson-incidence log-likelihood (+ gradient)
-constexpr int MODE_SAVE_JUMPS = 2;  // MODE_SAVE with ClipStepSizeController(jump_ts) step clipping (P == 0)
+constexpr int MODE_SAVE_JUMPS = 2;  // MODE_SAVE with ClipStepSizeController(jump_ts) step clipping
+constexpr int MODE_LOGLIK_JUMPS = 3;  // MODE_LOGLIK with it
 constexpr int kMaxJumps = 32;
 
 #ifndef DYN_SMEM_OFFLOAD

@@ -64,7 +64,9 @@ typedef struct {
    * save times arithmetically instead of loading them.  0 = read save_ts. */
   double save_dt;
   /* SolverParams.discontinuity_points (odes.py:120-131: ClipStepSizeController(jump_ts)): n_jump <= 32
-   * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none. */
+   * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none.
+   * Honoured by dynode_solve_f64, dynode_solve_sens_f64 and dynode_poisson_loglik_grad_f64 (tangents ride the
+   * clipped step sequence); dynode_poisson_loglik_adjoint_f64 rejects it. */
   const double* jump_ts;
   int32_t n_jump;
   /* Optional row mask: DEVICE [B] bytes.  When non-NULL, only trajectories with only[b] != 0 are integrated;

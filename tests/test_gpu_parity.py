@@ -137,6 +137,9 @@ def test_sensitivities_with_initial_state_tangents():
     ("sir_age2", 2, [0, 16], [0, 1]),            # NUTS config: Poisson on diff(R), d/d(beta, gamma)
     ("seirs_multi_a2s3", 4, [0, 1, 2, 16, 17, 18], [0, 1, 2, 3, 4, 5]),  # Poisson on diff(C)
     ("sir_age2", 0, [], []),
+    ("seirs_seasonal", 3, [], []),   # P == 0 on a shared-memory-offload instance (coefficients stay in registers)
+    ("seirs_1bin", 2, [], []),
+    ("seirs_seasonal", 1, [0, 16, 64], [0, 1, 4]),
 ])
 def test_fused_poisson_loglik_and_gradient(name, obs_comp, wrt_e, wrt_o):
     import torch
@@ -337,3 +340,48 @@ def test_tiny_ensembles_and_degenerate_grids(name):
     ref, _, rst = _run_oracle(case, 0.0, save_ts=np.array([0.0]))
     assert np.array_equal(st, rst) and np.all(st[:, 3] == 0)
     assert np.array_equal(ys, ref)
+
+
+@pytest.mark.parametrize("name", ["sir_age2", "seirs_seasonal", "seirs_multi_a2s3"])
+def test_discontinuity_points_with_sensitivities_and_loglik(name):
+    """jump_ts together with forward tangents (dynode_solve_sens_f64) and with the fused Poisson log-likelihood +
+    gradient: the tangents ride the clipped step sequence like any other (the clip times are constants), so both
+    must agree with the oracle run with the same jump_ts -- identical step counts included."""
+    import torch
+    from scipy.special import gammaln
+    from dynode_b200.engine import SolverOptions, poisson_loglik_grad
+    from oracle import oracle as orc
+    B = 41
+    case = make_case(name, B)
+    t1 = 100
+    jumps = (20.0, 55.5, 80.0)
+    wrt_e, wrt_o = WRT[name]
+    ys, dys, st = _run_engine(case, t1, wrt=wrt_e, opts=dict(jump_ts=jumps))
+    ref, dref, rst = _run_oracle(case, t1, wrt=wrt_o, jump_ts=jumps)
+    assert np.array_equal(st, rst) and np.all(st[:, 0] == 0)
+    _assert_close(ys, ref)
+    for p in range(len(wrt_e)):
+        _assert_close(dys[..., p], dref[..., p], rtol=1e-8, atol_scale=1e-11)
+    _, _, st_plain = _run_engine(case, t1, wrt=wrt_e)
+    assert not np.array_equal(st, st_plain)  # the jumps did clip steps
+    # fused log-likelihood on the last compartment
+    model = case["model"]
+    obs_comp = model.n_compartments - 1
+    sizes = model.compartment_sizes()
+    lo = sum(sizes[:obs_comp])
+    idx = list(range(lo, lo + sizes[obs_comp]))
+    fam, dims, theta, shared = case["oracle"]
+    ys_o, dys_o, rst2 = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, save_idx=idx, wrt=wrt_o, jump_ts=jumps)
+    obs = np.abs(np.diff(ys_o[0], axis=0)) + 0.05
+    lp_const = float(-gammaln(obs + 1).sum())
+    ts = np.linspace(0.0, t1, t1 + 1)
+    for w_e in (wrt_e, []):
+        lp, grad, st2 = poisson_loglik_grad(model, case["y0"], case["params"], case["contact"],
+                                            SolverOptions(t1=t1, jump_ts=jumps), ts, obs_comp, obs, lp_const, wrt=w_e)
+        torch.cuda.synchronize()
+        lp_ref, g_ref = orc.poisson_incidence(ys_o, dys_o, obs)
+        assert np.array_equal(st2.cpu().numpy(), rst2)
+        assert np.allclose(lp.cpu().numpy(), lp_ref, rtol=1e-10, atol=0)
+        if w_e:
+            g = grad.cpu().numpy()
+            assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
