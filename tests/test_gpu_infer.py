@@ -35,6 +35,30 @@ def test_simulate_is_differentiable_and_matches_oracle_tangents():
     assert np.allclose(sol.ys[2].detach().cpu().numpy(), ys[0][:, 4:6], rtol=1e-9, atol=1e-9)
 
 
+def test_simulate_with_discontinuity_points_is_differentiable():
+    """SolverParams.discontinuity_points (reference odes.py:120-131) under autograd: the gradient through
+    `simulate` equals the oracle's tangents of the same clipped step sequence."""
+    from dynode_b200.config import SolverParams
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate
+    from oracle import oracle as orc
+    from tests.cases import make_case
+    case = make_case("sir_age2", 1)
+    beta = torch.tensor(case["params"]["beta"][0], dtype=torch.float64, device=_dev(), requires_grad=True)
+    gamma = torch.tensor(case["params"]["gamma"][0], dtype=torch.float64, device=_dev(), requires_grad=True)
+    y0 = torch.tensor(case["y0"], dtype=torch.float64, device=_dev())
+    p = ex.AgeSIR_ODEParams(beta=beta, gamma=gamma, contact_matrix=torch.tensor(case["contact"], device=_dev()))
+    jumps = [30.0, 61.5]
+    sol = simulate(ex.sir_age_ode, 100, (y0[0:2], y0[2:4], y0[4:6]), p, SolverParams(discontinuity_points=jumps))
+    w = torch.linspace(0.5, 1.5, 101 * 2, dtype=torch.float64, device=_dev()).reshape(101, 2)
+    gb, gg = torch.autograd.grad((w * sol.ys[2]).sum(), (beta, gamma))
+    fam, dims, theta, shared = case["oracle"]
+    ys, dys, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=100, wrt=[0, 1], jump_ts=jumps)
+    ref = (w.cpu().numpy()[:, :, None] * dys[0][:, 4:6, :]).sum((0, 1))
+    assert np.allclose([float(gb), float(gg)], ref, rtol=1e-8)
+    assert int(sol.stats["num_accepted_steps"]) == int(st[0, 1])
+
+
 def test_gradient_with_respect_to_initial_state():
     from dynode_b200.config import SolverParams
     from dynode_b200.examples import rhs as ex
