@@ -385,3 +385,34 @@ def test_discontinuity_points_with_sensitivities_and_loglik(name):
         if w_e:
             g = grad.cpu().numpy()
             assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
+
+
+def test_fused_loglik_on_a_nonuniform_grid():
+    """The fused log-likelihood with observation times that are not build_saveat's uniform grid (the kernel then
+    loads the save times instead of generating them)."""
+    import torch
+    from scipy.special import gammaln
+    from dynode_b200.engine import SolverOptions, poisson_loglik_grad
+    from oracle import oracle as orc
+    B = 29
+    for name, obs_comp, wrt_e, wrt_o in (("seirs_multi_a2s3", 4, [0, 17], [0, 4]), ("seirs_seasonal", 3, [], [])):
+        case = make_case(name, B)
+        t1 = 90.0
+        ts = np.array([0.0, 0.5, 1.75, 4.0, 4.0 + 1e-7, 11.0, 30.0, 30.5, 62.0, 89.0, 90.0])
+        model = case["model"]
+        sizes = model.compartment_sizes()
+        lo = sum(sizes[:obs_comp])
+        idx = list(range(lo, lo + sizes[obs_comp]))
+        fam, dims, theta, shared = case["oracle"]
+        ys_o, dys_o, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, save_ts=ts, save_idx=idx, wrt=wrt_o)
+        obs = np.abs(np.diff(ys_o[0], axis=0)) + 0.05
+        lp_const = float(-gammaln(obs + 1).sum())
+        lp, grad, st = poisson_loglik_grad(model, case["y0"], case["params"], case["contact"], SolverOptions(t1=t1),
+                                           ts, obs_comp, obs, lp_const, wrt=wrt_e)
+        torch.cuda.synchronize()
+        lp_ref, g_ref = orc.poisson_incidence(ys_o, dys_o, obs)
+        assert np.array_equal(st.cpu().numpy(), rst)
+        assert np.allclose(lp.cpu().numpy(), lp_ref, rtol=1e-9, atol=0)
+        if wrt_e:
+            g = grad.cpu().numpy()
+            assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
