@@ -756,7 +756,11 @@ struct LaneSolver {
             bool pend = ts_next <= tnext;
             do {
               if (pend) {
+                // the time of the save after this one decides whether the loop goes on: it is the loop-carried
+                // chain (constant loads, I2F, FMA, compare, vote -- the top stall site of the r1 captures), so it is
+                // issued first and overlaps the dense evaluation
                 const double th = (ts_next - tprev) * inv_h;
+                ts_next = next_time(save_i + 1);
                 const double hthw = hw * th, hth2 = (h * th) * th;
                 const D v0 = dense(0, th, hthw, hth2);
                 if (lead) *row_ptr(out_s, save_i) = v0.v;
@@ -764,7 +768,6 @@ struct LaneSolver {
 #pragma unroll
                 for (int e = 1; e < NE; ++e) pc[(e - 1) * G * S] = dense(e, th, hthw, hth2).v;
                 ++save_i;
-                ts_next = next_time(save_i);
               }
               pend = ts_next <= tnext;
             } while (__any_sync(0xffffffffu, pend));
@@ -782,6 +785,7 @@ struct LaneSolver {
             do {
               if (pend) {
                 const double th = (ts_next - tprev) * inv_h;
+                ts_next = next_time(save_i + 1);  // issued early, see the fast path
                 const double hthw = hw * th, hth2 = (h * th) * th;
                 if constexpr (IS_SAVE) {
                   const int64_t row = (traj * a.T + save_i) * (int64_t)n_saved;
@@ -816,7 +820,6 @@ struct LaneSolver {
                   obs_prev = v;
                 }
                 ++save_i;
-                ts_next = next_time(save_i);
               }
               pend = ts_next <= tnext;
             } while (__any_sync(0xffffffffu, pend));
