@@ -136,9 +136,15 @@ def uniform_save_dt(save_ts, t0: float, t1: float) -> float:
 _GRID_CACHE: Dict[tuple, object] = {}
 
 
+def _row_strided(t) -> bool:
+    """[B, row] view whose rows are contiguous but lie batch_stride apart (a column block of a wider array):
+    DynodeArray describes it as it is, no gather copy needed."""
+    return t.dim() == 2 and t.shape[0] > 1 and t.stride(1) == 1 and t.stride(0) > t.shape[1]
+
+
 def _dev_f64(torch, x, device):
     t = torch.as_tensor(x, dtype=torch.float64, device=device)
-    return t.contiguous()
+    return t if _row_strided(t) else t.contiguous()
 
 
 def _as_array(t, row: int, B: int, name: str) -> _lib.Array:
@@ -148,7 +154,7 @@ def _as_array(t, row: int, B: int, name: str) -> _lib.Array:
     if t.numel() == row:
         return _lib.Array(t.data_ptr(), 0)
     if t.numel() == B * row:
-        return _lib.Array(t.data_ptr(), row)
+        return _lib.Array(t.data_ptr(), t.stride(0) if _row_strided(t) and t.shape == (B, row) else row)
     raise ValueError(f"{name}: expected {row} or {B}x{row} values, got shape {tuple(t.shape)}")
 
 
@@ -258,15 +264,17 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
     if obs_t.numel() != (b.T - 1) * m:
         raise ValueError(f"obs must be [{b.T - 1}][{m}], got {tuple(obs_t.shape)}")
     P = len(wrt)
-    lp = torch.empty((b.B,), dtype=torch.float64, device=b.dev)
-    grad = torch.empty((b.B, max(P, 1)), dtype=torch.float64, device=b.dev)
-    stats = torch.empty((b.B, 4), dtype=torch.int32, device=b.dev)
+    md, sd = model.desc(), opts.desc(b.save_dt)
+    # lp, grad and stats are views of ONE buffer: under a row mask (rows left out keep zeros) that is one fill
+    # instead of three
+    Pc = max(P, 1)
+    buf = (torch.zeros if _row_mask(sd, b.B) else torch.empty)((b.B * (Pc + 3),), dtype=torch.float64, device=b.dev)
+    lp = buf[:b.B]
+    grad = buf[b.B:b.B * (1 + Pc)].view(b.B, Pc)
+    stats = buf[b.B * (1 + Pc):].view(torch.int32).view(b.B, 4)
     d0 = None
     if dy0 is not None:
         d0 = _dev_f64(torch, dy0, b.dev)
-    md, sd = model.desc(), opts.desc(b.save_dt)
-    if _row_mask(sd, b.B):
-        lp.zero_(); grad.zero_(); stats.zero_()
     _lib.check(_lib.load().dynode_poisson_loglik_grad_f64(
         ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(),
         b.T, int(obs_comp), obs_t.data_ptr(), float(lp_const), P, _lib.i32_array(list(wrt)),

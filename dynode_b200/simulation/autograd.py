@@ -98,7 +98,7 @@ class SolvePayload:
 def _kernel_params(cfg: SolveConfig, theta: torch.Tensor):
     p = {}
     for kind, first, width in cfg.layout:
-        p[kind] = theta[:, first:first + width].contiguous()
+        p[kind] = theta[:, first:first + width]  # a column block: passed as a strided DynodeArray, no copy
     if cfg.payload.period is not None:
         p["season_period"] = cfg.payload.period
     return p
