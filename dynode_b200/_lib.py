@@ -83,7 +83,7 @@ _NUTS_PTRS = (
     "zL rL gL zR rR gR zP gP r_sum UP weight sum_acc depth nprop turning diverging "
     "s_n s_right s_turn s_div s_z s_r s_g s_zP s_gP s_rsum s_UP s_w s_acc r_ck rs_ck z_new r_half "
     "da_x da_xavg da_gavg da_t da_prox wf_n wf_mean wf_m2 out_z out_accept out_steps out_div out_energy "
-    "out_depth last_accept last_steps n_leap").split()
+    "out_depth last_accept last_steps n_leap any_active").split()
 
 
 class NutsState(ctypes.Structure):

@@ -67,6 +67,7 @@ __device__ __forceinline__ bool is_turning(const double* imm, const Vec& r_left,
 __global__ void __launch_bounds__(128) nuts_pre_kernel(const DynodeNutsState s, const double* __restrict__ rnd_n,
                                                        const double* __restrict__ rnd_u) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) *s.any_active = 0;  // _post of this round sets it again if a chain is still running
   if (c >= s.C) return;
   const int D = s.D;
   const int64_t o = (int64_t)c * D;
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   const double* imm = s.imm + o * D;
   const bool act = s.active[c] != 0;
   if (!act) return;  // nothing of an idle chain changes in a round
+  // "some chain is still running": set by every chain that entered this round active (one round late for the last
+  // chain to finish, which costs the driver at most one extra host check)
+  *s.any_active = 1;
 
   // ---- second half of the leapfrog; a non-finite potential or gradient makes a divergent leaf
   double U_new = U_in[c];

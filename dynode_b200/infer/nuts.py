@@ -444,8 +444,7 @@ class BatchedNUTS:
             U_new, g_new = self.pg(b.z_new)
         U_new, g_new = U_new.contiguous(), g_new.contiguous()
         self._lib.check(L.dynode_nuts_round_post(ctypes.byref(self._st), U_new.data_ptr(), g_new.data_ptr(),
-                                                 rnd_u.data_ptr(), stream))
-        b.any_active.copy_(b.active.any())
+                                                 rnd_u.data_ptr(), stream))  # also maintains b.any_active
 
     # ------------------------------------------------------------------ graph capture
     def _prepare_round_fn(self):

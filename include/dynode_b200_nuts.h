@@ -81,6 +81,7 @@ typedef struct {
   double *out_accept, *out_steps, *out_div, *out_energy, *out_depth; /* [C][N] */
   double *last_accept, *last_steps; /* [C] */
   int64_t *n_leap;                  /* [C] leapfrogs that belonged to a tree */
+  uint8_t *any_active;              /* [1] cleared by _pre, set by _post when a chain is still running afterwards */
 } DynodeNutsState;
 
 /* rnd_n [C][D] standard normals (fresh momentum), rnd_u [C][3] uniforms (direction, subtree transition,
