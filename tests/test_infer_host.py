@@ -194,3 +194,61 @@ def test_potential_matches_a_hand_written_density():
         dz[:, j] = eps
         num = (md.potential(z + dz) - md.potential(z - dz)) / (2 * eps)
         assert torch.allclose(g[:, j], num, rtol=1e-6, atol=1e-8)
+
+
+def test_transition_schedule_flags_follow_the_adaptation_windows():
+    """build_transition_schedule: what each chain does after its t-th transition (numpyro warmup_adapter: dual
+    averaging throughout warm-up, Welford in the slow windows, mass-matrix update + step-size search at their
+    ends, averaged step size after the last warm-up transition, draws stored afterwards)."""
+    from dynode_b200.infer import nuts as N
+    for nw, ns in ((150, 50), (100, 10), (10, 5), (0, 7), (1000, 3)):
+        fl, wl = N.build_transition_schedule(nw, ns, True, True)
+        assert len(fl) == len(wl) == nw + ns
+        wins = N.build_adaptation_schedule(nw) if nw > 0 else []
+        assert all(f & N.ADAPT for f in fl[:nw]) and not any(f & N.ADAPT for f in fl[nw:])
+        assert all(f == N.SAMPLING for f in fl[nw:])
+        for w, (a, e) in enumerate(wins):
+            middle = 0 < w < len(wins) - 1
+            assert all(bool(f & N.WELFORD) == middle for f in fl[a:e + 1])
+            assert bool(fl[e] & N.END_SLOW) == middle
+            assert not any(f & N.END_SLOW for f in fl[a:e])
+            assert all(x == float(e - a + 1) for x in wl[a:e + 1])
+        if nw > 0:
+            assert fl[nw - 1] & N.END_WARMUP and sum(1 for f in fl if f & N.END_WARMUP) == 1
+        fl2, _ = N.build_transition_schedule(nw, ns, False, False)
+        assert not any(f & (N.ADAPT | N.WELFORD) for f in fl2)
+
+
+def test_fused_site_specs_reproduce_log_prob():
+    """The (family, p0, p1, c, affine) description handed to dynode_site_logdensity_f64 restates each prior's
+    log_prob: evaluated here with numpy from the spec alone (the kernel's formulas, include/dynode_b200_ppl.h)."""
+    import numpy as np
+    from dynode_b200.infer import distributions as D
+
+    def from_spec(spec, x):
+        fam, p0, p1, c, loc, sc = spec
+        u = (x - loc) / sc
+        xlogy = lambda a, y: np.where(a == 0.0, 0.0, a * np.log(y))
+        f = {D.FAM_NORMAL: lambda: -0.5 * ((u - p0) / p1) ** 2, D.FAM_UNIFORM: lambda: np.zeros_like(u),
+             D.FAM_BETA: lambda: xlogy(p0 - 1.0, u) + xlogy(p1 - 1.0, 1.0 - u),
+             D.FAM_GAMMA: lambda: (p0 - 1.0) * np.log(u) - p1 * u,
+             D.FAM_LOGNORMAL: lambda: -0.5 * ((np.log(u) - p0) / p1) ** 2 - np.log(u),
+             D.FAM_HALFNORMAL: lambda: -0.5 * (u / p0) ** 2, D.FAM_EXPONENTIAL: lambda: -p0 * u}[fam]()
+        return f + c
+
+    rng = np.random.default_rng(1)
+    cases = [(D.Normal(0.3, 1.7), rng.normal(size=50)), (D.TruncatedNormal(loc=8, scale=2, low=2, high=15), rng.uniform(2, 15, 50)),
+             (D.TruncatedNormal(1.0, 0.5, low=0.0), rng.uniform(0, 4, 50)), (D.Uniform(-1.0, 3.0), rng.uniform(-1, 3, 50)),
+             (D.Beta(0.5, 0.5), rng.uniform(0.01, 0.99, 50)), (D.Beta(2.0, 5.0), rng.uniform(0.01, 0.99, 50)),
+             (D.Gamma(3.0, 0.5), rng.uniform(0.1, 20, 50)), (D.LogNormal(0.2, 0.8), rng.uniform(0.1, 9, 50)),
+             (D.HalfNormal(2.5), rng.uniform(0, 9, 50)), (D.Exponential(0.7), rng.uniform(0, 9, 50)),
+             (D.TransformedDistribution(D.Beta(0.5, 0.5), D.transforms.AffineTransform(1.5, 1)), rng.uniform(1.51, 2.49, 50)),
+             (D.TransformedDistribution(D.Gamma(2.0, 3.0), D.transforms.AffineTransform(0.25, 2.0)), rng.uniform(0.3, 6, 50))]
+    for fn, x in cases:
+        spec = D._family_spec(fn)
+        assert spec is not None, type(fn).__name__
+        ref = fn.log_prob(torch.as_tensor(x, dtype=torch.float64)).numpy()
+        assert np.allclose(from_spec(spec, x), ref, rtol=1e-12, atol=1e-12), type(fn).__name__
+        assert D._bijector_spec(fn.support) is not None
+    # parameters that are another site's value (a tensor with more than one element) cannot be folded into a constant
+    assert D._family_spec(D.Normal(torch.zeros(3, dtype=torch.float64), 1.0)) is None
