@@ -156,7 +156,7 @@ template <int P> DYN_DI Dual<P> dual_shfl(const Dual<P>& a, int src) {
   return r;
 }
 // log of a double >= 1e-6 (the clamped incidence of the fused log-likelihood): the fdlibm algorithm (exponent split, s = f/(2+f), degree-7 polynomial in
-// s^2; < 1 ulp with an exact quotient, < 2 ulp with div_fast) with every constant in c[][].  The libm call it
+// s^2; ~1-2 ulp as evaluated here) with every constant in c[][].  The libm call it
 // replaces in the fused log-likelihood's save pass is ~45 instructions plus 45 UMOVs of literals, per pass and slot.
 static __constant__ double kLogC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                        2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
@@ -168,11 +168,17 @@ DYN_DI double log_fast(double x) {
   double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
   const double f = m - 1.0;
-  const double s = div_fast(f, 2.0 + f);
+  // The caller's accumulation waits for this value at two warps per scheduler, so the dependent chain is kept
+  // short: the quotient is reciprocal x numerator without the correction step (2^-52 relative on s: 1e-16 on the
+  // result), and the polynomial is evaluated in Estrin form (4 dependent FMAs instead of 7).
+  const double s = f * rcp_fast(2.0 + f);
   const double z = s * s;
-  double R = kLogC[6];
-#pragma unroll
-  for (int k = 5; k >= 0; --k) R = fma(R, z, kLogC[k]);
+  const double z2 = z * z;
+  const double q01 = fma(kLogC[1], z, kLogC[0]);
+  const double q23 = fma(kLogC[3], z, kLogC[2]);
+  const double q45 = fma(kLogC[5], z, kLogC[4]);
+  const double q456 = fma(kLogC[6], z2, q45);
+  double R = fma(z2, fma(z2, q456, q23), q01);
   R *= z;
   const double hfsq = 0.5 * f * f;
   const double dk = (double)e;
