@@ -518,13 +518,17 @@ struct LaneSolver {
             }
           }
         } else {
+          // a trajectory that ran out of max_steps has a truncated sum: the reference raises (diffrax throw=True),
+          // the asynchronous kernel reports NaN for lp and its gradient -- as the adjoint kernel does -- so that a
+          // sampler sees a non-finite potential instead of a plausible number (stats carry the result code)
+          const bool failed = tprev < t1;
           const double tot = traj_sum(obs_owner ? lp_acc.v : 0.0, c);
-          if (fin && q == 0 && wp) a.lp[traj] = tot + a.lp_const;
+          if (fin && q == 0 && wp) a.lp[traj] = failed ? CUDART_NAN : tot + a.lp_const;
           if constexpr (P > 0) {
 #pragma unroll
             for (int k = 0; k < P; ++k) {
               const double gp = traj_sum(obs_owner ? lp_acc.d[k] : 0.0, c);
-              if (fin && q == 0 && p0s + k < a.P_total) a.grad[traj * a.P_total + p0s + k] = gp;
+              if (fin && q == 0 && p0s + k < a.P_total) a.grad[traj * a.P_total + p0s + k] = failed ? CUDART_NAN : gp;
             }
           }
         }

@@ -336,8 +336,9 @@ _OVERFLOW: Dict[int, object] = {}
 
 def _overflow_counter(torch, dev):
     """Device counter of trajectories whose accepted steps did not fit the adjoint's checkpoint scratch since
-    the last `adjoint_overflows(reset=True)`; updated with stream-ordered tensor ops (graph-capturable), so a
-    sampler can check ONCE at the end instead of synchronising on every evaluation."""
+    the last `adjoint_overflows(reset=True)`; updated with stream-ordered tensor ops (graph-capturable).  The
+    differentiable path (simulation/autograd.py::PoissonLoglik) re-evaluates such rows by forward sensitivities in
+    the same call, so the counter is a diagnostic (how often the fallback ran), not a failure count."""
     t = _OVERFLOW.get(dev.index)
     if t is None:
         t = torch.zeros((), dtype=torch.int64, device=dev)

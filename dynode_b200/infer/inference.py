@@ -88,12 +88,9 @@ class MCMC:
             _engine.adjoint_overflows(reset=True)
         z, extra, last = eng.run(z0, self.num_warmup, self.num_samples, progress)
         if md.device.type == "cuda":
-            lost = _engine.adjoint_overflows(reset=True)
-            if lost:
-                raise RuntimeError(
-                    f"{lost} log-density evaluations accepted more Tsit5 steps than the discrete adjoint's "
-                    "checkpoint scratch holds and returned NaN; raise DYNODE_B200_ADJOINT_CAP (default 512) or "
-                    "set DYNODE_B200_ADJOINT=0 to use forward sensitivities")
+            # rows beyond the adjoint's checkpoint capacity were re-evaluated by forward sensitivities where they
+            # occurred (simulation/autograd.py); the count is kept as a diagnostic
+            self.adjoint_fallbacks = _engine.adjoint_overflows(reset=True)
         self._samples_z, self._extra, self.last_state = z, extra, last
         C, N, D = z.shape
         flat = md.constrain(z.reshape(C * N, D), with_deterministic=True)
@@ -228,10 +225,24 @@ class SVI:
             z = self.guide.rsample(self.num_particles, gen)
             loss = md.potential(z).mean() - self.guide.entropy()  # -ELBO
             loss.backward()
+            # A non-finite loss (a solve that ran out of max_steps reports NaN) must not reach Adam: one NaN
+            # gradient poisons loc / scale for good.  Its gradients are zeroed on the device (no sync), the step is
+            # recorded, and the run stops at the next check below.
+            ok = torch.isfinite(loss.detach())
+            for p in self.guide.parameters():
+                if p.grad is not None:
+                    p.grad = torch.where(ok, p.grad, torch.zeros_like(p.grad))
             opt.step()
             losses[it] = loss.detach()
-            if progress_bar and ((it + 1) % every == 0 or it + 1 == num_steps):
-                print(f"[dynode_b200.infer] svi {it + 1}/{num_steps}  loss={float(loss):.4f}")
+            if (it + 1) % every == 0 or it + 1 == num_steps:
+                bad = int((~torch.isfinite(losses[:it + 1])).sum())
+                if bad:
+                    raise RuntimeError(
+                        f"SVI: {bad} of the first {it + 1} ELBO estimates were not finite (a model evaluation "
+                        "returned NaN/inf: e.g. an ODE solve that reached `max_steps`); the optimiser state was "
+                        "protected, the run is stopped")
+                if progress_bar:
+                    print(f"[dynode_b200.infer] svi {it + 1}/{num_steps}  loss={float(loss):.4f}")
         params = {"auto_loc": self.guide.loc.detach().clone(), "auto_scale_tril": self.guide.scale_tril().detach().clone()}
         return SVIRunResult(params, losses)
 

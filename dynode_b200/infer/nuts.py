@@ -478,13 +478,14 @@ class BatchedNUTS:
             self._graph = graph
             self._round_fn = graph.replay
             self.graph_used = True
-        except Exception as e:  # same kernels either way; say that replay is off and why
+        except Exception as e:  # the SAME round implementation runs eagerly; say that replay is off and why
             import traceback
             import warnings
             self.capture_error = traceback.format_exc()
             torch.cuda.synchronize()
             self._g = self.gen
-            self._round_fn = self._round
+            self._round_fn = round_impl  # kernels_used stays what it says: only the replay is dropped
+            self.graph_used = False
             where = "".join(self.capture_error.splitlines(keepends=True)[-14:])
             warnings.warn(f"BatchedNUTS: CUDA-graph capture of the round failed ({type(e).__name__}: {e}); "
                           f"running rounds eagerly\n{where}")

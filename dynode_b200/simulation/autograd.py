@@ -281,6 +281,18 @@ class PoissonLoglik(torch.autograd.Function):
             grad = g_all.index_select(1, _adjoint_columns(cfg, th.device))
             if cfg.y0_grad:
                 grad = torch.cat([grad, g_y0], dim=1)
+            # Rows that accepted more steps than the checkpoint scratch holds come back NaN with result code
+            # RESULT_ADJOINT_CAPACITY: they are re-evaluated right here by forward sensitivities, in a launch masked
+            # to exactly those rows (no host sync: when nothing overflowed every warp scans its mask bytes and exits),
+            # so neither NUTS nor SVI ever sees the capacity of a scratch buffer as a NaN log-density.
+            over = stats[:, _lib.STAT_RESULT] == _lib.RESULT_ADJOINT_CAPACITY
+            with engine.only_rows(over.view(torch.uint8)):
+                lp_f, grad_f, stats_f = engine.poisson_loglik_grad(
+                    cfg.model, y0c, _kernel_params(cfg, th), pl.contact, cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs,
+                    pl.lp_const, wrt=cfg.wrt_ids(), dy0=_seeds(cfg, B, th.device), B=B)
+            lp = torch.where(over, lp_f, lp)
+            grad = torch.where(over[:, None], grad_f, grad)
+            stats = torch.where(over[:, None], stats_f, stats)
             return lp, stats, grad
         lp, grad, stats = engine.poisson_loglik_grad(cfg.model, y0c, _kernel_params(cfg, th), pl.contact,
                                                      cfg.opts(), pl.save_ts, pl.obs_comp, pl.obs, pl.lp_const,

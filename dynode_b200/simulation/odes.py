@@ -89,11 +89,15 @@ def _solver_options(solver_parameters, duration_days) -> engine.SolverOptions:
         raise UnsupportedODEError(
             f"solver {type(solver_parameters.solver_method).__name__} is not implemented on the device; "
             "only Tsit5 is (reference default, config/params.py:28-34)")
+    const_dt = float(solver_parameters.constant_step_size)
+    # the reference builds ConstantStepSize() with no ClipStepSizeController: discontinuity points are ignored in
+    # constant-step mode (reference odes.py:113-131)
+    jumps = () if const_dt > 0.0 else tuple(float(x) for x in solver_parameters.discontinuity_points)
     return engine.SolverOptions(
-        jump_ts=tuple(float(x) for x in solver_parameters.discontinuity_points),
+        jump_ts=jumps,
         t0=0.0, t1=float(duration_days), rtol=solver_parameters.ode_solver_rel_tolerance,
         atol=solver_parameters.ode_solver_abs_tolerance,
-        const_dt=float(solver_parameters.constant_step_size), max_steps=int(solver_parameters.max_steps))
+        const_dt=const_dt, max_steps=int(solver_parameters.max_steps))
 
 
 def _numel_per_traj(t: torch.Tensor, batched: bool) -> int:
@@ -164,10 +168,10 @@ def _mask_from(indices: Optional[Sequence[int]], ncomp: int) -> int:
         return (1 << ncomp) - 1
     mask = 0
     for i in indices:
-        if not -ncomp <= int(i) < ncomp:
-            print(f"An index passed to sub_save_indices was out of range for initial_state values: {i}")
-            continue
-        mask |= 1 << (int(i) % ncomp)
+        # reference odes.py:185-190: `y[i] if i in sub_save_indices` with i in range(len(y)) -- an index outside
+        # [0, ncomp), negative ones included, never matches and saves nothing
+        if 0 <= int(i) < ncomp:
+            mask |= 1 << int(i)
     return mask
 
 
@@ -255,20 +259,32 @@ def _run_differentiable(ode, duration_days, initial_state, ode_parameters, solve
                     result=st[_lib.STAT_RESULT])
 
 
-_OBS_CACHE: Dict[int, tuple] = {}
+_OBS_CACHE: Dict[tuple, tuple] = {}
+
+
+def _obs_key(obs, dev) -> tuple:
+    """Identity AND content of the observations on one device: a tensor mutated in place bumps `_version`, an array's
+    bytes are hashed (observation tables are a few hundred values), and every CUDA device keeps its own copy."""
+    if isinstance(obs, torch.Tensor):
+        return ("t", id(obs), obs._version, obs.data_ptr(), tuple(obs.shape), str(dev))
+    a = np.ascontiguousarray(np.asarray(obs, dtype=np.float64))
+    return ("a", a.shape, hash(a.tobytes()), str(dev))
 
 
 def _observation_constants(obs, dev, rows: int):
-    """(device observations [T-1][m], -sum lgamma(obs+1)) cached per observation object: the constant is
+    """(device observations [T-1][m], -sum lgamma(obs+1)) cached per observation content and device: the constant is
     reduced on the device once, so the hot loop never synchronises on it."""
-    hit = _OBS_CACHE.get(id(obs))
-    if hit is not None and hit[0] is obs:
+    key = _obs_key(obs, dev)
+    hit = _OBS_CACHE.get(key)
+    if hit is not None and (not isinstance(obs, torch.Tensor) or hit[0] is obs):
         return hit[1], hit[2]
     obs_t = torch.as_tensor(obs, dtype=torch.float64).to(dev).reshape(rows, -1).contiguous()
+    if obs_t.data_ptr() == (obs.data_ptr() if isinstance(obs, torch.Tensor) else 0):
+        obs_t = obs_t.clone()  # never alias the caller's buffer: a later in-place edit must miss the cache, not change it
     lp_const = float(-torch.lgamma(obs_t + 1.0).sum())
     if len(_OBS_CACHE) > 64:
         _OBS_CACHE.clear()
-    _OBS_CACHE[id(obs)] = (obs, obs_t, lp_const)
+    _OBS_CACHE[key] = (obs if isinstance(obs, torch.Tensor) else None, obs_t, lp_const)
     return obs_t, lp_const
 
 

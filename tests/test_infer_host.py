@@ -252,3 +252,23 @@ def test_fused_site_specs_reproduce_log_prob():
         assert D._bijector_spec(fn.support) is not None
     # parameters that are another site's value (a tensor with more than one element) cannot be folded into a constant
     assert D._family_spec(D.Normal(torch.zeros(3, dtype=torch.float64), 1.0)) is None
+
+
+def test_svi_stops_on_a_non_finite_loss_without_poisoning_the_guide():
+    """A model evaluation that returns NaN (e.g. an ODE solve that reached max_steps) must not flow into Adam: the
+    gradients of that step are zeroed, and the run raises at the next check instead of returning NaN parameters."""
+    calls = {"n": 0}
+
+    def model():
+        x = ppl.sample("x", dist.Normal(0.0, 1.0))
+        calls["n"] += 1
+        bad = float("nan") if calls["n"] == 8 else 0.0
+        ppl.factor("lik", -0.5 * (x - 1.0) ** 2 + bad)
+
+    from dynode_b200.infer.inference import SVI, Adam, AutoMultivariateNormal, init_to_median
+    guide = AutoMultivariateNormal(model, init_loc_fn=init_to_median)
+    svi = SVI(model=model, guide=guide, optim=Adam(step_size=0.1))
+    with pytest.raises(RuntimeError, match="not finite"):
+        svi.run(PRNGKey(3), 50, progress_bar=False)
+    assert calls["n"] < 20  # stopped at the first check after the bad step, not after all 50
+    assert all(bool(torch.isfinite(p).all()) for p in guide.parameters())

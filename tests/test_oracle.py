@@ -284,32 +284,98 @@ def test_discontinuity_points_clip_steps_in_both_restatements():
     assert np.array_equal(st1, st0) and np.array_equal(ys1, ys0)
 
 
-def test_oracle_matches_diffrax_golden():
-    """Pins the restated solver to real diffrax output WHEN tests/golden/diffrax_golden.npz exists (written by
-    baseline/dump_diffrax_golden.py on a machine with diffrax 0.7 + jax x64).  It cannot be produced in this
-    image (no jax / diffrax, no network): until then the solver arithmetic is 'parity unpinned'."""
-    import os
-    from tests.cases import ALL_CASES, make_case
-    path = os.path.join(os.path.dirname(__file__), "golden", "diffrax_golden.npz")
-    if not os.path.exists(path):
-        pytest.skip("PARITY UNPINNED: tests/golden/diffrax_golden.npz absent (diffrax is not installable here)")
-    gold = np.load(path)
-    draws = int(gold["meta/draws"])
-    for name in ALL_CASES:
-        case = make_case(name, draws)
-        fam, dims, theta, shared = case["oracle"]
-        kw = {}
-        if name == "sir_age2":
-            kw["wrt"] = [0, 1]
-        ys, dys, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=case["t1"], **kw)
-        assert np.array_equal(st[:, 1], gold[f"{name}/accepted"]) and np.array_equal(st[:, 2], gold[f"{name}/rejected"])
-        ref = gold[f"{name}/ys"]
-        assert np.all(np.abs(ys - ref) <= 1e-6 * np.abs(ref) + 1e-9 * np.abs(ref).max())
-        if name == "sir_age2":
-            w = gold[f"{name}/grad_weights"]
-            g = (w[None, :, :, None] * dys[:, :, 4:6, :]).sum((1, 2))
-            assert np.allclose(g[:, 0], gold[f"{name}/grad_beta"][:, 0], rtol=1e-6)
-            assert np.allclose(g[:, 1], gold[f"{name}/grad_gamma"][:, 0], rtol=1e-6)
+def _oracle_golden_solver(name, B, jump_ts=(), const_dt=0.0, save_step=1, sub_save=None, rtol=1e-5, atol=1e-6):
+    """tests/golden_check.py solver: the C++ oracle on tests.cases.make_case(name, B)."""
+    from tests.cases import make_case
+    case = make_case(name, B)
+    fam, dims, theta, shared = case["oracle"]
+    t1 = case["t1"]
+    kw = dict(t1=t1, rtol=rtol, atol=atol, const_dt=const_dt, jump_ts=jump_ts,
+              save_ts=np.linspace(0.0, t1, int(t1 // save_step) + 1))
+    if sub_save == "first_last":
+        sizes = case["model"].compartment_sizes()
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        kw["save_idx"] = list(range(offs[0], offs[1])) + list(range(offs[-2], offs[-1]))
+    ys, _, st = orc.solve(fam, dims, case["y0"], theta, shared, **kw)
+    return ys, st
+
+
+def config2_potential_on_host(z, obs, names):
+    """numpyro's potential energy of the config-2 model (reference examples/sir_infer_parameters.py:21-59) and its
+    gradient at unconstrained points z [K,2]: priors / bijectors / Jacobians from dynode_b200.infer.distributions on
+    CPU torch, the Poisson log-likelihood and its (beta, gamma) gradient from the oracle's frozen-step tangents."""
+    import torch
+    from dynode_b200.infer import distributions as dist
+    from tests.cases import CONTACT2
+    priors = {"strains_0_r0": dist.TransformedDistribution(dist.Beta(0.5, 0.5), dist.transforms.AffineTransform(1.5, 1)),
+              "strains_0_infectious_period": dist.TruncatedNormal(loc=8, scale=2, low=2, high=15)}
+    zt = torch.as_tensor(z, dtype=torch.float64).requires_grad_(True)
+    x, lp_prior = {}, 0.0
+    for k, nm in enumerate(names):
+        d = priors[str(nm)]
+        t = dist.biject_to(d.support)
+        x[str(nm)] = t(zt[:, k])
+        lp_prior = lp_prior + d.log_prob(x[str(nm)]) + t.log_abs_det_jacobian(zt[:, k], x[str(nm)])
+    r0, tinf = x["strains_0_r0"], x["strains_0_infectious_period"]
+    beta, gamma = r0 / tinf, 1.0 / tinf
+    C = CONTACT2 / np.max(np.real(np.linalg.eigvals(CONTACT2)))
+    y0 = np.concatenate([1000 * 0.99 * np.array([0.75, 0.25]), 1000 * 0.01 * np.array([0.75, 0.25]), np.zeros(2)])
+    theta = np.stack([beta.detach().numpy(), gamma.detach().numpy()], axis=1)
+    ys, dys, st = orc.solve(orc.SIR_AGE, (2, 1, 1), y0, theta, C, t1=100, wrt=[0, 1])
+    ll, g = orc.poisson_incidence(ys[:, :, 4:6], dys[:, :, 4:6, :], obs)
+    # chain rule through (beta, gamma) by giving autograd the oracle's gradient as a constant
+    ll_t = torch.as_tensor(ll) + ((beta - beta.detach()) * torch.as_tensor(g[:, 0])
+                                  + (gamma - gamma.detach()) * torch.as_tensor(g[:, 1]))
+    U = -(lp_prior + ll_t)
+    (dU,) = torch.autograd.grad(U.sum(), zt)
+    return U.detach().numpy(), dU.numpy(), ll, r0.detach().numpy(), tinf.detach().numpy()
+
+
+@pytest.mark.parametrize("kind", ["diffrax", "standin"])
+def test_oracle_matches_golden(kind):
+    """EVERY key of the golden file written by baseline/dump_diffrax_golden.py (all cases, discontinuity points,
+    constant step, save_step 2/3/7, sub-save, tight tolerances, stats; with real diffrax also numpyro's config-2
+    potential and gradient) against the C++ oracle.
+
+    kind="diffrax": the reference on real diffrax 0.7 + jax x64 -- not producible in this image (no jax / diffrax, no
+    network): until someone runs the dump script off-box and commits tests/golden/diffrax_golden.npz the solver
+    arithmetic is PARITY UNPINNED and this test says so.
+    kind="standin": the reference's own simulate() / RHS / SolverParams over baseline/standin_stack.py (its
+    `diffeqsolve` is the numpy restatement): pins the plumbing either side of the solver arithmetic."""
+    from tests import golden_check as gc
+    gold = gc.load(kind)
+    if gold is None:
+        assert kind == "diffrax", "tests/golden/standin_golden.npz must be committed"
+        pytest.skip("PARITY UNPINNED: tests/golden/diffrax_golden.npz absent (diffrax is not installable here; "
+                    "run baseline/dump_diffrax_golden.py where DynODE's stack is installed)")
+    assert gc.check(gold, _oracle_golden_solver) == 9 + 3 * 7
+    if "c2/potential" in gold:
+        U, dU, ll, r0, tinf = config2_potential_on_host(gold["c2/z"], gold["c2/obs"], gold["c2/site_names"])
+        assert np.allclose(r0, gold["c2/r0"], rtol=1e-12) and np.allclose(tinf, gold["c2/infectious_period"], rtol=1e-12)
+        assert np.allclose(ll, gold["c2/loglik"], rtol=1e-6)
+        assert np.allclose(U, gold["c2/potential"], rtol=1e-6)
+        assert np.allclose(dU, gold["c2/grad"], rtol=1e-6, atol=1e-6 * np.abs(gold["c2/grad"]).max())
+
+
+def test_config2_potential_on_host_is_self_consistent():
+    """The host statement of numpyro's config-2 potential used above: its gradient equals central differences of its
+    value along the frozen step sequence's neighbourhood (adaptive re-solves agree to O(rtol))."""
+    rng = np.random.default_rng(4)
+    z = rng.normal(0, 0.7, size=(3, 2))
+    y0 = np.concatenate([1000 * 0.99 * np.array([0.75, 0.25]), 1000 * 0.01 * np.array([0.75, 0.25]), np.zeros(2)])
+    from tests.cases import CONTACT2
+    C = CONTACT2 / np.max(np.real(np.linalg.eigvals(CONTACT2)))
+    ys, _, _ = orc.solve(orc.SIR_AGE, (2, 1, 1), y0, np.array([[2.0 / 7.0, 1.0 / 7.0]]), C, t1=100)
+    obs = np.diff(ys[0, :, 4:6], axis=0)
+    names = ["strains_0_r0", "strains_0_infectious_period"]
+    U, dU, *_ = config2_potential_on_host(z, obs, names)
+    eps = 1e-4
+    for k in range(2):
+        zp, zm = z.copy(), z.copy()
+        zp[:, k] += eps
+        zm[:, k] -= eps
+        fd = (config2_potential_on_host(zp, obs, names)[0] - config2_potential_on_host(zm, obs, names)[0]) / (2 * eps)
+        assert np.allclose(fd, dU[:, k], rtol=5e-3, atol=5e-3 * np.abs(dU).max())
 
 
 def test_seip_family_invariants_and_two_statements_of_the_rhs():

@@ -110,3 +110,35 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "libdynode_oracle" not in txt, f
+
+
+def test_constant_step_mode_ignores_discontinuity_points():
+    # reference odes.py:113-131: ConstantStepSize() is built WITHOUT a ClipStepSizeController, so the list is unused
+    from dynode_b200.simulation.odes import _solver_options
+    o = _solver_options(SolverParams(constant_step_size=0.5, discontinuity_points=[10.0, 20.0]), 100)
+    assert o.jump_ts == () and o.const_dt == 0.5
+    o = _solver_options(SolverParams(discontinuity_points=[10.0, 20.0]), 100)
+    assert o.jump_ts == (10.0, 20.0) and o.const_dt == 0.0
+
+
+def test_sub_save_indices_outside_the_compartments_save_nothing():
+    # reference odes.py:185-190: `y[i] if i in sub_save_indices ... for i in range(len(y))` -- negative or too-large
+    # indices never match (they do NOT wrap around)
+    from dynode_b200.simulation.odes import _mask_from
+    assert _mask_from(None, 3) == 0b111
+    assert _mask_from((0, 2), 3) == 0b101
+    assert _mask_from((-1,), 3) == 0
+    assert _mask_from((1, 7, -3), 3) == 0b010
+
+
+def test_observation_cache_sees_in_place_edits_and_devices():
+    from dynode_b200.simulation.odes import _obs_key
+    obs = torch.arange(6.0, dtype=torch.float64)
+    k0 = _obs_key(obs, "cuda:0")
+    assert _obs_key(obs, "cuda:0") == k0 and _obs_key(obs, "cuda:1") != k0
+    obs[2] = 9.0  # in-place edit bumps the version counter
+    assert _obs_key(obs, "cuda:0") != k0
+    a = np.arange(6.0)
+    ka = _obs_key(a, "cuda:0")
+    a[1] = 5.0
+    assert _obs_key(a, "cuda:0") != ka
