@@ -41,6 +41,11 @@ WORKLOADS = {
     "c4": ("seirs_multi_a2s3", 100_000,
            "C4 multi-strain age-stratified SEIRS+C (A=2,S=3,n=26), 365 d, daily SaveAt T=366"),
     "c3": ("seirs_seasonal", 1_000_000, "C3 seasonally forced SEIRS (n=4), 365 d, daily SaveAt T=366"),
+    # BASELINE.json configs[4]: a NUTS run, not an ensemble solve -- see run_c5
+    "c5": ("seirs_multi_g6s3", 1024,
+           "C5 age(3) x risk(2) x strain(3) SEIRS+C (n=78) NUTS inference of 3 r0 + 3 infectious periods, Poisson "
+           "likelihood on 120 d of daily incidence, 1024 chains sharded over the GPUs, NCCL gather of "
+           "posterior-predictive trajectories"),
 }
 F_RHS = {"seirs_multi_a2s3": 130, "seirs_seasonal": 18}  # flops per RHS evaluation
 
@@ -138,6 +143,8 @@ def run_reference(args):
     if rank != 0:
         return
     name, B, desc = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        return run_reference_c5(args)
     chunk = 8192
     from oracle import oracle as orc
     case = make_inputs(args.workload, chunk, 20260101)
@@ -161,6 +168,44 @@ def run_reference(args):
         "note": "reference JAX/diffrax stack not installable here; CPU oracle (C++ restatement, OpenMP) timed instead",
     }
     print(json.dumps(line))
+
+
+def run_reference_c5(args):
+    """Reference arm of --workload c5: what one NUTS leapfrog costs on the host -- the CPU oracle's solve with the six
+    forward tangents (r0 and infectious period of three strains -> beta, gamma) plus the Poisson log-likelihood and
+    its gradient, on all host threads, for `chunk` chains per step.  (numpyro itself is not installable here.)"""
+    from oracle import oracle as orc
+    from tests.cases import make_case
+    chunk = 1024
+    case = make_case("seirs_multi_g6s3", chunk, seed=20260105)
+    fam, dims, theta, shared = case["oracle"]
+    cores = host_threads()
+    wrt = [0, 1, 2, 3, 4, 5]  # beta_s, gamma_s
+    sizes = case["model"].compartment_sizes()
+    idx = list(range(sum(sizes[:4]), sum(sizes)))
+    truth, _, _ = orc.solve(fam, dims, case["y0"][:1], theta[:1], shared, t1=120, save_idx=idx)
+    obs = np.abs(np.diff(truth[0], axis=0)) + 0.05
+
+    def step():
+        ys, dys, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=120, save_idx=idx, wrt=wrt, nthreads=cores)
+        return orc.poisson_incidence(ys, dys, obs)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = args.steps * chunk / dt
+    sample = f"{chunk} chains' (log-density, gradient) per step, {args.steps} steps, OpenMP over {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "NUTS grad-evals/s", "value": v, "unit": "grad-evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS["c5"][2], "chains_per_step": chunk},
+        "cpu_baseline": {"value": v, "unit": "grad-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "numpyro / JAX not installable here; CPU oracle (forward tangents + Poisson gradient) timed instead"}))
 
 
 def nuts_leg(args, dev, world, barrier):
@@ -300,6 +345,147 @@ def nuts_leg(args, dev, world, barrier):
     return out
 
 
+def run_c5(args):
+    """BASELINE.json configs[4]: age x risk x multi-strain SEIRS NUTS inference, `--c5-chains` chains STRONG-scaled over
+    the ranks, then posterior-predictive trajectories from every rank's draws gathered with NCCL.
+
+    A step = one complete NUTS run (warm-up + sampling) of all chains through the public `MCMC(NUTS(model))` API
+    (reference src/dynode/infer/inference.py:149-163); no collective inside it.  value = gradient evaluations of the
+    whole job per second of the slowest rank.  e2e adds what a user does next: posterior samples to the host,
+    `Predictive` on a thinned subset (inference.py:225-235), `gather_draws` over NVLink, gathered draws to the host."""
+    import torch
+    import torch.distributed as dist
+
+    from dynode_b200.distributed import gather_draws
+    from dynode_b200.examples import seirs_age_risk_strain as m5
+    from dynode_b200.infer import MCMC, NUTS, Predictive, PRNGKey
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    tf = 120
+    total = args.c5_chains
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    chains = hi - lo
+    obs = m5.synthetic_incidence(tf).to(dev)
+    cfg = m5.get_config(infer=True)
+
+    def nuts_run(num_warmup, num_samples, seed):
+        mc = MCMC(NUTS(m5.model_fused, max_tree_depth=args.c5_tree_depth), num_warmup=num_warmup,
+                  num_samples=num_samples, num_chains=chains, progress_bar=False)
+        mc.run(PRNGKey(seed + rank), config=cfg, tf=tf, obs_data=obs)
+        return mc
+
+    def predictive_and_gather(mc, seed):
+        post = mc.get_samples()
+        n = next(iter(post.values())).shape[0]
+        per_rank = max(1, args.c5_predictive // world)
+        pick = torch.linspace(0, n - 1, min(n, per_rank), device=dev).long()
+        thin = {k: v[pick] for k, v in post.items()}
+        t0 = time.perf_counter()
+        pp = Predictive(m5.model, posterior_samples=thin)(PRNGKey(seed + rank), config=cfg, tf=tf, obs_data=None)
+        torch.cuda.synchronize()
+        t_pred = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        allpp = gather_draws({"incidence": pp["incidence"], **thin})
+        torch.cuda.synchronize()
+        t_gather = time.perf_counter() - t0
+        return post, allpp, t_pred, t_gather
+
+    # ---- untimed warm-up steps: short runs of the same program (module loading, vmap traces, graph capture, NCCL
+    # channels for the gather) -- one-time costs of the process, not of a NUTS run
+    for w in range(max(args.warmup, 1)):
+        mcw = nuts_run(12, 4, 1000 + 17 * w)
+        predictive_and_gather(mcw, 5 + w)
+    barrier()
+    sampler_clk = ClockSampler(local)
+    sampler_clk.start()
+    walls, evals, rounds, e2e_walls = [], [], [], []
+    d2h_bytes = 0
+    for k in range(args.steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        mc = nuts_run(args.c5_warmup, args.c5_samples, 8675314 + 1000 * k)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_dev = ev0.elapsed_time(ev1) * 1e-3
+        post, allpp, t_pred, t_gather = predictive_and_gather(mc, 31 + k)
+        host = {name: v.cpu() for name, v in post.items()}
+        host_pp = {name: v.cpu() for name, v in allpp.items()} if rank == 0 else {}
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        d2h_bytes = sum(v.numel() * v.element_size() for v in host.values()) + \
+            sum(v.numel() * v.element_size() for v in host_pp.values())
+        walls.append(reduce_max(t_dev))
+        e2e_walls.append(reduce_max(t_e2e))
+        evals.append(reduce_sum(float(mc.engine.grad_evals)))
+        rounds.append(mc.engine.rounds)
+    clocks = sampler_clk.stop()
+    barrier()
+    mean_wall = sum(walls) / len(walls)
+    value = sum(evals) / sum(walls)
+    leap = float(mc.get_extra_fields()["num_steps"].double().mean()) if "num_steps" in mc.get_extra_fields() else None
+    if rank == 0:
+        names_r0 = [f"strains_{k}_r0" for k in range(3)]
+        names_inf = [f"strains_{k}_infectious_period" for k in range(3)]
+        line = {
+            "metric": "NUTS grad-evals/s", "value": value, "unit": "grad-evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * mean_wall,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"][2], "chains_total": total, "chains_per_gpu": chains,
+                       "num_warmup": args.c5_warmup, "num_samples": args.c5_samples,
+                       "max_tree_depth": args.c5_tree_depth, "tf": tf, "rtol": 1e-5, "atol": 1e-6,
+                       "l2": "not applicable: a step is a whole NUTS run (thousands of dependent launches), "
+                             "inputs are 6 numbers per chain"},
+            "clocks": clocks,
+            "gpu_launches": int(sum(rounds) * 3),
+            "e2e": {"value": sum(evals) / sum(e2e_walls), "unit": "grad-evals/s", "ms_per_step": 1e3 * sum(e2e_walls) / len(e2e_walls),
+                    "h2d_bytes_per_step": int(obs.numel() * 8), "d2h_bytes_per_step": int(d2h_bytes),
+                    "api": "MCMC(NUTS(model)).run + get_samples().cpu() + Predictive + gather_draws + .cpu()"},
+            "nuts": {
+                "grad_evals_per_s": value, "mcmc_wall_s": mean_wall, "rounds": rounds,
+                "grad_evals_per_run": evals, "mean_leapfrogs_per_transition": leap,
+                "cuda_graph": mc.engine.graph_used, "cuda_round_kernels": mc.engine.kernels_used,
+                "posterior_mean_r0": [float(allpp[k].mean()) for k in names_r0],
+                "posterior_mean_infectious_period": [float(allpp[k].mean()) for k in names_inf],
+                "truth_r0": list(m5.TRUE_R0), "truth_infectious_period": list(m5.TRUE_INF),
+                "predictive_s": t_pred, "gather_s": t_gather,
+                "posterior_predictive_gathered_shape": list(allpp["incidence"].shape),
+                "gather_bytes": int(allpp["incidence"].numel() * 8),
+            },
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -431,8 +617,15 @@ def run_ours(args):
             sizes = [1, 1, 1, 1]
             shp = [(B, 1)] * 4
         offs = np.concatenate([[0], np.cumsum(sizes)])
-        state = tuple(y0h[:, offs[i]:offs[i + 1]].reshape(shp[i]) for i in range(len(sizes)))
-        out_h = torch.empty((B, T, ns), dtype=torch.float64).pin_memory()
+        # one page-locked array per compartment, as a caller holding `initial_state` tuples per draw would have
+        state = tuple(y0h[:, offs[i]:offs[i + 1]].reshape(shp[i]).contiguous().pin_memory() for i in range(len(sizes)))
+        from dynode_b200 import hostmem
+        if args.host_alloc == "thp":  # page-locked + 2 MiB huge pages (dynode_b200/hostmem.py): the product default
+            out_h = hostmem.pinned_empty((B, T, ns))
+            huge = out_h._dynode_host_buffer.huge_bytes()
+        else:
+            out_h = torch.empty((B, T, ns), dtype=torch.float64).pin_memory()
+            huge = None
         sp = SolverParams()
         k_e2e = max(1, min(args.steps, args.e2e_steps))
 
@@ -456,9 +649,31 @@ def run_ours(args):
                      - ys[:64, :, -(sizes[-1]):]).abs().max())
         h2d = int(sum(v.numel() for v in hp.values()) * 8 + y0h.numel() * 8)
         d2h = int(out_h.numel() * 8 + B * 16)
+        # the host link's own ceiling, measured in this run on the same buffers: every rank copies its resident
+        # `ys` into its `out_h` at once (no solve), same chunking -- what a perfect pipeline could reach on this box
+        def raw_d2h():
+            for lo in range(0, B, args.host_chunk):
+                out_h[lo:lo + args.host_chunk].copy_(ys[lo:lo + args.host_chunk], non_blocking=True)
+        raw_d2h()
+        barrier()
+        t0 = time.perf_counter()
+        raw_d2h(); raw_d2h()
+        barrier()
+        dt_raw = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([dt_raw], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_raw = float(t.item())
+        ceiling = world * out_h.numel() * 8 / dt_raw / 1e9
+        e2e_gbs = world * d2h * k_e2e / dt / 1e9
         e2e = {"value": world * B * k_e2e / dt, "unit": "trajectories/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
-               "api": "dynode_b200.simulation.simulate_ensemble (pinned host in/out, chunked H2D/solve/D2H overlap)",
+               "api": "dynode_b200.simulation.simulate_ensemble (page-locked host in/out, chunked solve/D2H overlap)",
+               "d2h_gbs": e2e_gbs, "pcie_ceiling_gbs": ceiling, "link_fraction": e2e_gbs / ceiling,
+               "pcie_ceiling_how": f"all {world} rank(s) copying their resident ys to the same host buffers at once, "
+                                   "no solve, measured in this run (aggregate GB/s)",
+               "host_buffer": "mmap + MADV_HUGEPAGE + cudaHostRegister" if args.host_alloc == "thp" else "cudaHostAlloc",
+               "host_buffer_huge_bytes": huge,
                "max_abs_diff_vs_device_run": chk}
 
     # ---- all-gather of the saved trajectories (N > 1): the only collective of the path, reported beside
@@ -535,13 +750,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 100; 2 for --workload c5)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override draws per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--host-chunk", type=int, default=2048)
+    ap.add_argument("--host-alloc", default="thp", choices=["thp", "cuda"], help="page-locked output buffer kind")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU wall time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nuts", action="store_true")
@@ -549,9 +765,18 @@ def main():
     ap.add_argument("--gather-draws", type=int, default=20000, help="draws per GPU in the all-gather leg")
     ap.add_argument("--nuts-chains", type=int, default=65536, help="chains per GPU in the NUTS leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--c5-chains", type=int, default=1024, help="total NUTS chains of --workload c5 (over all GPUs)")
+    ap.add_argument("--c5-warmup", type=int, default=150)
+    ap.add_argument("--c5-samples", type=int, default=50)
+    ap.add_argument("--c5-tree-depth", type=int, default=7)
+    ap.add_argument("--c5-predictive", type=int, default=2048, help="posterior-predictive draws over all GPUs")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 2 if args.workload == "c5" else 100
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

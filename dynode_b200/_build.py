@@ -40,7 +40,8 @@ def instance_ids():
 def _sources():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "xla_ffi_shim.cc"]
     deps += [os.path.join(INCLUDE, "dynode_b200.h"), os.path.join(INCLUDE, "dynode_b200_nuts.h"),
-             os.path.join(INCLUDE, "dynode_b200_seip.h"), os.path.join(INCLUDE, "dynode_b200_ppl.h")]
+             os.path.join(INCLUDE, "dynode_b200_seip.h"), os.path.join(INCLUDE, "dynode_b200_ppl.h"),
+             os.path.join(INCLUDE, "dynode_b200_host.h")]
     return deps
 
 
@@ -65,7 +66,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, ext
     for k in instance_ids():
         obj = os.path.join(BUILD_, f"inst_{k}.o")
         jobs.append((obj, [nvcc, *flags, f"-DDYN_INST={k}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]))
-    for unit in ("capi", "nuts_round", "seip_solver", "ppl_kernels"):
+    for unit in ("capi", "nuts_round", "seip_solver", "ppl_kernels", "host_buffers"):
         obj = os.path.join(BUILD_, f"{unit}.o")
         jobs.append((obj, [nvcc, *flags, "-c", os.path.join(CSRC, f"{unit}.cu"), "-o", obj]))
 

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "dynode_nuts_round_pre", "dynode_nuts_round_post", "dynode_seip_state_size", "dynode_seip_solve_f64",
     "dynode_bijector_f64", "dynode_bijector_vjp_f64", "dynode_site_logdensity_f64",
     "dynode_site_logdensity_vjp_f64",
+    "dynode_host_alloc", "dynode_host_free", "dynode_host_info",
 )
 
 
@@ -152,6 +153,12 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int
     L.dynode_probe_hbm_write.argtypes = [vp, i64, vp]
+    L.dynode_host_alloc.restype = ctypes.c_int
+    L.dynode_host_alloc.argtypes = [ctypes.c_size_t, u32, i32, ctypes.POINTER(vp)]
+    L.dynode_host_free.restype = ctypes.c_int
+    L.dynode_host_free.argtypes = [vp, ctypes.c_size_t, u32]
+    L.dynode_host_info.restype = i64
+    L.dynode_host_info.argtypes = [vp, ctypes.c_size_t]
     _lib = L
     return L
 

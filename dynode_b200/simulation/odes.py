@@ -359,16 +359,22 @@ def _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, s
     out_dev = initial_state[0].device
     shapes = [tuple(c.shape[1:] if state_batched else c.shape) for c in initial_state]
     n = model.state_size
-    if state_batched:
+    T = len(saveat.times)
+    ns = model.saved_size(mask)
+    cuda = torch.device("cuda", torch.cuda.current_device())
+    streamed = out_dev.type != "cuda" and ensemble and B > host_chunk
+    if streamed and state_batched:
+        # host-resident ensemble: every compartment goes up on its own (asynchronously when it is page-locked) and
+        # the state rows are assembled on the device -- no B x n concatenation on the host inside the call
+        y0 = torch.cat([c.to(cuda, dtype=torch.float64, non_blocking=True).reshape(B, -1) for c in initial_state],
+                       dim=1)
+    elif state_batched:
         y0 = torch.cat([c.reshape(B, -1).to(torch.float64) for c in initial_state], dim=1)
     else:
         y0 = torch.cat([c.reshape(-1).to(torch.float64) for c in initial_state])
     assert y0.shape[-1] == n
-    T = len(saveat.times)
-    ns = model.saved_size(mask)
-    cuda = torch.device("cuda", torch.cuda.current_device())
 
-    if out_dev.type == "cuda" or not ensemble or B <= host_chunk:
+    if not streamed:
         dev_out = out if (out is not None and out.is_cuda) else None  # e.g. a slice of a gather buffer
         ys, _, stats = engine.solve_ensemble(model, y0, params, contact, opts, saveat.times, mask, B=B,
                                              out=dev_out)
@@ -461,47 +467,56 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
                     ys=tuple(outs), stats=stats_d, result=pick(_lib.STAT_RESULT))
 
 
-def _host_pipeline(model, y0, params, contact, opts, save_ts, mask, B, T, ns, out, chunk, cuda):
-    """Host-resident ensemble: per chunk H2D(params) -> kernel -> D2H(ys), double-buffered on two
-    streams so the PCIe copy of chunk k overlaps the solve of chunk k+1."""
+def _host_pipeline(model, y0, params, contact, opts, save_ts, mask, B, T, ns, out, chunk, cuda, depth: int = 3):
+    """Host-resident ensemble.  The draws (B x (n + P) doubles, 0.4 % of the output) go up in one H2D; the kernel
+    then solves `chunk` draws at a time into a ring of `depth` device buffers while the copy engine drains the ring
+    into the page-locked output on a second stream, so the PCIe copy of chunk k overlaps the solve of chunk k+1 and
+    the link never idles.  `stats` stay on the device until the end and cross once.
+
+    The output buffer is what bounds the rate: it must be page-locked, and `hostmem.pinned_empty` backs it with
+    2 MiB huge pages (pass one as `out=` to reuse it across calls -- pinning 7.6 GB takes longer than a step)."""
+    from .. import hostmem
+
     S = model.n_strains
     n = model.state_size
     if out is None:
-        out = torch.empty((B, T, ns), dtype=torch.float64, pin_memory=True)
-    stats_h = torch.empty((B, 4), dtype=torch.int32, pin_memory=True)
+        out = hostmem.pinned_empty((B, T, ns))
     compute = torch.cuda.current_stream()
     copy = torch.cuda.Stream()
-    bufs = [torch.empty((chunk, T, ns), dtype=torch.float64, device=cuda) for _ in range(2)]
-    sbufs = [torch.empty((chunk, 4), dtype=torch.int32, device=cuda) for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    ts_dev = save_ts  # host grid: the engine caches its device copy and detects the uniform pattern
+    depth = max(2, int(depth))
+    bufs = [torch.empty((chunk, T, ns), dtype=torch.float64, device=cuda) for _ in range(depth)]
+    stats_d = torch.empty((B, 4), dtype=torch.int32, device=cuda)
+    free = [torch.cuda.Event() for _ in range(depth)]
+    done = [torch.cuda.Event() for _ in range(depth)]
     contact_dev = None if contact is None else contact.to(cuda)
 
-    def rows(t, row, lo, hi):
+    def up(t, row):  # whole-ensemble H2D of one input (pinned inputs copy asynchronously)
         if t is None:
-            return None
-        if t.numel() == row:
-            return t.to(cuda, non_blocking=True)
-        return t.reshape(B, row)[lo:hi].to(cuda, non_blocking=True)
+            return None, False
+        d = t if t.is_cuda else t.to(cuda, non_blocking=True)
+        return (d, False) if t.numel() == row else (d.reshape(B, row), True)
+
+    p_dev = {name: up(t, S if name in ("beta", "gamma", "sigma", "omega") else 1) for name, t in params.items()}
+    y_dev, y_batched = up(y0, n)
 
     k = 0
     for lo in range(0, B, chunk):
         hi = min(B, lo + chunk)
-        j = k % 2
-        if k >= 2:
+        j = k % depth
+        if k >= depth:
             compute.wait_event(free[j])  # D2H of the chunk that used this buffer has finished
-        p = {name: rows(t, S if name in ("beta", "gamma", "sigma", "omega") else 1, lo, hi)
-             for name, t in params.items()}
-        y = rows(y0, n, lo, hi)
-        engine.solve_ensemble(model, y, p, contact_dev, opts, ts_dev, mask, out=bufs[j][: hi - lo],
-                              stats_out=sbufs[j][: hi - lo], B=hi - lo)
+        p = {name: (None if d is None else (d[lo:hi] if batched else d)) for name, (d, batched) in p_dev.items()}
+        y = y_dev[lo:hi] if y_batched else y_dev
+        engine.solve_ensemble(model, y, p, contact_dev, opts, save_ts, mask, out=bufs[j][: hi - lo],
+                              stats_out=stats_d[lo:hi], B=hi - lo)
         done[j].record(compute)
         copy.wait_event(done[j])
         with torch.cuda.stream(copy):
             out[lo:hi].copy_(bufs[j][: hi - lo], non_blocking=True)
-            stats_h[lo:hi].copy_(sbufs[j][: hi - lo], non_blocking=True)
             free[j].record(copy)
         k += 1
+    stats_h = torch.empty((B, 4), dtype=torch.int32, pin_memory=True)
+    stats_h.copy_(stats_d, non_blocking=True)  # one D2H, after the last kernel of the compute stream
+    compute.synchronize()
     copy.synchronize()
     return out, stats_h
