@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "dynode_bijector_f64", "dynode_bijector_vjp_f64", "dynode_site_logdensity_f64",
     "dynode_site_logdensity_vjp_f64",
     "dynode_host_alloc", "dynode_host_free", "dynode_host_info",
+    "dynode_potential_pre_f64", "dynode_potential_post_f64",
 )
 
 
@@ -57,6 +58,17 @@ class SiteDesc(ctypes.Structure):
     _fields_ = [("bijector", ctypes.c_int32), ("family", ctypes.c_int32), ("a", ctypes.c_double),
                 ("b", ctypes.c_double), ("p0", ctypes.c_double), ("p1", ctypes.c_double), ("c", ctypes.c_double),
                 ("aff_loc", ctypes.c_double), ("aff_scale", ctypes.c_double)]
+
+
+PLAN_MAX_SITES, PLAN_MAX_RATES = 16, 32
+
+
+class PotentialPlan(ctypes.Structure):
+    """DynodePotentialPlan of include/dynode_b200_ppl.h."""
+
+    _fields_ = [("n_sites", ctypes.c_int32), ("n_rates", ctypes.c_int32), ("site", SiteDesc * PLAN_MAX_SITES),
+                ("rate_c", ctypes.c_double * PLAN_MAX_RATES),
+                ("rate_e", (ctypes.c_int8 * PLAN_MAX_SITES) * PLAN_MAX_RATES)]
 
 
 class Array(ctypes.Structure):
@@ -149,6 +161,12 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.dynode_site_logdensity_f64.argtypes = [SD, i64, vp, i64, vp, vp, vp]
     L.dynode_site_logdensity_vjp_f64.restype = ctypes.c_int
     L.dynode_site_logdensity_vjp_f64.argtypes = [SD, i64, vp, i64, vp, vp, vp, vp]
+    PL = ctypes.POINTER(PotentialPlan)
+    L.dynode_potential_pre_f64.restype = ctypes.c_int
+    L.dynode_potential_pre_f64.argtypes = [PL, i64, vp, i64, vp, vp, vp, vp]
+    L.dynode_potential_post_f64.restype = ctypes.c_int
+    L.dynode_potential_post_f64.argtypes = [PL, i64, vp, vp, vp, vp, i64, ctypes.POINTER(i32), vp, vp, i64,
+                                            ctypes.POINTER(i32), vp, vp, vp, vp, vp]
     L.dynode_probe_dfma.restype = i64
     L.dynode_probe_dfma.argtypes = [vp, i32, vp]
     L.dynode_probe_hbm_write.restype = ctypes.c_int

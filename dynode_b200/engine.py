@@ -100,6 +100,14 @@ class only_rows:
         return False
 
 
+def current_row_mask(B: int):
+    """The active `only_rows` mask when it fits an ensemble of B rows, else None."""
+    m = _ONLY[0]
+    if m is None or not m.is_cuda or m.numel() != B or m.element_size() != 1 or not m.is_contiguous():
+        return None
+    return m
+
+
 def _row_mask(sd, B: int):
     """Point sd.only at the active context mask when it matches this launch; tells the caller to zero-fill."""
     m = _ONLY[0]
@@ -255,8 +263,9 @@ def solve_ensemble(model: FlowModel, y0, params: Dict[str, object], contact, opt
 
 def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions,
                         save_ts, obs_comp: int, obs, lp_const: float = 0.0, wrt: Sequence[int] = (),
-                        dy0=None, B: Optional[int] = None):
-    """Fused solve + Poisson-incidence log-likelihood + gradient: returns (lp[B], grad[B,P], stats)."""
+                        dy0=None, B: Optional[int] = None, zero_masked: bool = True):
+    """Fused solve + Poisson-incidence log-likelihood + gradient: returns (lp[B], grad[B,P], stats).
+    `zero_masked=False`: rows left out by an `only_rows` mask are not zero-filled (the caller never reads them)."""
     b = _Bound(model, y0, params, contact, save_ts, B, opts)
     torch = b.torch
     m = model.compartment_sizes()[obs_comp]
@@ -268,7 +277,9 @@ def poisson_loglik_grad(model: FlowModel, y0, params: Dict[str, object], contact
     # lp, grad and stats are views of ONE buffer: under a row mask (rows left out keep zeros) that is one fill
     # instead of three
     Pc = max(P, 1)
-    buf = (torch.zeros if _row_mask(sd, b.B) else torch.empty)((b.B * (Pc + 3),), dtype=torch.float64, device=b.dev)
+    masked = _row_mask(sd, b.B)
+    buf = (torch.zeros if (masked and zero_masked) else torch.empty)((b.B * (Pc + 3),), dtype=torch.float64,
+                                                                     device=b.dev)
     lp = buf[:b.B]
     grad = buf[b.B:b.B * (1 + Pc)].view(b.B, Pc)
     stats = buf[b.B * (1 + Pc):].view(torch.int32).view(b.B, 4)
@@ -299,7 +310,7 @@ def _scratch(torch, dev, name: str, numel: int):
 
 def poisson_loglik_adjoint(model: FlowModel, y0, params: Dict[str, object], contact, opts: SolverOptions, save_ts,
                            obs_comp: int, obs, lp_const: float = 0.0, with_y0_grad: bool = False,
-                           B: Optional[int] = None, cap: int = 512):
+                           B: Optional[int] = None, cap: int = 512, zero_masked: bool = True):
     """Fused solve + Poisson-incidence log-likelihood + gradient w.r.t. ALL rates (and y0) by the discrete
     adjoint: returns (lp[B], grad[B, 4*S+2] ordered (beta_s, gamma_s, sigma_s, omega_s, amp, phase),
     grad_y0[B, n] or None, stats[B, 4]).  `cap` bounds the accepted steps per trajectory that fit the
@@ -319,9 +330,11 @@ def poisson_loglik_adjoint(model: FlowModel, y0, params: Dict[str, object], cont
     vsave = _scratch(torch, b.dev, "vsave", b.B * b.T * m)
     md, sd = model.desc(), opts.desc(b.save_dt)
     if _row_mask(sd, b.B):
-        lp.zero_(); grad.zero_(); stats.zero_()
-        if g0 is not None:
-            g0.zero_()
+        stats.zero_()  # always: the overflow counter and the forward-mode fallback read the result code of every row
+        if zero_masked:
+            lp.zero_(); grad.zero_()
+            if g0 is not None:
+                g0.zero_()
     _lib.check(_lib.load().dynode_poisson_loglik_adjoint_f64(
         ctypes.byref(md), ctypes.byref(sd), b.B, b.c_y0, ctypes.byref(b.c_params), b.save_ts.data_ptr(), b.T,
         int(obs_comp), obs_t.data_ptr(), float(lp_const), lp.data_ptr(), grad.data_ptr(),

@@ -65,6 +65,7 @@ class ModelDensity:
             info["slice"] = (off, off + n)
             off += n
         self.dim = off
+        self._plan, self._plan_tried, self.plan_reason = None, False, "not compiled yet"
 
     # ------------------------------------------------------------------ packing
     def unpack(self, z: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -113,7 +114,19 @@ class ModelDensity:
         return torch.vmap(self._potential_one)(Z)
 
     def potential_and_grad(self, Z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """U [C], dU/dz [C, D] for unconstrained positions Z [C, D]: one vmapped model evaluation."""
+        """U [C], dU/dz [C, D] for unconstrained positions Z [C, D].  Models of the compiled form (constant-parameter
+        priors on scalar sites, monomial rates, one fused ODE likelihood) take three launches
+        (infer/potential_plan.py); everything else one vmapped evaluation of the Python model."""
+        if self._plan is None and not self._plan_tried and Z.is_cuda:
+            self._plan_tried = True
+            from .potential_plan import compile_plan
+            self._plan, self.plan_reason = compile_plan(self)
+        if self._plan is not None and Z.is_cuda:
+            return self._plan.potential_and_grad(Z.detach())
+        return self.potential_and_grad_composed(Z)
+
+    def potential_and_grad_composed(self, Z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same through the vmapped Python model and autograd (~35 launches for a DynODE model)."""
         Zr = Z.detach().requires_grad_(True)
         with torch.enable_grad():
             U = self.potential(Zr)

@@ -308,7 +308,10 @@ def simulate_incidence_loglik(ode, duration_days, initial_state, ode_parameters,
         ode, duration_days, initial_state, ode_parameters, solver_parameters, None, save_step,
         obs=obs_t, obs_comp=comp, lp_const=lp_const)
     lp, stats, _ = ag.PoissonLoglik.apply(y0r, theta, cfg)
-    return lp[0]
+    out = lp[0]
+    from ..infer import potential_plan  # a model being compiled remembers the solve behind its likelihood factor
+    potential_plan.record_loglik_call(cfg, y0r, theta, out)
+    return out
 
 
 def simulate_ensemble(

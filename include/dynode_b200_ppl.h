@@ -61,6 +61,43 @@ int dynode_site_logdensity_f64(const DynodeSiteDesc* site, int64_t n, const doub
 int dynode_site_logdensity_vjp_f64(const DynodeSiteDesc* site, int64_t n, const double* z, int64_t z_stride,
                                    const double* gx, const double* glp, double* gz, void* stream);
 
+/* ---- a whole model evaluation around ONE ODE launch --------------------------------------------------------
+ * numpyro's potential energy of a DynODE model (reference src/dynode/infer/inference.py:149-163 ->
+ * examples/sir_infer_parameters.py:21-59) is
+ *     U(z) = -( sum_j [ log p_j(x_j) + log|dx_j/dz_j| ]  +  log L(obs | theta(x)) ),   x_j = bijector_j(z_j)
+ * with the kernel's rates a MONOMIAL map of the constrained sites, theta_k = c_k * prod_j x_j^e_kj, e in {-1,0,1}
+ * (every get_odeparams of the reference: beta = r0 / infectious_period, gamma = 1 / infectious_period,
+ * sigma = 1 / latent_period, omega = 1 / waning_period; examples/seirs_multi_strain_age_stratified.py:187-209).
+ * Evaluated through tensor operations that is ~35 launches per gradient evaluation; here it is three:
+ *     dynode_potential_pre_f64   z -> theta, and per site x, dx/dz, d(lp_j)/dz, plus the summed prior term
+ *     dynode_poisson_loglik_*    theta -> log L, d log L / d theta        (include/dynode_b200.h)
+ *     dynode_potential_post_f64  chain rule back to z: U, dU/dz
+ * Rows with only[c] == 0 (the sampler's finished chains) are skipped by all three and come back as zeros.      */
+#define DYNODE_PLAN_MAX_SITES 16
+#define DYNODE_PLAN_MAX_RATES 32
+
+typedef struct {
+  int32_t n_sites; /* scalar latent sites = columns of z */
+  int32_t n_rates; /* columns of theta */
+  DynodeSiteDesc site[DYNODE_PLAN_MAX_SITES];
+  double rate_c[DYNODE_PLAN_MAX_RATES];
+  int8_t rate_e[DYNODE_PLAN_MAX_RATES][DYNODE_PLAN_MAX_SITES];
+} DynodePotentialPlan;
+
+/* aux row (3 * n_sites + 1 doubles): x_j, dx_j/dz_j, d(log p_j + ladj_j)/dz_j for every site, then the prior sum */
+int dynode_potential_pre_f64(const DynodePotentialPlan* plan, int64_t C, const double* z, int64_t z_stride,
+                             double* theta, double* aux, const uint8_t* only, void* stream);
+
+/* lp [C], grad [C][grad_stride] with theta column k's derivative at grad_col[k] (-1: not differentiated).
+ * A second (lp, grad, col map) triple may be given together with stats [C][4]: rows whose stats result code is
+ * DYNODE_RESULT_ADJOINT_CAPACITY take it instead (the forward-sensitivity re-evaluation of rows that overflowed the
+ * adjoint's checkpoint scratch).  Writes U [C] and dU [C][n_sites].                                             */
+int dynode_potential_post_f64(const DynodePotentialPlan* plan, int64_t C, const double* theta, const double* aux,
+                              const double* lp, const double* grad, int64_t grad_stride, const int32_t* grad_col,
+                              const double* lp_fb, const double* grad_fb, int64_t grad_fb_stride,
+                              const int32_t* grad_fb_col, const int32_t* stats, const uint8_t* only, double* U,
+                              double* dU, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

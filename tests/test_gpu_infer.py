@@ -324,3 +324,51 @@ def test_fused_site_kernel_equals_bijector_plus_log_prob():
             assert torch.allclose(a[fin], b[fin].detach(), rtol=1e-11, atol=1e-11), type(fn).__name__
     # a prior whose parameter is another site's value keeps the composed path
     assert D.fused_site(D.Normal(z0[:3], 1.0), z0[:3]) is None
+
+
+@pytest.mark.parametrize("which", ["c2", "c5"])
+def test_compiled_potential_equals_the_composed_model_evaluation(which, monkeypatch):
+    """dynode_potential_pre_f64 -> fused log-likelihood -> dynode_potential_post_f64 (three launches) against the
+    vmapped Python model + autograd (~35 launches): same potential, same gradient, with and without the sampler's row
+    mask, in forward mode and through the adjoint (incl. rows that overflow its checkpoint capacity)."""
+    from dynode_b200 import engine
+    from dynode_b200.infer import ModelDensity
+    dev = torch.device("cuda", 0)
+    if which == "c2":
+        from dynode_b200.examples import sir_infer_parameters as m
+        kw = dict(config=m.get_config(), tf=100, obs_data=m.synthetic_incidence(100).to(dev))
+    else:
+        from dynode_b200.examples import seirs_age_risk_strain as m
+        kw = dict(config=m.get_config(infer=True), tf=120, obs_data=m.synthetic_incidence(120).to(dev))
+    md = ModelDensity(m.model_fused, (), kw, device=dev)
+    g = torch.Generator(device=dev).manual_seed(11)
+    Z = md.init_to_median(1) + 0.6 * torch.randn(301, md.dim, dtype=torch.float64, device=dev, generator=g)
+    U, dU = md.potential_and_grad(Z)
+    assert md._plan is not None, md.plan_reason
+    for force in ("0", "1"):
+        monkeypatch.setenv("DYNODE_B200_ADJOINT", force)
+        if force == "1":
+            monkeypatch.setenv("DYNODE_B200_ADJOINT_CAP", "24")  # some rows overflow and take the forward fallback
+        U_c, dU_c = md.potential_and_grad_composed(Z)
+        U_p, dU_p = md._plan.potential_and_grad(Z)
+        assert torch.allclose(U_p, U_c, rtol=1e-10), (force, float((U_p - U_c).abs().max()))
+        assert torch.allclose(dU_p, dU_c, rtol=1e-7, atol=1e-8 * float(dU_c.abs().max()))
+        mask = (torch.arange(301, device=dev) % 3 != 0)
+        with engine.only_rows(mask.view(torch.uint8)):
+            U_m, dU_m = md._plan.potential_and_grad(Z)
+        assert torch.equal(U_m[mask], U_p[mask]) and torch.equal(dU_m[mask], dU_p[mask])
+        assert bool((U_m[~mask] == 0).all()) and bool((dU_m[~mask] == 0).all())
+
+
+def test_models_outside_the_compiled_form_keep_the_composed_path():
+    """The trajectory-materialising model (an observed `sample` site on diff(R), not the fused factor) is not of the
+    compiled form: the plan says why and the vmapped evaluation runs."""
+    from dynode_b200.examples import sir_infer_parameters as m
+    from dynode_b200.infer import ModelDensity
+    dev = torch.device("cuda", 0)
+    md = ModelDensity(m.model, (), dict(config=m.get_config(), tf=100, obs_data=m.synthetic_incidence(100).to(dev)),
+                      device=dev)
+    Z = md.init_to_median(5)
+    U, dU = md.potential_and_grad(Z)
+    assert md._plan is None and "fused log-likelihood" in md.plan_reason
+    assert bool(torch.isfinite(U).all()) and bool(torch.isfinite(dU).all())
