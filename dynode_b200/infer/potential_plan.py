@@ -148,7 +148,7 @@ def _trace_rates(md, x: torch.Tensor):
     return rec, tr.trace
 
 
-def compile_plan(md, n_check: int = 48, rtol: float = 1e-9):
+def compile_plan(md, n_check: int = 12, rtol: float = 1e-9):
     """PotentialPlan for `md`, or (None, reason)."""
     if md.device.type != "cuda":
         return None, "the compiled evaluation runs on a CUDA device"

@@ -128,6 +128,12 @@ def _resolve(ode, initial_state, ode_parameters, batch_size: Optional[int], stat
         model.check_supported()
     except _lib.DynodeError as e:
         raise UnsupportedODEError(str(e)) from None
+    from ..flows import verify_flow_body
+    shapes = [tuple(c.shape[1:] if state_batched else c.shape) for c in initial_state]
+    cshape = None
+    if spec.contact is not None:
+        cshape = tuple(torch.as_tensor(get_path(ode_parameters, spec.contact)).shape)
+    verify_flow_body(ode, spec, shapes, ode_parameters, G, S, cshape)
     params = {}
     for kname, path in spec.fields.items():
         params[kname] = torch.as_tensor(get_path(ode_parameters, path), dtype=torch.float64)

@@ -142,3 +142,63 @@ def test_observation_cache_sees_in_place_edits_and_devices():
     ka = _obs_key(a, "cuda:0")
     a[1] = 5.0
     assert _obs_key(a, "cuda:0") != ka
+
+
+def test_registered_bodies_are_checked_against_the_compiled_flow():
+    """`simulate` integrates the compiled flow, never the Python body: a registered function whose body computes
+    something else (an edited copy of the SIR example, a function registered under the wrong flow) must fail loudly
+    instead of silently getting the compiled equations.  The shipped examples all pass the same check."""
+    from dynode_b200.flows import verify_flow_body
+
+    @dataclass
+    class MyParams(AbstractODEParams):
+        beta: Any
+        gamma: Any
+
+    @flow_family("sir")
+    def edited_sir(t: float, state, p: MyParams):
+        s, i, r = state
+        N = s + i + r
+        new = p.beta * s * i / N * 0.5  # a user "improves" the force of infection
+        return (-new, new - p.gamma * i, p.gamma * i)
+
+    y0 = (torch.tensor([0.9]), torch.tensor([0.1]), torch.tensor([0.0]))
+    with pytest.raises(UnsupportedODEError, match="does not compute the flow 'sir'"):
+        simulate(edited_sir, 10, y0, MyParams(beta=0.3, gamma=0.1), SolverParams())
+
+    @flow_family("sir")  # frequency-dependent registration, density-dependent body
+    def wrong_flag(t: float, state, p: MyParams):
+        s, i, r = state
+        return (-p.beta * s * i, p.beta * s * i - p.gamma * i, p.gamma * i)
+
+    with pytest.raises(UnsupportedODEError, match="does not compute"):
+        simulate(wrong_flag, 10, y0, MyParams(beta=0.3, gamma=0.1), SolverParams())
+
+    @flow_family("sir")
+    def crashes(t: float, state, p: MyParams):
+        raise ZeroDivisionError("boom")
+
+    with pytest.raises(UnsupportedODEError, match="could not be evaluated"):
+        simulate(crashes, 10, y0, MyParams(beta=0.3, gamma=0.1), SolverParams())
+
+    # every shipped example body equals the flow it is registered as
+    G, S = 2, 3
+    one = lambda *sh: torch.ones(sh, dtype=torch.float64)
+    cases = [
+        (ex.sir_ode, ex.SIR_ODEParams(beta=0.3, gamma=0.1), [(1,)] * 3, 1, 1, None),
+        (ex.sir_density_ode, ex.DensitySIR_ODEParams(beta=0.3, gamma=0.1), [(1,)] * 3, 1, 1, None),
+        (ex.seirs_ode, ex.SEIRS_ODEParams(beta=0.3, gamma=0.1, sigma=0.2, omega=0.01), [(1,)] * 4, 1, 1, None),
+        (ex.seirs_ode_seasonal,
+         ex.SeasonalSEIRS_ODEParams(beta=0.3, gamma=0.1, sigma=0.2, omega=0.01,
+                                    seasonality_params=ex.SeasonalityParams(forcing_amp=0.1, forcing_phase=0.0,
+                                                                            forcing_period=365.0)),
+         [(1,)] * 4, 1, 1, None),
+        (ex.sir_age_ode, ex.AgeSIR_ODEParams(beta=0.3, gamma=0.1, contact_matrix=one(4, 4)), [(4,)] * 3, 4, 1, (4, 4)),
+        (ex.sir_age_risk_ode, ex.AgeRiskSIR_ODEParams(beta=0.3, gamma=0.1, contact_matrix=one(3, 2, 3, 2)),
+         [(3, 2)] * 3, 6, 1, (3, 2, 3, 2)),
+        (ex.seirs_multi_strain_ode,
+         ex.SEIRS_MultiStrain_ODEParams(beta=one(S), gamma=one(S), sigma=one(S), omega=one(S), contact_matrix=one(G, G)),
+         [(G,)] + [(G, S)] * 4, G, S, (G, G)),
+    ]
+    for ode, prm, shapes, g, s_, cshape in cases:
+        verify_flow_body(ode, flow_spec_of(ode), shapes, prm, g, s_, cshape)
