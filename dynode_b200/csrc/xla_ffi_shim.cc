@@ -1,15 +1,27 @@
-// xla_ffi_shim.cc -- typed XLA-FFI handlers over the C ABI of include/dynode_b200.h, so that
-// DynODE's JAX code reaches the sm_100a kernels through jax.ffi.ffi_call.
+// xla_ffi_shim.cc -- typed XLA-FFI handlers over the C ABI (include/dynode_b200*.h), so that DynODE's JAX code
+// reaches the sm_100a kernels through jax.ffi.ffi_call.
 //
-// NOT compiled in this image: the XLA FFI headers ship with jaxlib (jax.ffi.include_dir()), which is
-// absent here.  dynode_b200/_build.py builds libdynode_b200_xla.so from this file only when
-// `import jax` works.  The handlers only enqueue on the stream XLA passes in; XLA owns every buffer.
+// One handler per launch entry point of the path:
+//   DynodeSolve                 dynode_solve_f64                   diffeqsolve + SaveAt (odes.py:133-144)
+//   DynodeSolveSens             dynode_solve_sens_f64              the same with forward tangents (jvp / small-P vjp)
+//   DynodePoissonLoglikGrad     dynode_poisson_loglik_grad_f64     fused NUTS log-likelihood, forward mode
+//   DynodePoissonLoglikAdjoint  dynode_poisson_loglik_adjoint_f64  fused NUTS log-likelihood, discrete adjoint
+//   DynodeSeipSolve             dynode_seip_solve_f64              immune-history family (one CTA per trajectory)
+//   DynodeSiteLogdensity / DynodeSiteLogdensityVjp                 a latent site's bijector + prior, each way
+// Every solver handler takes `jump_ts` (SolverParams.discontinuity_points, odes.py:120-131) and `only` (row mask) as
+// trailing input buffers; a zero-element buffer means "none".  Scratch of the adjoint arrives as extra results, so XLA
+// owns and reuses it.
 //
-// Replaces, at the JAX level, diffrax.diffeqsolve(...) in reference src/dynode/simulation/odes.py:133-144
-// under jax.vmap (leading batch axis on y0 and the rate arrays).
+// The real headers ship with jaxlib (jax.ffi.include_dir()), absent from this image: dynode_b200/_build.py::
+// build_xla_shim compiles this file against them wherever `import jax` works; tests/test_xla_shim.py compiles it here
+// against tests/mock_xla (a model of the subset of xla/ffi/api/ffi.h used below that checks every handler's signature
+// against its binding), and says loudly which of the two it did.  The handlers only enqueue on the stream XLA passes
+// in; XLA owns every buffer.
 #include <cuda_runtime.h>
 
 #include "../../include/dynode_b200.h"
+#include "../../include/dynode_b200_ppl.h"
+#include "../../include/dynode_b200_seip.h"
 #include "xla/ffi/api/ffi.h"
 
 namespace ffi = xla::ffi;
@@ -17,6 +29,7 @@ namespace ffi = xla::ffi;
 namespace {
 
 using F64 = ffi::Buffer<ffi::F64>;
+using U8 = ffi::Buffer<ffi::U8>;
 using F64Out = ffi::ResultBuffer<ffi::F64>;
 using S32Out = ffi::ResultBuffer<ffi::S32>;
 
@@ -46,56 +59,164 @@ DynodeParams pack(const F64& beta, const F64& gamma, const F64& sigma, const F64
   return p;
 }
 
-ffi::Error SolveImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F64 sigma, F64 omega, F64 season,
-                     F64 contact, F64 save_ts, int32_t flow, int32_t flags, int32_t n_groups,
-                     int32_t n_strains, int64_t save_mask, double t0, double t1, double rtol, double atol,
-                     double const_dt, int64_t max_steps, double save_dt, F64Out ys, S32Out stats) {
+DynodeSolverDesc solver_desc(double t0, double t1, double rtol, double atol, double const_dt, int64_t max_steps,
+                             double save_dt, const F64& jump_ts, const U8& only) {
+  DynodeSolverDesc s{};
+  s.t0 = t0; s.t1 = t1; s.rtol = rtol; s.atol = atol; s.const_dt = const_dt; s.max_steps = max_steps;
+  s.save_dt = save_dt;
+  // the reference ignores discontinuity points in constant-step mode (odes.py:113-131)
+  const bool jumps = jump_ts.element_count() > 0 && !(const_dt > 0.0);
+  s.jump_ts = jumps ? jump_ts.typed_data() : nullptr;
+  s.n_jump = jumps ? (int32_t)jump_ts.element_count() : 0;
+  s.only = only.element_count() > 0 ? only.typed_data() : nullptr;
+  return s;
+}
+
+ffi::Error status(int rc) {
+  return rc == 0 ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInvalidArgument, dynode_last_error());
+}
+
+#define DYN_MODEL_PARAMS int32_t flow, int32_t flags, int32_t n_groups, int32_t n_strains
+#define DYN_SOLVER_PARAMS \
+  double t0, double t1, double rtol, double atol, double const_dt, int64_t max_steps, double save_dt
+#define DYN_SOLVER_ARGS t0, t1, rtol, atol, const_dt, max_steps, save_dt
+
+ffi::Error SolveImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F64 sigma, F64 omega, F64 season, F64 contact,
+                     F64 save_ts, F64 jump_ts, U8 only, DYN_MODEL_PARAMS, int64_t save_mask, DYN_SOLVER_PARAMS,
+                     F64Out ys, S32Out stats) {
   const DynodeModelDesc model{flow, flags, n_groups, n_strains};
-  const DynodeSolverDesc solver{t0, t1, rtol, atol, const_dt, max_steps, save_dt};
+  const DynodeSolverDesc solver = solver_desc(DYN_SOLVER_ARGS, jump_ts, only);
   const int64_t B = stats->dimensions()[0];
   const DynodeParams p = pack(beta, gamma, sigma, omega, season, contact, B);
-  if (dynode_solve_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
-                       (int32_t)save_ts.element_count(), (uint32_t)save_mask, ys->typed_data(),
-                       stats->typed_data(), stream) != 0)
-    return ffi::Error(ffi::ErrorCode::kInvalidArgument, dynode_last_error());
-  return ffi::Error::Success();
+  return status(dynode_solve_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
+                                 (int32_t)save_ts.element_count(), (uint32_t)save_mask, ys->typed_data(),
+                                 stats->typed_data(), stream));
+}
+
+ffi::Error SolveSensImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F64 sigma, F64 omega, F64 season,
+                         F64 contact, F64 save_ts, F64 jump_ts, U8 only, F64 dy0, ffi::Span<const int32_t> wrt,
+                         DYN_MODEL_PARAMS, int64_t save_mask, DYN_SOLVER_PARAMS, F64Out ys, F64Out dys,
+                         S32Out stats) {
+  const DynodeModelDesc model{flow, flags, n_groups, n_strains};
+  const DynodeSolverDesc solver = solver_desc(DYN_SOLVER_ARGS, jump_ts, only);
+  const int64_t B = stats->dimensions()[0];
+  const DynodeParams p = pack(beta, gamma, sigma, omega, season, contact, B);
+  return status(dynode_solve_sens_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
+                                      (int32_t)save_ts.element_count(), (uint32_t)save_mask, (int32_t)wrt.size(),
+                                      wrt.begin(), dy0.element_count() > 0 ? dy0.typed_data() : nullptr,
+                                      ys->typed_data(), dys->typed_data(), stats->typed_data(), stream));
 }
 
 ffi::Error LoglikGradImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F64 sigma, F64 omega, F64 season,
-                          F64 contact, F64 save_ts, F64 obs, F64 dy0, ffi::Span<const int32_t> wrt, int32_t flow,
-                          int32_t flags, int32_t n_groups, int32_t n_strains, int32_t obs_comp, double lp_const,
-                          double t0, double t1, double rtol, double atol, double const_dt, int64_t max_steps,
-                          double save_dt, F64Out lp, F64Out grad, S32Out stats) {
+                          F64 contact, F64 save_ts, F64 jump_ts, U8 only, F64 obs, F64 dy0,
+                          ffi::Span<const int32_t> wrt, DYN_MODEL_PARAMS, int32_t obs_comp, double lp_const,
+                          DYN_SOLVER_PARAMS, F64Out lp, F64Out grad, S32Out stats) {
   const DynodeModelDesc model{flow, flags, n_groups, n_strains};
-  const DynodeSolverDesc solver{t0, t1, rtol, atol, const_dt, max_steps, save_dt};
+  const DynodeSolverDesc solver = solver_desc(DYN_SOLVER_ARGS, jump_ts, only);
   const int64_t B = stats->dimensions()[0];
   const DynodeParams p = pack(beta, gamma, sigma, omega, season, contact, B);
-  if (dynode_poisson_loglik_grad_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
-                                     (int32_t)save_ts.element_count(), obs_comp, obs.typed_data(), lp_const,
-                                     (int32_t)wrt.size(), wrt.begin(),
-                                     dy0.element_count() > 0 ? dy0.typed_data() : nullptr, lp->typed_data(),
-                                     grad->typed_data(), stats->typed_data(), stream) != 0)
-    return ffi::Error(ffi::ErrorCode::kInvalidArgument, dynode_last_error());
-  return ffi::Error::Success();
+  return status(dynode_poisson_loglik_grad_f64(
+      &model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(), (int32_t)save_ts.element_count(), obs_comp,
+      obs.typed_data(), lp_const, (int32_t)wrt.size(), wrt.begin(),
+      dy0.element_count() > 0 ? dy0.typed_data() : nullptr, lp->typed_data(), grad->typed_data(),
+      stats->typed_data(), stream));
+}
+
+// ckpt [B][cap][n + 2] and vsave [B][T][m] are results XLA allocates (scratch); grad_y0 may be a zero-element result.
+ffi::Error LoglikAdjointImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F64 sigma, F64 omega, F64 season,
+                             F64 contact, F64 save_ts, F64 jump_ts, U8 only, F64 obs, DYN_MODEL_PARAMS,
+                             int32_t obs_comp, double lp_const, int32_t cap, DYN_SOLVER_PARAMS, F64Out lp,
+                             F64Out grad, F64Out grad_y0, S32Out stats, F64Out ckpt, F64Out vsave) {
+  const DynodeModelDesc model{flow, flags, n_groups, n_strains};
+  const DynodeSolverDesc solver = solver_desc(DYN_SOLVER_ARGS, jump_ts, only);
+  const int64_t B = stats->dimensions()[0];
+  const DynodeParams p = pack(beta, gamma, sigma, omega, season, contact, B);
+  return status(dynode_poisson_loglik_adjoint_f64(
+      &model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(), (int32_t)save_ts.element_count(), obs_comp,
+      obs.typed_data(), lp_const, lp->typed_data(), grad->typed_data(),
+      grad_y0->element_count() > 0 ? grad_y0->typed_data() : nullptr, stats->typed_data(), ckpt->typed_data(), cap,
+      vsave->typed_data(), stream));
+}
+
+ffi::Error SeipSolveImpl(cudaStream_t stream, F64 y0, F64 beta, F64 sigma, F64 gamma, F64 omega, F64 contact, F64 pop,
+                         F64 immunity, F64 save_ts, U8 only, int32_t n_ages, int32_t n_strains, int32_t n_wane,
+                         DYN_SOLVER_PARAMS, F64Out ys, S32Out stats) {
+  const DynodeSeipDesc model{n_ages, n_strains, n_wane};
+  DynodeSolverDesc solver{};
+  solver.t0 = t0; solver.t1 = t1; solver.rtol = rtol; solver.atol = atol; solver.const_dt = const_dt;
+  solver.max_steps = max_steps; solver.save_dt = save_dt;
+  solver.only = only.element_count() > 0 ? only.typed_data() : nullptr;
+  const int64_t B = stats->dimensions()[0];
+  DynodeSeipParams p{};
+  p.beta = as_array(beta, B); p.sigma = as_array(sigma, B); p.gamma = as_array(gamma, B); p.omega = as_array(omega, B);
+  p.contact = contact.typed_data(); p.pop = pop.typed_data(); p.immunity = immunity.typed_data();
+  return status(dynode_seip_solve_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
+                                      (int32_t)save_ts.element_count(), ys->typed_data(), stats->typed_data(),
+                                      stream));
+}
+
+#define DYN_SITE_PARAMS                                                                                          \
+  int32_t bijector, int32_t family, double a, double b, double p0, double p1, double c, double aff_loc, \
+      double aff_scale
+#define DYN_SITE_INIT {bijector, family, a, b, p0, p1, c, aff_loc, aff_scale}
+
+ffi::Error SiteImpl(cudaStream_t stream, F64 z, DYN_SITE_PARAMS, F64Out x, F64Out lp) {
+  const DynodeSiteDesc site DYN_SITE_INIT;
+  return status(dynode_site_logdensity_f64(&site, (int64_t)z.element_count(), z.typed_data(), 1, x->typed_data(),
+                                           lp->typed_data(), stream));
+}
+
+ffi::Error SiteVjpImpl(cudaStream_t stream, F64 z, F64 gx, F64 glp, DYN_SITE_PARAMS, F64Out gz) {
+  const DynodeSiteDesc site DYN_SITE_INIT;
+  return status(dynode_site_logdensity_vjp_f64(&site, (int64_t)z.element_count(), z.typed_data(), 1, gx.typed_data(),
+                                               glp.typed_data(), gz->typed_data(), stream));
 }
 
 }  // namespace
 
 #define DYN_MODEL_ATTRS \
   .Attr<int32_t>("flow").Attr<int32_t>("flags").Attr<int32_t>("n_groups").Attr<int32_t>("n_strains")
-#define DYN_SOLVER_ATTRS                                                                         \
-  .Attr<double>("t0").Attr<double>("t1").Attr<double>("rtol").Attr<double>("atol")                \
+#define DYN_SOLVER_ATTRS                                                                          \
+  .Attr<double>("t0").Attr<double>("t1").Attr<double>("rtol").Attr<double>("atol")                 \
       .Attr<double>("const_dt").Attr<int64_t>("max_steps").Attr<double>("save_dt")
-#define DYN_INPUTS                                                                               \
+// stream, y0, beta, gamma, sigma, omega, season, contact, save_ts, jump_ts, only
+#define DYN_INPUTS                                                                                     \
   .Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>() \
-      .Arg<F64>().Arg<F64>().Arg<F64>()
+      .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<U8>()
+#define DYN_SITE_ATTRS                                                                                       \
+  .Attr<int32_t>("bijector").Attr<int32_t>("family").Attr<double>("a").Attr<double>("b").Attr<double>("p0") \
+      .Attr<double>("p1").Attr<double>("c").Attr<double>("aff_loc").Attr<double>("aff_scale")
+#define S32 ffi::Buffer<ffi::S32>
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSolve, SolveImpl,
                               ffi::Ffi::Bind() DYN_INPUTS DYN_MODEL_ATTRS.Attr<int64_t>("save_mask")
-                                  DYN_SOLVER_ATTRS.Ret<F64>().Ret<ffi::Buffer<ffi::S32>>());
+                                  DYN_SOLVER_ATTRS.Ret<F64>().Ret<S32>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSolveSens, SolveSensImpl,
+                              ffi::Ffi::Bind() DYN_INPUTS.Arg<F64>().Attr<ffi::Span<const int32_t>>("wrt")
+                                  DYN_MODEL_ATTRS.Attr<int64_t>("save_mask") DYN_SOLVER_ATTRS.Ret<F64>()
+                                  .Ret<F64>().Ret<S32>());
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodePoissonLoglikGrad, LoglikGradImpl,
                               ffi::Ffi::Bind() DYN_INPUTS.Arg<F64>().Arg<F64>()
                                   .Attr<ffi::Span<const int32_t>>("wrt") DYN_MODEL_ATTRS.Attr<int32_t>("obs_comp")
-                                  .Attr<double>("lp_const") DYN_SOLVER_ATTRS.Ret<F64>().Ret<F64>()
-                                  .Ret<ffi::Buffer<ffi::S32>>());
+                                  .Attr<double>("lp_const") DYN_SOLVER_ATTRS.Ret<F64>().Ret<F64>().Ret<S32>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodePoissonLoglikAdjoint, LoglikAdjointImpl,
+                              ffi::Ffi::Bind() DYN_INPUTS.Arg<F64>() DYN_MODEL_ATTRS.Attr<int32_t>("obs_comp")
+                                  .Attr<double>("lp_const").Attr<int32_t>("cap") DYN_SOLVER_ATTRS.Ret<F64>()
+                                  .Ret<F64>().Ret<F64>().Ret<S32>().Ret<F64>().Ret<F64>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSeipSolve, SeipSolveImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<U8>().Attr<int32_t>("n_ages").Attr<int32_t>("n_strains")
+                                  .Attr<int32_t>("n_wane") DYN_SOLVER_ATTRS.Ret<F64>().Ret<S32>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSiteLogdensity, SiteImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>()
+                                  DYN_SITE_ATTRS.Ret<F64>().Ret<F64>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSiteLogdensityVjp, SiteVjpImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>() DYN_SITE_ATTRS.Ret<F64>());
