@@ -117,3 +117,40 @@ def test_empty_ensemble_is_a_no_op(lib):
     prm.beta = prm.gamma = arr
     assert lib.dynode_solve_f64(ctypes.byref(d), ctypes.byref(sv), 0, arr, ctypes.byref(prm), ptr, 2, 0b111,
                                 ptr, ptr, None) == 0
+
+
+def test_host_buffers_without_a_gpu(lib):
+    """include/dynode_b200_host.h: the mapping itself (2 MiB aligned, huge-page advised, first-touched in parallel)
+    needs no device when DYNODE_HOST_NO_PIN is set; registration with CUDA is exercised by the GPU tests / bench."""
+    import numpy as np
+    from dynode_b200 import hostmem
+    buf = hostmem.HostBuffer(3 * (1 << 20) + 17, hugepages=True, pin=False, threads=3)
+    assert buf.ptr % (2 << 20) == 0
+    a = buf.array((1 << 18,), np.float64)
+    a[:] = np.arange(a.size)
+    assert a[-1] == a.size - 1 and buf.huge_bytes() >= -1
+    t = buf.tensor((4, 8))
+    t.fill_(2.5)
+    assert float(t.sum()) == 80.0
+    del a, t
+    buf.free()
+    p = ctypes.c_void_p()
+    assert lib.dynode_host_alloc(0, 0, 1, ctypes.byref(p)) != 0 and b"zero bytes" in lib.dynode_last_error()
+
+
+def test_potential_plan_validation(lib):
+    from dynode_b200 import _lib
+    plan = _lib.PotentialPlan()
+    plan.n_sites, plan.n_rates = 0, 1
+    assert lib.dynode_potential_pre_f64(ctypes.byref(plan), 4, 1, 1, 1, 1, None, None) != 0
+    assert b"n_sites" in lib.dynode_last_error()
+    plan.n_sites, plan.n_rates = 2, 2
+    for j in range(2):
+        plan.site[j] = _lib.SiteDesc(0, 1, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+    plan.rate_e[0][0] = 2
+    assert lib.dynode_potential_pre_f64(ctypes.byref(plan), 4, 1, 2, 1, 1, None, None) != 0
+    assert b"exponents" in lib.dynode_last_error()
+    plan.rate_e[0][0] = 1
+    assert lib.dynode_potential_pre_f64(ctypes.byref(plan), 4, 1, 1, 1, 1, None, None) != 0  # z_stride < n_sites
+    assert lib.dynode_potential_post_f64(ctypes.byref(plan), 4, 1, 1, 1, 1, 2, None, None, None, 0, None, None, None,
+                                         1, 1, None) != 0  # missing column map
