@@ -374,3 +374,38 @@ def test_models_outside_the_compiled_form_keep_the_composed_path():
     U, dU = md.potential_and_grad(Z)
     assert md._plan is None and "fused log-likelihood" in md.plan_reason
     assert bool(torch.isfinite(U).all()) and bool(torch.isfinite(dU).all())
+
+
+def test_cuda_nuts_rounds_reproduce_the_numpy_oracle_on_a_gaussian():
+    """dynode_nuts_round_pre / _post (one thread per chain, state machines) against oracle/nuts_np.py (numpyro's
+    sequential tree building restated in numpy) on a shared random tape: same tree depth, leapfrog count and
+    divergence flag in every transition, same acceptance statistic, step size and draws."""
+    from tests.nuts_tape import compare_with_oracle
+    from tests.test_nuts_oracle import Z0, pg_batched, pg_single
+    dev = "cuda"
+    compare_with_oracle(pg_batched, pg_single, Z0, 30, 20, seed=77, max_tree_depth=6, device=dev, cuda_kernels=True,
+                        atol=1e-8)
+    compare_with_oracle(pg_batched, pg_single, Z0, 120, 40, seed=5, max_tree_depth=6, device=dev, cuda_kernels=True,
+                        atol=1e-11, adapt_step_size=False, step_size=0.5)
+    compare_with_oracle(pg_batched, pg_single, Z0[:2], 150, 30, seed=77, max_tree_depth=6, device=dev,
+                        cuda_kernels=True, atol=5e-2)
+
+
+def test_cuda_nuts_rounds_reproduce_the_numpy_oracle_on_config_2():
+    """The same on the posterior of reference examples/sir_infer_parameters.py (fused ODE log-likelihood): the CUDA
+    sampler evaluates all chains in one compiled-potential launch per round, the oracle one chain and one leapfrog at a
+    time through the same potential."""
+    from dynode_b200.examples import sir_infer_parameters as m
+    from dynode_b200.infer import ModelDensity
+    from tests.nuts_tape import compare_with_oracle
+    dev = torch.device("cuda", 0)
+    md = ModelDensity(m.model_fused, (), dict(config=m.get_config(), tf=100, obs_data=m.synthetic_incidence(100).to(dev)),
+                      device=dev)
+    z0 = md.init_to_median(3).cpu().numpy() + np.array([[0.0, 0.0], [0.3, -0.2], [-0.4, 0.1]])
+
+    def pg_single(z):
+        U, g = md.potential_and_grad(torch.as_tensor(z[None, :], device=dev))
+        return float(U[0]), g[0].cpu().numpy()
+
+    compare_with_oracle(md.potential_and_grad, pg_single, z0, 30, 15, seed=11, max_tree_depth=6, device="cuda",
+                        cuda_kernels=True, atol=1e-7)
