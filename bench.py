@@ -50,6 +50,24 @@ WORKLOADS = {
 F_RHS = {"seirs_multi_a2s3": 130, "seirs_seasonal": 18}  # flops per RHS evaluation
 
 
+def gradient_work(n, m, T, f_rhs, n_att_total, n_acc_total, B, P=0, adjoint=False):
+    """Algorithmic flops of one fused log-likelihood + gradient launch (SURVEY.md 8d "Gradient work"; DESIGN.md
+    section 4).  Per attempted step the primal costs 6 F_rhs + 70 n + 50 (stage sums 49 n, error estimate and norm
+    21 n, controller 50); nothing is saved, but the observed compartment (m elements) is evaluated by dense output at
+    the T save times (14 m + 45) and enters the Poisson term (25 m: difference, clamp, log, multiply-add).
+      forward mode, P directions: every RHS also pushes P tangents (a JVP is 2 F_rhs), the stage sums and the dense
+        output run for the tangents too; the error estimate does not:  (6 N_att + 3) F_rhs (1 + 2 P)
+        + N_att (49 n (1 + P) + 21 n + 50) + T (14 m + 45) (1 + P) + T m (25 + 2 P)
+      discrete adjoint: the primal forward sweep, then per ACCEPTED step the 6 stages are recomputed (6 F_rhs + 49 n),
+        7 vector-Jacobian products are pulled back (2 F_rhs each, + their parameter contractions ~ F_rhs each) and the
+        stage cotangents summed (49 n):  primal + N_acc (27 F_rhs + 98 n) + T m 25"""
+    primal = (6 * n_att_total + 3 * B) * f_rhs + n_att_total * (70 * n + 50) + B * T * (14 * m + 45) + B * T * m * 25
+    if adjoint:
+        return primal + n_acc_total * (27 * f_rhs + 98 * n)
+    return ((6 * n_att_total + 3 * B) * f_rhs * (1 + 2 * P) + n_att_total * (49 * n * (1 + P) + 21 * n + 50)
+            + B * T * (14 * m + 45) * (1 + P) + B * T * m * (25 + 2 * P))
+
+
 def algorithmic_work(n, p_in, T, n_saved, f_rhs, n_att_total, B):
     """SURVEY.md 8(d): flops = (6*N_att+3)*F_rhs + N_att*(70n+50) + T*(14*n_s+45);
     bytes = 8*(n+P_in) + 8*T*n_s + 16 per trajectory."""
@@ -208,7 +226,7 @@ def run_reference_c5(args):
         "note": "numpyro / JAX not installable here; CPU oracle (forward tangents + Poisson gradient) timed instead"}))
 
 
-def nuts_leg(args, dev, world, barrier):
+def nuts_leg(args, dev, world, barrier, fp64_peak_tf=None):
     """NUTS grad-evals/s (BASELINE metric 2) on config 2, per GPU and whole job.
 
     kernel: dynode_poisson_loglik_grad_f64 alone on B random unconstrained draws z ~ N(0,1)^2 mapped
@@ -261,9 +279,19 @@ def nuts_leg(args, dev, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kms = float(t.item())
     n_att = float(st[:, 3].double().mean())
+    def fp64_roofline(flops, ms):
+        if not fp64_peak_tf:
+            return None
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"bound": "fp64_fma", "achieved": ach, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak_tf, "algorithmic_flops_per_launch": flops,
+                "peak_source": "dynode_probe_dfma measured in this run"}
+
+    fl2 = gradient_work(6, 2, 101, 26, int(st[:, 3].sum()), int(st[:, 1].sum()), Bk, P=2)
     out["kernel"] = {"value": world * Bk / (kms * 1e-3), "draws_per_gpu": Bk, "ms_per_launch": kms,
                      "mean_attempted_steps": n_att,
-                     "finite_fraction": float(torch.isfinite(lp).double().mean())}
+                     "finite_fraction": float(torch.isfinite(lp).double().mean()),
+                     "roofline_fp64": fp64_roofline(fl2, kms)}
     # config 5 (age x risk x strain SEIRS + C, n = 78, six differentiated rates): kernel-level only
     try:
         from dynode_b200.examples import seirs_age_risk_strain as m5
@@ -301,13 +329,17 @@ def nuts_leg(args, dev, world, barrier):
         e1.record()
         barrier()
         ms5a = e0.elapsed_time(e1) / 3
+        att5, acc5 = int(st5[:, 3].sum()), int(st5[:, 1].sum())
         out["kernel_config5_adjoint"] = {
             "value": world * B5 / (ms5a * 1e-3), "draws_per_gpu": B5, "ms_per_launch": ms5a,
+            "roofline_fp64": fp64_roofline(gradient_work(78, 18, 121, 560, att5, acc5, B5, adjoint=True), ms5a),
             "directions": "all 12 rates (+ y0 on request) from one reverse sweep",
             "max_abs_diff_lp_vs_forward": float((lpa - lp5).abs().max()),
             "max_rel_diff_grad_vs_forward": float(((ga[:, :6] - g5).abs() / (g5.abs() + 1e-300)).max())}
         out["kernel_config5"] = {"value": world * B5 / (ms5 * 1e-3), "draws_per_gpu": B5, "ms_per_launch": ms5,
                                  "directions": 6, "tangent_groups_in_one_launch": 6,
+                                 # six single-direction work items per draw, each repeating the primal
+                                 "roofline_fp64": fp64_roofline(6 * gradient_work(78, 18, 121, 560, att5, acc5, B5, P=1), ms5),
                                  "config": "C5 age(3) x risk(2) x strain(3) SEIRS + C (n=78), 120 d, Poisson on diff(C)"}
     except Exception as exc:  # reported, not hidden: the headline NUTS numbers above do not depend on it
         out["kernel_config5"] = {"error": f"{type(exc).__name__}: {exc}"}
@@ -707,7 +739,7 @@ def run_ours(args):
     # likelihood, gradient w.r.t. r0 and the infectious period), fused kernel + many-chain sampler
     nuts = None
     if not args.no_nuts:
-        nuts = nuts_leg(args, dev, world, barrier)
+        nuts = nuts_leg(args, dev, world, barrier, fp64_peak_tf)
 
     # ---- CPU baseline on rank 0, N=1 only
     cpu = None

@@ -83,14 +83,15 @@ class PotentialPlan:
         L = _lib.load()
         C = Z.shape[0]
         dev = Z.device
-        if Z.stride(1) != 1:
+        if Z.stride(1) != 1 or (C > 1 and Z.stride(0) < self.D):
             Z = Z.contiguous()
+        z_stride = Z.stride(0) if C > 1 else self.D  # the stride of a size-1 axis is arbitrary
         stream = ctypes.c_void_p(_lib.current_stream_ptr())
         only = engine.current_row_mask(C)
         only_ptr = only.data_ptr() if only is not None else None
         theta = torch.empty((C, self.K), dtype=torch.float64, device=dev)
         aux = torch.empty((C, 3 * self.D + 1), dtype=torch.float64, device=dev)
-        _lib.check(L.dynode_potential_pre_f64(ctypes.byref(self.c_plan), C, Z.data_ptr(), Z.stride(0), theta.data_ptr(),
+        _lib.check(L.dynode_potential_pre_f64(ctypes.byref(self.c_plan), C, Z.data_ptr(), z_stride, theta.data_ptr(),
                                               aux.data_ptr(), only_ptr, stream))
         opts = cfg.opts()
         params = ag._kernel_params(cfg, theta)
