@@ -82,12 +82,16 @@ class Params(ctypes.Structure):
 
 
 class SeipDesc(ctypes.Structure):
-    _fields_ = [("n_ages", ctypes.c_int32), ("n_strains", ctypes.c_int32), ("n_wane", ctypes.c_int32)]
+    _fields_ = [("n_ages", ctypes.c_int32), ("n_strains", ctypes.c_int32), ("n_wane", ctypes.c_int32),
+                ("n_vax", ctypes.c_int32), ("n_knots", ctypes.c_int32)]
 
 
 class SeipParams(ctypes.Structure):
     _fields_ = [("beta", Array), ("sigma", Array), ("gamma", Array), ("omega", Array),
-                ("contact", ctypes.c_void_p), ("pop", ctypes.c_void_p), ("immunity", ctypes.c_void_p)]
+                ("contact", ctypes.c_void_p), ("pop", ctypes.c_void_p), ("immunity", ctypes.c_void_p),
+                ("vax_base", ctypes.c_void_p), ("vax_knots", ctypes.c_void_p), ("vax_coef", ctypes.c_void_p),
+                ("intro_time", Array), ("intro_scale", Array), ("intro_pct", Array),
+                ("intro_ages", ctypes.c_void_p), ("season_tau", ctypes.c_double), ("season_on", ctypes.c_double)]
 
 
 NUTS_ADAPT, NUTS_WELFORD, NUTS_SAMPLING, NUTS_END_SLOW, NUTS_END_WARMUP = 1, 2, 4, 8, 16  # DYNODE_NUTS_*

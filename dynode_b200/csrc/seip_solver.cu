@@ -25,11 +25,16 @@ constexpr int kSeipThreads = 128;
 
 struct SeipArgs {
   int A, K, W, H, n;
+  int V, NK;  // vaccination tiers, spline knots
   int64_t B;
   DynodeArray y0, beta, sigma, gamma, omega;
+  DynodeArray itime, iscale, ipct;  // external introductions per strain (ptr NULL = none)
   const double* contact;
   const double* pop;
   const double* imm;
+  const double *vbase, *vknot, *vcoef;  // vaccination-rate splines [A][V][4 | NK | NK] (vbase NULL = no vaccination)
+  const double* iages;                  // [K][A]
+  double season_tau, season_on;
   double t0, t1, rtol, atol, const_dt, save_dt;
   const double* save_ts;
   int T;
@@ -41,6 +46,7 @@ struct SeipArgs {
 struct Smem {
   double *y, *ys, *f[7];
   double *itot, *foi, *beta, *sigma, *gamma, *omega, *contact, *pop, *imm, *red;
+  double *rate, *vbase, *vknot, *vcoef, *iages, *itime, *iscale, *ipct;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -56,20 +62,50 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// dx = f(x): all threads call it; x and dx are shared-memory arrays of n doubles.  KT / WT > 0 fix the number
+// dx = f(t, x): all threads call it; x and dx are shared-memory arrays of n doubles.  KT / WT > 0 fix the number
 // of strains / waning stages at compile time (loops unrolled, index arithmetic folded); 0 = runtime value.
+// Term by term oracle/dynode_oracle.cpp FAM_SEIPV (V = 1 without splines / introductions is FAM_SEIP), same
+// summation order.
 template <int KT, int WT>
-__device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, const double* x, double* dx) {
-  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H;
+__device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, double t, const double* x, double* dx) {
+  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H, V = a.V, NK = a.NK;
+  const int nS = A * H * V * W, nX = A * H * V * K;
   const double* xS = x;
-  const double* xE = x + A * H * W;
-  const double* xI = xE + A * H * K;
+  const double* xE = x + nS;
+  const double* xI = xE + nX;
   for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
     const int ag = q / K, k = q - ag * K;
-    double acc = xI[(ag * H + 0) * K + k];
-#pragma unroll
-    for (int j = 1; j < H; ++j) acc += xI[(ag * H + j) * K + k];
-    sm.itot[q] = acc / sm.pop[ag];  // infectious fraction of age group ag for strain k (divided once, not per target)
+    double acc = 0.0;
+    for (int jv = 0; jv < H * V; ++jv) acc += xI[(ag * H * V + jv) * K + k];
+    double fr = acc / sm.pop[ag];  // infectious fraction of age group ag for strain k (divided once, not per target)
+    if (a.ipct.ptr && sm.ipct[k] != 0.0) {  // external introductions: Gaussian in time (ode_model.md:183)
+      const double zs = (t - sm.itime[k]) / sm.iscale[k];
+      const double pdf = exp(-0.5 * zs * zs) / (sm.iscale[k] * 2.5066282746310002);
+      fr += pdf * sm.ipct[k] * sm.iages[k * A + ag];
+    }
+    sm.itot[q] = fr;
+  }
+  for (int q = threadIdx.x; q < A * V; q += blockDim.x) {
+    // vaccination rate out of tier v of age group ag: min(nu(t) pop / sum_{j,w} S, 1)  (ode_model.md:19-29)
+    const int ag = q / V, v = q - ag * V;
+    double r = 0.0;
+    if (a.vbase) {
+      const double* bs = sm.vbase + q * 4;
+      double nu = bs[0] + bs[1] * t + bs[2] * t * t + bs[3] * t * t * t;
+      for (int i = 0; i < NK; ++i) {
+        const double d = t - sm.vknot[q * NK + i];
+        if (d > 0.0) nu += sm.vcoef[q * NK + i] * d * d * d;
+      }
+      if (!(nu > 0.0)) nu = 0.0;
+      double tot = 0.0;
+      for (int j = 0; j < H; ++j)
+        for (int w = 0; w < W; ++w) tot += xS[((ag * H + j) * V + v) * W + w];
+      if (nu > 0.0 && tot > 0.0) {
+        r = (nu * sm.pop[ag]) / tot;
+        if (!(r < 1.0)) r = 1.0;
+      }
+    }
+    sm.rate[q] = r;
   }
   __syncthreads();
   for (int q = threadIdx.x; q < A * K; q += blockDim.x) {
@@ -79,18 +115,38 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
     sm.foi[q] = sm.beta[k] * acc;
   }
   __syncthreads();
-  // one thread per (age, history) cell group: the W x K exposure terms are formed once and feed dS (summed over
-  // strains), dE and dC (summed over waning stages) -- the loop body of oracle FAM_SEIP, same summation order
+  double phi = 0.0;  // seasonal reset of the top tier (ode_model.md:72-75)
+  if (a.season_on != 0.0 && V >= 2) {
+    const double sn = sin(2.0 * 3.14159265358979323846 * (t + a.season_tau) / 730.0);
+    phi = a.season_on * pow(sn * sn, 500.0);
+  }
+  // one thread per (age, history, tier) cell group: the W x K exposure terms are formed once and feed dS (summed over
+  // strains), dE and dC (summed over waning stages)
   constexpr int KMAX = KT ? KT : DYNODE_SEIP_MAX_STRAINS;
   double* dS = dx;
-  double* dE = dx + A * H * W;
-  double* dI = dE + A * H * K;
-  double* dC = dI + A * H * K;
-  for (int cell = threadIdx.x; cell < A * H; cell += blockDim.x) {
-    const int ag = cell / H, j = cell - ag * H;
+  double* dE = dx + nS;
+  double* dI = dE + nX;
+  double* dC = dI + nX;
+  for (int cell = threadIdx.x; cell < A * H * V; cell += blockDim.x) {
+    const int ag = cell / (H * V), jv = cell - ag * H * V, j = jv / V, v = jv - j * V;
+    const bool top = v == V - 1;
+    const double rv = sm.rate[ag * V + v];
     double expo[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) expo[k] = 0.0;
+    double vin = 0.0;  // vaccinated into this cell's stage 0: from the tier below, and boosters within the top tier
+    if (v >= 1) {
+      double below = 0.0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) below += xS[(cell - 1) * W + w];
+      vin += sm.rate[ag * V + v - 1] * below;
+    }
+    if (top) {
+      double older = 0.0;
+#pragma unroll
+      for (int w = 1; w < W; ++w) older += xS[cell * W + w];
+      vin += rv * older;
+    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       const double s = xS[cell * W + w];
@@ -98,7 +154,7 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-          const double xk = sm.foi[ag * K + k] * (1.0 - sm.imm[(j * W + w) * K + k]) * s;
+          const double xk = sm.foi[ag * K + k] * (1.0 - sm.imm[(jv * W + w) * K + k]) * s;
           expo[k] += xk;
           out += xk;
         }
@@ -110,7 +166,13 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
           if (k < K && ((j >> k) & 1))
-            d += sm.gamma[k] * (xI[cell * K + k] + xI[(ag * H + (j ^ (1 << k))) * K + k]);
+            d += sm.gamma[k] * (xI[cell * K + k] + xI[((ag * H + (j ^ (1 << k))) * V + v) * K + k]);
+      }
+      if (!(top && w == 0)) d -= rv * s;
+      if (w == 0) d += vin;
+      if (phi != 0.0) {
+        if (top) d -= phi * s;
+        if (v == V - 2) d += phi * xS[(cell + 1) * W + w];
       }
       dS[cell * W + w] = d;
     }
@@ -118,8 +180,14 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, cons
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
         const int q = cell * K + k;
-        dE[q] = expo[k] - sm.sigma[k] * xE[q];
-        dI[q] = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
+        double de = expo[k] - sm.sigma[k] * xE[q];
+        double di = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
+        if (phi != 0.0) {
+          if (top) { de -= phi * xE[q]; di -= phi * xI[q]; }
+          if (v == V - 2) { de += phi * xE[q + K]; di += phi * xI[q + K]; }
+        }
+        dE[q] = de;
+        dI[q] = di;
         dC[q] = expo[k];
       }
     }
@@ -145,8 +213,16 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   sm.omega = p; p += W;
   sm.contact = p; p += A * A;
   sm.pop = p; p += A;
-  sm.imm = p; p += H * W * K;
+  sm.imm = p; p += H * a.V * W * K;
   sm.red = p; p += 8;
+  sm.rate = p; p += A * a.V;
+  sm.vbase = p; p += A * a.V * 4;
+  sm.vknot = p; p += A * a.V * a.NK;
+  sm.vcoef = p; p += A * a.V * a.NK;
+  sm.iages = p; p += K * A;
+  sm.itime = p; p += K;
+  sm.iscale = p; p += K;
+  sm.ipct = p; p += K;
 
   const int64_t traj = blockIdx.x;
   const int tid = threadIdx.x;
@@ -159,7 +235,19 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   for (int q = tid; q < W; q += blockDim.x) sm.omega[q] = a.omega.ptr[traj * a.omega.batch_stride + q];
   for (int q = tid; q < A * A; q += blockDim.x) sm.contact[q] = a.contact[q];
   for (int q = tid; q < A; q += blockDim.x) sm.pop[q] = a.pop[q];
-  for (int q = tid; q < H * W * K; q += blockDim.x) sm.imm[q] = a.imm[q];
+  for (int q = tid; q < H * a.V * W * K; q += blockDim.x) sm.imm[q] = a.imm[q];
+  if (a.vbase) {
+    for (int q = tid; q < A * a.V * 4; q += blockDim.x) sm.vbase[q] = a.vbase[q];
+    for (int q = tid; q < A * a.V * a.NK; q += blockDim.x) { sm.vknot[q] = a.vknot[q]; sm.vcoef[q] = a.vcoef[q]; }
+  }
+  if (a.ipct.ptr) {
+    for (int q = tid; q < K; q += blockDim.x) {
+      sm.itime[q] = a.itime.ptr[traj * a.itime.batch_stride + q];
+      sm.iscale[q] = a.iscale.ptr[traj * a.iscale.batch_stride + q];
+      sm.ipct[q] = a.ipct.ptr[traj * a.ipct.batch_stride + q];
+    }
+    for (int q = tid; q < K * A; q += blockDim.x) sm.iages[q] = a.iages[q];
+  }
   for (int e = tid; e < n; e += blockDim.x) sm.y[e] = a.y0.ptr[traj * a.y0.batch_stride + e];
   __syncthreads();
 
@@ -172,7 +260,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   };
 
   // ---- FSAL f0 and the initial step (Hairer-Wanner, PIDController._select_initial_step)
-  seip_rhs<KT, WT>(a, sm, sm.y, sm.f[0]);
+  seip_rhs<KT, WT>(a, sm, a.t0, sm.y, sm.f[0]);
   double tprev = a.t0, tnext;
   if (a.const_dt > 0.0) {
     tnext = a.t0 + a.const_dt;
@@ -190,7 +278,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
     for (int e = tid; e < n; e += blockDim.x) sm.ys[e] = sm.y[e] + h0 * sm.f[0][e];
     __syncthreads();
-    seip_rhs<KT, WT>(a, sm, sm.ys, sm.f[1]);
+    seip_rhs<KT, WT>(a, sm, a.t0 + h0, sm.ys, sm.f[1]);
     double p2 = 0.0;
     for (int e = tid; e < n; e += blockDim.x) {
       const double sc = atol + fabs(sm.y[e]) * rtol;
@@ -220,7 +308,9 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
         sm.ys[e] = fma(h, acc, sm.y[e]);
       }
       __syncthreads();
-      seip_rhs<KT, WT>(a, sm, sm.ys, sm.f[s]);  // autonomous right-hand side: no stage times needed
+      // stage times tprev + c_s h; the two c = 1 stages use tnext itself
+      const double ts = s >= 5 ? tnext : fma(kTab[I_c2 + (s - 1)], h, tprev);
+      seip_rhs<KT, WT>(a, sm, ts, sm.ys, sm.f[s]);
     };
     stage(std::integral_constant<int, 1>{});
     stage(std::integral_constant<int, 2>{});
@@ -297,8 +387,9 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   }
 }
 
-size_t seip_smem_bytes(int A, int K, int W, int H, int n) {
-  const size_t doubles = (size_t)9 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * W * K + 8;
+size_t seip_smem_bytes(int A, int K, int W, int H, int V, int NK, int n) {
+  const size_t doubles = (size_t)9 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * V * W * K + 8 +
+                         (size_t)A * V * (5 + 2 * NK) + (size_t)K * A + 3 * K;
   return doubles * sizeof(double);
 }
 
@@ -311,8 +402,9 @@ extern "C" {
 
 int dynode_seip_state_size(const DynodeSeipDesc* m) {
   if (!m || m->n_ages < 1 || m->n_strains < 1 || m->n_strains > DYNODE_SEIP_MAX_STRAINS || m->n_wane < 1) return -1;
-  const int H = 1 << m->n_strains;
-  return m->n_ages * H * (m->n_wane + 3 * m->n_strains);
+  if (m->n_vax < 0 || m->n_vax > 64 || m->n_knots < 0 || m->n_knots > 64) return -1;
+  const int H = 1 << m->n_strains, V = m->n_vax > 0 ? m->n_vax : 1;
+  return m->n_ages * H * V * (m->n_wane + 3 * m->n_strains);
 }
 
 int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* sv, int64_t B, DynodeArray y0,
@@ -338,15 +430,23 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   if (B == 0) return 0;
   SeipArgs a;
   a.A = model->n_ages; a.K = model->n_strains; a.W = model->n_wane; a.H = 1 << a.K; a.n = n;
+  a.V = model->n_vax > 0 ? model->n_vax : 1;
+  a.NK = model->n_knots;
   a.B = B;
   a.y0 = y0; a.beta = p->beta; a.sigma = p->sigma; a.gamma = p->gamma; a.omega = p->omega;
   a.contact = p->contact; a.pop = p->pop; a.imm = p->immunity;
+  a.vbase = p->vax_base; a.vknot = p->vax_knots; a.vcoef = p->vax_coef;
+  if (a.vbase && a.NK > 0 && (!a.vknot || !a.vcoef)) return fail_msg("vax_knots / vax_coef are required with n_knots > 0");
+  a.itime = p->intro_time; a.iscale = p->intro_scale; a.ipct = p->intro_pct; a.iages = p->intro_ages;
+  if (a.ipct.ptr && (!a.itime.ptr || !a.iscale.ptr || !a.iages))
+    return fail_msg("intro_time / intro_scale / intro_ages are required with intro_pct");
+  a.season_tau = p->season_tau; a.season_on = p->season_on;
   a.t0 = sv->t0; a.t1 = sv->t1; a.rtol = sv->rtol; a.atol = sv->atol; a.const_dt = sv->const_dt;
   a.save_dt = sv->save_dt > 0.0 ? sv->save_dt : 0.0;
   a.save_ts = save_ts; a.T = T;
   a.max_steps = (int)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.ys = ys; a.stats = stats;
-  const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, n);
+  const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, a.V, a.NK, n);
   // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
   void (*kern)(const SeipArgs) = seip_solver_kernel<0, 0>;
 #define SEIP_CASE(KK, WW) if (a.K == KK && a.W == WW) kern = seip_solver_kernel<KK, WW>;

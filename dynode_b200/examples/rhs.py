@@ -173,27 +173,80 @@ class SEIP_ODEParams(AbstractODEParams):
     omega: Any  # (wane,) waning rates, the last stage absorbs
     contact_matrix: Any  # (age, age)
     population: Any  # (age,)
-    immunity: Any  # (2^strains, wane, strains) protection in [0, 1]
+    immunity: Any  # (2^strains, [vax,] wane, strains) protection in [0, 1]
+    # vaccination (reference utils/splines.py:72-109): nu[age][vax](t) = cubic spline, proportion of the age group per day
+    vax_base: Any = None  # (age, vax, 4)   a + b t + c t^2 + d t^3
+    vax_knots: Any = None  # (age, vax, knots)
+    vax_coef: Any = None  # (age, vax, knots)  coefficient of (t - knot)^3 for t > knot
+    # external introductions (reference config/strains.py:59-109)
+    intro_time: Any = None  # (strains,) day of the peak
+    intro_scale: Any = None  # (strains,) standard deviation in days
+    intro_pct: Any = None  # (strains,) external population relative to the tracked one (0 = none)
+    intro_ages: Any = None  # (strains, age) age structure of the external population
+    season_tau: Any = None  # seasonal reset of the top vaccination tier: phi(t) = sin(2 pi (t + tau) / 730)^1000
+
+
+def evaluate_cubic_spline(t, knot_locations, base_equations, knot_coefficients):
+    """reference utils/splines.py:72-109: base cubic + sum_i coef_i (t - knot_i)^3 [t > knot_i]."""
+    t = torch.as_tensor(t, dtype=torch.float64)
+    powers = torch.stack([torch.ones_like(t), t, t ** 2, t ** 3])
+    base = (base_equations * powers).sum(-1)
+    d = torch.clamp(t - knot_locations, min=0.0)
+    return base + (d ** 3 * knot_coefficients).sum(-1)
 
 
 @flow_family("seip", sigma="sigma", omega="omega", contact="contact_matrix", population="population",
              immunity="immunity")
 def seip_ode(t: float, state: CompartmentState, p: SEIP_ODEParams):
-    """S (age, hist, wane); E, I, C (age, hist, strain); hist = bit set of strains recovered from."""
+    """S (age, hist, [vax,] wane); E, I, C (age, hist, [vax,] strain); hist = bit set of strains recovered from.
+    The equations are this repository's reading of reference ode_model.md:15-53 (stated term by term in
+    oracle/dynode_oracle.cpp FAM_SEIPV, of which this is the vectorised twin)."""
     s, e, i, c = state
+    flat = s.dim() == 3  # no vaccination dimension
+    if flat:
+        s, e, i = s.unsqueeze(2), e.unsqueeze(2), i.unsqueeze(2)
+    imm = p.immunity if p.immunity.dim() == 4 else p.immunity.unsqueeze(1)
+    A, H, V, W = s.shape
     K = e.shape[-1]
-    foi = p.beta * (p.contact_matrix @ (i.sum(1) / p.population[:, None]))  # (age, strain)
-    expo = foi[:, None, None, :] * (1.0 - p.immunity)[None] * s[..., None]  # (age, hist, wane, strain)
+    frac = i.sum((1, 2)) / p.population[:, None]  # (age, strain)
+    if p.intro_pct is not None:
+        z = (t - p.intro_time) / p.intro_scale
+        pdf = torch.exp(-0.5 * z * z) / (p.intro_scale * math.sqrt(2.0 * math.pi))
+        frac = frac + (pdf * p.intro_pct)[None, :] * p.intro_ages.T
+    foi = p.beta * (p.contact_matrix @ frac)  # (age, strain)
+    expo = foi[:, None, None, None, :] * (1.0 - imm)[None] * s[..., None]  # (age, hist, vax, wane, strain)
     ds = -expo.sum(-1)
     ds[..., 1:] += p.omega[:-1] * s[..., :-1]
     ds[..., :-1] -= p.omega[:-1] * s[..., :-1]
-    for j in range(s.shape[1]):
+    for j in range(H):
         for k in range(K):
             if (j >> k) & 1:
-                ds[:, j, 0] += p.gamma[k] * (i[:, j, k] + i[:, j ^ (1 << k), k])
-    de = expo.sum(2) - p.sigma * e
+                ds[:, j, :, 0] += p.gamma[k] * (i[:, j, :, k] + i[:, j ^ (1 << k), :, k])
+    if p.vax_base is not None:
+        nu = torch.clamp(evaluate_cubic_spline(t, p.vax_knots, p.vax_base, p.vax_coef), min=0.0)  # (age, vax)
+        tot = s.sum((1, 3))
+        ok = (nu > 0) & (tot > 0)
+        rate = torch.where(ok, torch.clamp(nu * p.population[:, None] / torch.where(ok, tot, torch.ones_like(tot)),
+                                           max=1.0), torch.zeros_like(tot))
+        out = rate[:, None, :, None] * s
+        out[:, :, V - 1, 0] = 0.0  # a dose in the top tier moves stages >= 1 back to stage 0; stage 0 stays
+        ds = ds - out
+        vin = torch.zeros((A, H, V), dtype=s.dtype)
+        vin[:, :, 1:] += rate[:, None, :-1] * s[:, :, :-1, :].sum(-1)
+        vin[:, :, V - 1] += rate[:, None, V - 1] * s[:, :, V - 1, 1:].sum(-1)
+        ds[..., 0] += vin
+    de = expo.sum(3) - p.sigma * e
     di = p.sigma * e - p.gamma * i
-    return (ds, de, di, expo.sum(2))
+    if p.season_tau is not None and V >= 2:
+        phi = torch.sin(torch.as_tensor(2.0 * math.pi * (t + p.season_tau) / 730.0, dtype=torch.float64)) ** 1000
+        for d_, x in ((ds, s), (de, e), (di, i)):
+            top = x[:, :, V - 1].clone()
+            d_[:, :, V - 1] -= phi * top
+            d_[:, :, V - 2] += phi * top
+    dc = expo.sum(3)
+    if flat:
+        ds, de, di, dc = ds.squeeze(2), de.squeeze(2), di.squeeze(2), dc.squeeze(2)
+    return (ds, de, di, dc)
 
 
 __all__ = [n for n in dir() if not n.startswith("_") and n not in ("SimpleNamespace",)]

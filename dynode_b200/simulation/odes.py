@@ -428,12 +428,20 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
     if len(initial_state) != 4:
         raise UnsupportedODEError("flow 'seip' integrates compartments (s, e, i, c)")
     shapes = [tuple(c.shape[1:] if state_batched else c.shape) for c in initial_state]
-    if len(shapes[0]) != 3 or len(shapes[1]) != 3 or shapes[1] != shapes[2] or shapes[1] != shapes[3] \
-            or shapes[0][:2] != shapes[1][:2] or shapes[0][1] != (1 << shapes[1][2]):
-        raise UnsupportedODEError("flow 'seip' needs s (ages, 2^strains, wane) and e, i, c (ages, 2^strains, strains)")
-    A, H, W = shapes[0]
-    K = shapes[1][2]
-    model = seip.SeipModel(A, K, W)
+    nd = len(shapes[0])
+    if nd not in (3, 4) or len(shapes[1]) != nd or shapes[1] != shapes[2] or shapes[1] != shapes[3] \
+            or shapes[0][:-1] != shapes[1][:-1] or shapes[0][1] != (1 << shapes[1][-1]):
+        raise UnsupportedODEError("flow 'seip' needs s (ages, 2^strains, [vax,] wane) and e, i, c "
+                                  "(ages, 2^strains, [vax,] strains)")
+    A, H, W = shapes[0][0], shapes[0][1], shapes[0][-1]
+    V = shapes[0][2] if nd == 4 else 1
+    K = shapes[1][-1]
+    vb = getattr(ode_parameters, "vax_base", None)
+    NK = 0
+    if vb is not None:
+        kn = getattr(ode_parameters, "vax_knots", None)
+        NK = 0 if kn is None else int(torch.as_tensor(kn).shape[-1])
+    model = seip.SeipModel(A, K, W, V, NK)
     try:
         model.check_supported()
     except _lib.DynodeError as e:
@@ -453,8 +461,18 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
     get = lambda k: torch.as_tensor(get_path(ode_parameters, spec.fields[k]), dtype=torch.float64)
     params = {k: get(k) for k in ("beta", "sigma", "gamma", "omega")}
     saveat = build_saveat(opts.t0, duration_days, save_step, None)
+    opt = lambda name: getattr(ode_parameters, name, None)
+    vaccination = None
+    if vb is not None:
+        z = torch.zeros((A, V, 0), dtype=torch.float64)
+        vaccination = (vb, opt("vax_knots") if NK else z, opt("vax_coef") if NK else z)
+    introductions = None
+    if opt("intro_pct") is not None:
+        introductions = dict(time=opt("intro_time"), scale=opt("intro_scale"), pct=opt("intro_pct"),
+                             ages=opt("intro_ages"))
     ys, stats = seip.solve_ensemble(model, y0, params, get_path(ode_parameters, spec.contact), get("population"),
-                                    get("immunity"), opts, saveat.times, B=B)
+                                    get("immunity"), opts, saveat.times, B=B, vaccination=vaccination,
+                                    introductions=introductions, season_tau=opt("season_tau"))
     out_dev = initial_state[0].device
     st = stats if out_dev.type == "cuda" else stats.cpu()
     if throw and bool((stats[:, _lib.STAT_RESULT] != 0).any()):

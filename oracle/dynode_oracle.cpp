@@ -69,6 +69,8 @@ template <int P> inline Dual<P> operator-(const Dual<P>& b, double a) {
 template <int P> inline Dual<P> dsin(const Dual<P>& a) {
   Dual<P> r; r.v = std::sin(a.v); double c = std::cos(a.v);
   for (int p = 0; p < P; ++p) r.d[p] = c * a.d[p]; return r; }
+template <int P> inline Dual<P> dexp(const Dual<P>& a) {
+  Dual<P> r; r.v = std::exp(a.v); for (int p = 0; p < P; ++p) r.d[p] = r.v * a.d[p]; return r; }
 template <int P> inline Dual<P> dlog(const Dual<P>& a) {
   Dual<P> r; r.v = std::log(a.v); for (int p = 0; p < P; ++p) r.d[p] = a.d[p] / a.v; return r; }
 
@@ -150,6 +152,9 @@ enum Family {
   FAM_SIR_AGE_RISK = 5,      // examples/sir_age_risk_stratified.py:157-173 shared=CM[A][R][A][R]
   FAM_SEIRS_MULTISTRAIN = 6, // examples/seirs_multi_strain_age_stratified.py:213-243
                              //   theta = [beta[S], gamma[S], sigma[S], omega[S]], shared = C[A][A]
+  FAM_SEIPV = 8,             // FAM_SEIP + the vaccination dimension, spline vaccination rates, the seasonal tier
+                             //   reset and external introductions of reference ode_model.md:15-53,72-75,179-190
+                             //   (utils/splines.py:72-109, config/strains.py:59-109); see the case below
   FAM_SEIP = 7               // immune-history / waning family after reference ode_model.md:15-53,100-118,179-211
                              //   (no reference implementation exists; the equations below are this repo's
                              //   reading of the prose model, without the vaccination dimension):
@@ -159,7 +164,14 @@ enum Family {
                              //   shared [contact[A][A] (target, source), pop[A], immunity[H][W][K] in [0, 1]]
 };
 
-struct Dims { int A, R, S; };
+struct Dims { int A, R, S; int V = 1, NK = 0; };
+// FAM_SEIPV carries two more sizes than the three ints of the C interface: they ride in the upper bytes of S
+// (S = K | V << 8 | NK << 16; oracle.py::seipv_dims builds it).
+inline Dims make_dims(int fam, int A, int R, int S) {
+  Dims d{A, R, S};
+  if (fam == 8) { d.S = S & 0xff; d.V = (S >> 8) & 0xff; d.NK = (S >> 16) & 0xff; }
+  return d;
+}
 const int MAXG = 32;  // max groups (A*R)
 const int MAXS = 8;   // max strains
 
@@ -171,6 +183,7 @@ inline int state_size(int fam, Dims d) {
     case FAM_SIR_AGE_RISK: return 3 * d.A * d.R;
     case FAM_SEIRS_MULTISTRAIN: return d.A + 4 * d.A * d.S;
     case FAM_SEIP: return d.A * (1 << d.S) * (d.R + 3 * d.S);
+    case FAM_SEIPV: return d.A * (1 << d.S) * d.V * (d.R + 3 * d.S);
   }
   return -1;
 }
@@ -181,6 +194,7 @@ inline int theta_size(int fam, Dims d) {
     case FAM_SEIRS_SEASONAL: return 7;
     case FAM_SEIRS_MULTISTRAIN: return 4 * d.S;
     case FAM_SEIP: return 3 * d.S + d.R;
+    case FAM_SEIPV: return 6 * d.S + d.R;
   }
   return -1;
 }
@@ -338,6 +352,131 @@ void rhs(int fam, Dims dm, double t, const T* y, const T* th, const double* sh, 
             dC[q] = expo[k];
           }
         }
+    } break;
+    case FAM_SEIPV: {
+      // FAM_SEIP with a vaccination tier v = 0..V-1 on every cell (ode_model.md:15-53; this repository's reading
+      // where the prose is silent or does not conserve people):
+      //   state  S[A][H][V][W], E[A][H][V][K], I[A][H][V][K], C[A][H][V][K]
+      //   theta  [beta[K], sigma[K], gamma[K], omega[W], intro_time[K], intro_scale[K], intro_pct[K]]
+      //   shared [contact[A][A], pop[A], immunity[H][V][W][K], vax_base[A][V][4], vax_knots[A][V][NK],
+      //           vax_coef[A][V][NK], intro_ages[K][A], season_tau, season_on]
+      //   external introductions (ode_model.md:183, strains.py:59-109): the infectious fraction of age b for strain k
+      //     is (sum_{j,v} I[b][j][v][k] + N(t; intro_time_k, intro_scale_k) intro_pct_k intro_ages[k][b] pop[b]) / pop[b]
+      //   vaccination (ode_model.md:19-29, splines.py:72-109): nu[a][v](t) = max(0, cubic spline), the rate out of
+      //     tier v is r[a][v] = min(nu pop[a] / sum_{j,w} S[a][j][v][w], 1); S[a][j][v][w] -> S[a][j][v+1][0];
+      //     in the top tier a dose moves waning stages w >= 1 back to stage 0 (the prose adds sum_w including w = 0 to
+      //     stage 0 without removing it, which creates people; here the w = 0 term is left out of both sides)
+      //   seasonal reset (ode_model.md:32,37,43,72-75): phi(t) = season_on sin(2 pi (t + tau) / 730)^1000 moves the top
+      //     tier of S, E and I to the tier below
+      const int A = dm.A, W = dm.R, K = dm.S, H = 1 << K, V = dm.V, NK = dm.NK;
+      const int nS = A * H * V * W, nX = A * H * V * K;
+      const T* Sx = y; const T* E = y + nS; const T* I = E + nX;
+      const T* beta = th; const T* sigma = th + K; const T* gamma = th + 2 * K; const T* omega = th + 3 * K;
+      const T* itime = omega + W; const T* iscale = itime + K; const T* ipct = iscale + K;
+      const double* contact = sh; const double* pop = contact + A * A; const double* imm = pop + A;
+      const double* vbase = imm + H * V * W * K; const double* vknot = vbase + A * V * 4;
+      const double* vcoef = vknot + A * V * NK; const double* iages = vcoef + A * V * NK;
+      const double tau = iages[K * A], season_on = iages[K * A + 1];
+      std::vector<T> frac(A * K), foi(A * K), rate(A * V);
+      for (int a = 0; a < A; ++a)
+        for (int k = 0; k < K; ++k) {
+          T acc = T(0.0);
+          for (int j = 0; j < H; ++j)
+            for (int v = 0; v < V; ++v) acc = acc + I[((a * H + j) * V + v) * K + k];
+          T f = acc / T(pop[a]);
+          if (val(ipct[k]) != 0.0) {
+            const T zs = (T(t) - itime[k]) / iscale[k];
+            const T pdf = dexp(T(-0.5) * zs * zs) / (iscale[k] * 2.5066282746310002);
+            f = f + pdf * ipct[k] * iages[k * A + a];
+          }
+          frac[a * K + k] = f;
+        }
+      for (int a = 0; a < A; ++a)
+        for (int k = 0; k < K; ++k) {
+          T acc = contact[a * A + 0] * frac[0 * K + k];
+          for (int b = 1; b < A; ++b) acc = acc + contact[a * A + b] * frac[b * K + k];
+          foi[a * K + k] = beta[k] * acc;
+        }
+      for (int a = 0; a < A; ++a)
+        for (int v = 0; v < V; ++v) {
+          const double* bs = vbase + (a * V + v) * 4;
+          double nu = bs[0] + bs[1] * t + bs[2] * t * t + bs[3] * t * t * t;
+          for (int i = 0; i < NK; ++i) {
+            const double d = t - vknot[(a * V + v) * NK + i];
+            if (d > 0.0) nu += vcoef[(a * V + v) * NK + i] * d * d * d;
+          }
+          if (!(nu > 0.0)) nu = 0.0;
+          T tot = T(0.0);
+          for (int j = 0; j < H; ++j)
+            for (int w = 0; w < W; ++w) tot = tot + Sx[((a * H + j) * V + v) * W + w];
+          T r = T(0.0);
+          if (nu > 0.0 && val(tot) > 0.0) {
+            r = T(nu * pop[a]) / tot;
+            if (!(val(r) < 1.0)) r = T(1.0);
+          }
+          rate[a * V + v] = r;
+        }
+      double phi = 0.0;
+      if (season_on != 0.0 && V >= 2) {
+        const double sn = std::sin(2.0 * 3.14159265358979323846 * (t + tau) / 730.0);
+        phi = season_on * std::pow(sn * sn, 500.0);
+      }
+      T* dS = dy; T* dE = dy + nS; T* dI = dE + nX; T* dC = dI + nX;
+      for (int a = 0; a < A; ++a)
+        for (int j = 0; j < H; ++j)
+          for (int v = 0; v < V; ++v) {
+            const int cell = (a * H + j) * V + v;
+            const bool top = v == V - 1;
+            T expo[MAXS];
+            for (int k = 0; k < K; ++k) expo[k] = T(0.0);
+            // people vaccinated into this cell's stage 0: from the tier below, and boosters within the top tier
+            T vin = T(0.0);
+            if (v >= 1) {
+              T below = T(0.0);
+              for (int w = 0; w < W; ++w) below = below + Sx[(cell - 1) * W + w];
+              vin = vin + rate[a * V + v - 1] * below;
+            }
+            if (top) {
+              T older = T(0.0);
+              for (int w = 1; w < W; ++w) older = older + Sx[cell * W + w];
+              vin = vin + rate[a * V + v] * older;
+            }
+            for (int w = 0; w < W; ++w) {
+              const T s = Sx[cell * W + w];
+              T out = T(0.0);
+              for (int k = 0; k < K; ++k) {
+                T x = foi[a * K + k] * (1.0 - imm[((j * V + v) * W + w) * K + k]) * s;
+                expo[k] = expo[k] + x;
+                out = out + x;
+              }
+              T d = -out;
+              if (w > 0) d = d + omega[w - 1] * Sx[cell * W + w - 1];
+              if (w < W - 1) d = d - omega[w] * s;
+              if (w == 0)
+                for (int k = 0; k < K; ++k)
+                  if ((j >> k) & 1)
+                    d = d + gamma[k] * (I[cell * K + k] + I[((a * H + (j ^ (1 << k))) * V + v) * K + k]);
+              if (!(top && w == 0)) d = d - rate[a * V + v] * s;
+              if (w == 0) d = d + vin;
+              if (phi != 0.0) {
+                if (top) d = d - phi * s;
+                if (v == V - 2) d = d + phi * Sx[(cell + 1) * W + w];
+              }
+              dS[cell * W + w] = d;
+            }
+            for (int k = 0; k < K; ++k) {
+              const int q = cell * K + k;
+              T de = expo[k] - sigma[k] * E[q];
+              T di = sigma[k] * E[q] - gamma[k] * I[q];
+              if (phi != 0.0) {
+                if (top) { de = de - phi * E[q]; di = di - phi * I[q]; }
+                if (v == V - 2) { de = de + phi * E[q + K]; di = di + phi * I[q + K]; }
+              }
+              dE[q] = de;
+              dI[q] = di;
+              dC[q] = expo[k];
+            }
+          }
     } break;
   }
 }
@@ -533,13 +672,13 @@ int solve_batch(int fam, Dims dm, const SolveCfg& c, int64_t B, const double* y0
 
 extern "C" {
 
-int oracle_state_size(int fam, int A, int R, int S) { return state_size(fam, Dims{A, R, S}); }
-int oracle_theta_size(int fam, int A, int R, int S) { return theta_size(fam, Dims{A, R, S}); }
+int oracle_state_size(int fam, int A, int R, int S) { return state_size(fam, make_dims(fam, A, R, S)); }
+int oracle_theta_size(int fam, int A, int R, int S) { return theta_size(fam, make_dims(fam, A, R, S)); }
 
 // dy = f(t, y; theta, shared)
 int oracle_rhs(int fam, int A, int R, int S, double t, const double* y, const double* theta,
                const double* shared, double* dy) {
-  Dims dm{A, R, S};
+  Dims dm = make_dims(fam, A, R, S);
   const int n = state_size(fam, dm), nt = theta_size(fam, dm);
   if (n < 0) return 1;
   std::vector<Dual<0>> yy(n), th(nt), out(n);
@@ -568,8 +707,8 @@ int oracle_solve(int fam, int A, int R, int S, int64_t B, const double* y0, int6
                  const double* save_ts, int T, const int32_t* save_idx, int n_saved, int n_wrt,
                  const int32_t* wrt, const double* dy0, double* ys, double* dys, int32_t* stats,
                  int nthreads, const double* jump_ts, int n_jump) {
-  Dims dm{A, R, S};
-  if (state_size(fam, dm) < 0 || (fam != FAM_SEIP && A * R > MAXG) || A > MAXG || S > MAXS) return 1;
+  Dims dm = make_dims(fam, A, R, S);
+  if (state_size(fam, dm) < 0 || (fam != FAM_SEIP && fam != FAM_SEIPV && A * R > MAXG) || A > MAXG || dm.S > MAXS) return 1;
   SolveCfg c{t0, t1, rtol, atol, const_dt, max_steps, save_ts, T, save_idx, n_saved, jump_ts, n_jump};
 #define ORC_CASE(PP) case PP: return solve_batch<PP>(fam, dm, c, B, y0, y0_bs, theta, th_bs, shared, \
                                                     wrt, dy0, ys, dys, stats, nthreads);

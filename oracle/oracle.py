@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libdynode_oracle.so")
 
 # family ids (dynode_oracle.cpp enum Family)
-SIR_1BIN, SIR_DENSITY, SEIRS_1BIN, SEIRS_SEASONAL, SIR_AGE, SIR_AGE_RISK, SEIRS_MULTISTRAIN, SEIP = range(8)
+SIR_1BIN, SIR_DENSITY, SEIRS_1BIN, SEIRS_SEASONAL, SIR_AGE, SIR_AGE_RISK, SEIRS_MULTISTRAIN, SEIP, SEIPV = range(9)
 
 _lib = None
 
@@ -82,6 +82,13 @@ def _ip(a: Optional[np.ndarray]):
 
 def _c(a, dtype=np.float64) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=dtype))
+
+
+def seipv_dims(A: int, W: int, K: int, V: int, NK: int):
+    """dims tuple of FAM_SEIPV: the vaccination tiers and spline knots ride in the upper bytes of the third int
+    (dynode_oracle.cpp::make_dims)."""
+    assert 0 < K < 256 and 0 < V < 256 and 0 <= NK < 256
+    return (A, W, K | (V << 8) | (NK << 16))
 
 
 def state_size(family: int, dims=(1, 1, 1)) -> int:

@@ -556,3 +556,57 @@ def test_adjoint_capacity_overflow_falls_back_to_forward_sensitivities(monkeypat
     assert 0 < n_over < 64, n_over
     assert bool(torch.isfinite(U_a).all()) and bool(torch.isfinite(g_a).all())
     assert torch.allclose(U_a, U_f, rtol=1e-10) and torch.allclose(g_a, g_f, rtol=1e-7, atol=1e-7 * float(g_f.abs().max()))
+
+
+@pytest.mark.parametrize("A,K,W,V,NK,kw", [
+    (3, 2, 3, 3, 2, {}),                       # everything on
+    (2, 2, 4, 2, 0, dict(season=False)),       # base cubic only, no reset
+    (4, 1, 2, 4, 3, dict(intro=False)),        # one strain, four tiers
+    (2, 3, 3, 2, 1, dict(vaccinate=False)),    # tiers present but nobody is vaccinated; reset + introductions only
+    (3, 2, 3, 1, 0, dict(season=False)),       # V = 1: boosters within the single tier
+])
+def test_seip_vaccination_kernel_matches_oracle(A, K, W, V, NK, kw):
+    """The vaccination extension of the CTA-per-trajectory kernel (tiers, spline rates with the min(.,1) cap, the
+    seasonal reset, external introductions; include/dynode_b200_seip.h [V]) against oracle FAM_SEIPV: 1e-9 and the
+    same accepted / rejected step counts, directly and through `simulate_ensemble`."""
+    import torch
+    from dynode_b200 import seip
+    from dynode_b200.config import SolverParams
+    from dynode_b200.engine import SolverOptions
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate_ensemble
+    from tests.cases import make_seipv_case
+    B, t1 = 29, 180
+    case = make_seipv_case(B, A=A, K=K, W=W, V=V, NK=NK, t1=t1, **kw)
+    ts = np.linspace(0.0, t1, t1 + 1)
+    ys, st = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                 case["immunity"], SolverOptions(t1=float(t1)), ts, vaccination=case["vaccination"],
+                                 introductions=case["introductions"], season_tau=case["season_tau"])
+    torch.cuda.synchronize()
+    ref, _, rst = _run_oracle(case, t1)
+    assert np.array_equal(st.cpu().numpy(), rst) and np.all(rst[:, 0] == 0)
+    _assert_close(ys.cpu().numpy(), ref)
+    # the public API: compartments shaped (A, H, [V,] W) / (A, H, [V,] K), optional fields of SEIP_ODEParams
+    H = 1 << K
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    nS, nX = A * H * V * W, A * H * V * K
+    y0 = case["y0"]
+    shp_s, shp_x = ((A, H, V, W), (A, H, V, K)) if V > 1 else ((A, H, W), (A, H, K))
+    state = (t(y0[:nS]).reshape(shp_s), t(y0[nS:nS + nX]).reshape(shp_x), t(y0[nS + nX:nS + 2 * nX]).reshape(shp_x),
+             t(y0[nS + 2 * nX:]).reshape(shp_x))
+    prm = case["params"]
+    intro, vac = case["introductions"], case["vaccination"]
+    imm = case["immunity"] if V > 1 else case["immunity"].reshape(H, W, K)
+    p = ex.SEIP_ODEParams(
+        beta=t(prm["beta"]), sigma=t(prm["sigma"]), gamma=t(prm["gamma"]), omega=t(prm["omega"]),
+        contact_matrix=t(case["contact"]), population=t(case["pop"]), immunity=t(imm),
+        vax_base=None if vac is None else t(vac[0]), vax_knots=None if vac is None else t(vac[1]),
+        vax_coef=None if vac is None else t(vac[2]),
+        intro_time=None if intro is None else t(intro["time"]), intro_scale=None if intro is None else t(intro["scale"]),
+        intro_pct=None if intro is None else t(intro["pct"]), intro_ages=None if intro is None else t(intro["ages"]),
+        season_tau=case["season_tau"])
+    sol = simulate_ensemble(ex.seip_ode, t1, state, p, SolverParams(), batch_size=B, state_batched=False)
+    got = torch.cat([c.reshape(B, t1 + 1, -1) for c in sol.ys], dim=2).cpu().numpy()
+    assert np.array_equal(got, ys.cpu().numpy())
+    assert sol.ys[0].shape == (B, t1 + 1) + shp_s

@@ -417,3 +417,74 @@ def test_seip_family_invariants_and_two_statements_of_the_rhs():
     truth = solve_ivp(lambda tt, y: torch_rhs(y, theta[0]), (0, 200), case["y0"], method="DOP853", rtol=1e-11,
                       atol=1e-11, t_eval=np.arange(201.0)).y.T
     assert np.max(np.abs(ys[0] - truth)) < 5e-3 * np.max(np.abs(truth))
+
+
+def test_seipv_vaccination_introductions_and_seasonal_reset():
+    """The vaccination extension of the immune-history family (reference ode_model.md:15-53,72-75,183;
+    utils/splines.py:72-109; config/strains.py:59-109 -- prose only, no reference implementation): the oracle's loop
+    form equals the vectorised torch statement; without tiers / splines / introductions it IS the first version bit
+    for bit; people are conserved through vaccination and the seasonal reset; doses move people up the tiers;
+    a strain absent at t = 0 arrives through external introduction and not otherwise; the reset empties the top tier
+    into the one below; a tight DOP853 integration of the torch RHS agrees to solver tolerance."""
+    import torch
+    from scipy.integrate import solve_ivp
+    from dynode_b200.examples import rhs as ex
+    from tests.cases import make_seip_case, make_seipv_case
+    # (1) reduction to FAM_SEIP
+    base = make_seip_case(2, A=3, K=2, W=3)
+    fam, dims, theta, shared = base["oracle"]
+    A, W, K = dims
+    H = 1 << K
+    th_v = np.hstack([theta, np.zeros((2, K)), np.ones((2, K)), np.zeros((2, K))])
+    sh_v = np.concatenate([shared, np.zeros(A * 4), np.zeros(K * A), [0.0, 0.0]])
+    ys0, _, st0 = orc.solve(fam, dims, base["y0"], theta, shared, t1=120)
+    ys1, _, st1 = orc.solve(orc.SEIPV, orc.seipv_dims(A, W, K, 1, 0), base["y0"], th_v, sh_v, t1=120)
+    assert np.array_equal(ys0, ys1) and np.array_equal(st0, st1)
+    # (2) the full model
+    V, NK = 3, 2
+    case = make_seipv_case(2, A=3, K=2, W=3, V=V, NK=NK)
+    fam, dims, theta, shared = case["oracle"]
+    nS, nX = A * H * V * W, A * H * V * K
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    vb, vk, vc = case["vaccination"]
+    intro = case["introductions"]
+
+    def torch_rhs(tt, y, b=0):
+        state = (t(y[:nS]).reshape(A, H, V, W), t(y[nS:nS + nX]).reshape(A, H, V, K),
+                 t(y[nS + nX:nS + 2 * nX]).reshape(A, H, V, K), t(y[nS + 2 * nX:]).reshape(A, H, V, K))
+        prm = case["params"]
+        p = ex.SEIP_ODEParams(beta=t(prm["beta"][b]), sigma=t(prm["sigma"][b]), gamma=t(prm["gamma"][b]),
+                              omega=t(prm["omega"][b]), contact_matrix=t(case["contact"]), population=t(case["pop"]),
+                              immunity=t(case["immunity"]), vax_base=t(vb), vax_knots=t(vk), vax_coef=t(vc),
+                              intro_time=t(intro["time"][b]), intro_scale=t(intro["scale"][b]),
+                              intro_pct=t(intro["pct"][b]), intro_ages=t(intro["ages"]), season_tau=case["season_tau"])
+        return torch.cat([x.reshape(-1) for x in ex.seip_ode(tt, state, p)]).numpy()
+
+    rng = np.random.default_rng(3)
+    for tt in (0.0, 45.0, 75.0, 118.0, 121.5):
+        yr = rng.uniform(0.1, 5.0, nS + 3 * nX)
+        want = orc.rhs(fam, dims, tt, yr, theta[0], shared)
+        assert np.allclose(want, torch_rhs(tt, yr), rtol=1e-12, atol=1e-12)
+        assert abs(want[:nS + 2 * nX].sum()) < 1e-10  # vaccination, waning, recovery and the reset move people only
+    ys, _, st = orc.solve(fam, dims, case["y0"], theta, shared, t1=200)
+    assert np.all(st[:, 0] == 0)
+    people = ys[:, :, :nS + 2 * nX].sum(2)
+    assert np.allclose(people, people[:, :1], rtol=0, atol=1e-8)
+    assert ys.min() > -1e-5  # a tier emptied by the reset undershoots zero by less than the solver's atol
+    S = ys[:, :, :nS].reshape(2, 201, A, H, V, W)
+    assert np.all(S[:, 0, :, :, 1:].sum((1, 2, 3, 4)) == 0)       # nobody vaccinated at t = 0
+    assert np.all(S[:, 100, :, :, 1:].sum((1, 2, 3, 4)) > 50.0)  # doses moved people up the tiers
+    # the seasonal reset (peak at day 120) empties the top tier into the one below
+    top = S[:, :, :, :, V - 1].sum((2, 3, 4))
+    mid = S[:, :, :, :, V - 2].sum((2, 3, 4))
+    assert np.all(top[:, 110] > 100.0) and np.all(top[:, 122] < 0.05 * top[:, 110])
+    assert np.all(mid[:, 122] > mid[:, 110] + 0.8 * top[:, 110])  # ... and they arrive in the tier below
+    # strain 1 is absent at t = 0: it appears only through the external introduction
+    cum1 = ys[:, :, nS + 2 * nX:].reshape(2, 201, A, H, V, K)[..., 1].sum((2, 3, 4))
+    assert np.all(cum1[:, 30] < 1e-3) and np.all(cum1[:, -1] > 10.0)
+    quiet = make_seipv_case(2, A=3, K=2, W=3, V=V, NK=NK, intro=False)
+    yq, _, _ = orc.solve(*quiet["oracle"][:2], quiet["y0"], *quiet["oracle"][2:], t1=200)
+    assert np.all(yq[:, :, nS + 2 * nX:].reshape(2, 201, A, H, V, K)[..., 1] == 0.0)
+    truth = solve_ivp(lambda tt, y: torch_rhs(tt, y), (0, 200), case["y0"], method="DOP853", rtol=1e-10, atol=1e-10,
+                      t_eval=np.arange(201.0), max_step=0.5).y.T
+    assert np.max(np.abs(ys[0] - truth)) < 5e-3 * np.max(np.abs(truth))
