@@ -66,9 +66,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // of strains / waning stages at compile time (loops unrolled, index arithmetic folded); 0 = runtime value.
 // Term by term oracle/dynode_oracle.cpp FAM_SEIPV (V = 1 without splines / introductions is FAM_SEIP), same
 // summation order.
-template <int KT, int WT>
+// EXT = false compiles the vaccination tiers, splines, introductions and the seasonal reset out (V == 1, no tables):
+// the lean right-hand side of the first version, at its speed.
+template <int KT, int WT, bool EXT>
 __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, double t, const double* x, double* dx) {
-  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H, V = a.V, NK = a.NK;
+  const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H, V = EXT ? a.V : 1,
+            NK = EXT ? a.NK : 0;
   const int nS = A * H * V * W, nX = A * H * V * K;
   const double* xS = x;
   const double* xE = x + nS;
@@ -78,13 +81,14 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
     double acc = 0.0;
     for (int jv = 0; jv < H * V; ++jv) acc += xI[(ag * H * V + jv) * K + k];
     double fr = acc / sm.pop[ag];  // infectious fraction of age group ag for strain k (divided once, not per target)
-    if (a.ipct.ptr && sm.ipct[k] != 0.0) {  // external introductions: Gaussian in time (ode_model.md:183)
+    if (EXT && a.ipct.ptr && sm.ipct[k] != 0.0) {  // external introductions: Gaussian in time (ode_model.md:183)
       const double zs = (t - sm.itime[k]) / sm.iscale[k];
       const double pdf = exp(-0.5 * zs * zs) / (sm.iscale[k] * 2.5066282746310002);
       fr += pdf * sm.ipct[k] * sm.iages[k * A + ag];
     }
     sm.itot[q] = fr;
   }
+  if constexpr (EXT)
   for (int q = threadIdx.x; q < A * V; q += blockDim.x) {
     // vaccination rate out of tier v of age group ag: min(nu(t) pop / sum_{j,w} S, 1)  (ode_model.md:19-29)
     const int ag = q / V, v = q - ag * V;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
   }
   __syncthreads();
   double phi = 0.0;  // seasonal reset of the top tier (ode_model.md:72-75)
-  if (a.season_on != 0.0 && V >= 2) {
+  if (EXT && a.season_on != 0.0 && V >= 2) {
     const double sn = sin(2.0 * 3.14159265358979323846 * (t + a.season_tau) / 730.0);
     phi = a.season_on * pow(sn * sn, 500.0);
   }
@@ -130,11 +134,12 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
   for (int cell = threadIdx.x; cell < A * H * V; cell += blockDim.x) {
     const int ag = cell / (H * V), jv = cell - ag * H * V, j = jv / V, v = jv - j * V;
     const bool top = v == V - 1;
-    const double rv = sm.rate[ag * V + v];
+    const double rv = EXT ? sm.rate[ag * V + v] : 0.0;
     double expo[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) expo[k] = 0.0;
     double vin = 0.0;  // vaccinated into this cell's stage 0: from the tier below, and boosters within the top tier
+    if constexpr (EXT) {
     if (v >= 1) {
       double below = 0.0;
 #pragma unroll
@@ -146,6 +151,7 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
 #pragma unroll
       for (int w = 1; w < W; ++w) older += xS[cell * W + w];
       vin += rv * older;
+    }
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -168,11 +174,13 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
           if (k < K && ((j >> k) & 1))
             d += sm.gamma[k] * (xI[cell * K + k] + xI[((ag * H + (j ^ (1 << k))) * V + v) * K + k]);
       }
-      if (!(top && w == 0)) d -= rv * s;
-      if (w == 0) d += vin;
-      if (phi != 0.0) {
-        if (top) d -= phi * s;
-        if (v == V - 2) d += phi * xS[(cell + 1) * W + w];
+      if constexpr (EXT) {
+        if (!(top && w == 0)) d -= rv * s;
+        if (w == 0) d += vin;
+        if (phi != 0.0) {
+          if (top) d -= phi * s;
+          if (v == V - 2) d += phi * xS[(cell + 1) * W + w];
+        }
       }
       dS[cell * W + w] = d;
     }
@@ -182,7 +190,7 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
         const int q = cell * K + k;
         double de = expo[k] - sm.sigma[k] * xE[q];
         double di = sm.sigma[k] * xE[q] - sm.gamma[k] * xI[q];
-        if (phi != 0.0) {
+        if (EXT && phi != 0.0) {
           if (top) { de -= phi * xE[q]; di -= phi * xI[q]; }
           if (v == V - 2) { de += phi * xE[q + K]; di += phi * xI[q + K]; }
         }
@@ -195,7 +203,7 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
   __syncthreads();
 }
 
-template <int KT, int WT>
+template <int KT, int WT, bool EXT>
 __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArgs a) {
   using namespace tsit5;
   extern __shared__ double smem_raw[];
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   };
 
   // ---- FSAL f0 and the initial step (Hairer-Wanner, PIDController._select_initial_step)
-  seip_rhs<KT, WT>(a, sm, a.t0, sm.y, sm.f[0]);
+  seip_rhs<KT, WT, EXT>(a, sm, a.t0, sm.y, sm.f[0]);
   double tprev = a.t0, tnext;
   if (a.const_dt > 0.0) {
     tnext = a.t0 + a.const_dt;
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
     for (int e = tid; e < n; e += blockDim.x) sm.ys[e] = sm.y[e] + h0 * sm.f[0][e];
     __syncthreads();
-    seip_rhs<KT, WT>(a, sm, a.t0 + h0, sm.ys, sm.f[1]);
+    seip_rhs<KT, WT, EXT>(a, sm, a.t0 + h0, sm.ys, sm.f[1]);
     double p2 = 0.0;
     for (int e = tid; e < n; e += blockDim.x) {
       const double sc = atol + fabs(sm.y[e]) * rtol;
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
       __syncthreads();
       // stage times tprev + c_s h; the two c = 1 stages use tnext itself
       const double ts = s >= 5 ? tnext : fma(kTab[I_c2 + (s - 1)], h, tprev);
-      seip_rhs<KT, WT>(a, sm, ts, sm.ys, sm.f[s]);
+      seip_rhs<KT, WT, EXT>(a, sm, ts, sm.ys, sm.f[s]);
     };
     stage(std::integral_constant<int, 1>{});
     stage(std::integral_constant<int, 2>{});
@@ -448,8 +456,10 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   a.ys = ys; a.stats = stats;
   const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, a.V, a.NK, n);
   // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
-  void (*kern)(const SeipArgs) = seip_solver_kernel<0, 0>;
-#define SEIP_CASE(KK, WW) if (a.K == KK && a.W == WW) kern = seip_solver_kernel<KK, WW>;
+  const bool ext = a.V > 1 || a.vbase || a.ipct.ptr || a.season_on != 0.0;
+  void (*kern)(const SeipArgs) = ext ? seip_solver_kernel<0, 0, true> : seip_solver_kernel<0, 0, false>;
+#define SEIP_CASE(KK, WW) \
+  if (a.K == KK && a.W == WW) kern = ext ? seip_solver_kernel<KK, WW, true> : seip_solver_kernel<KK, WW, false>;
   SEIP_CASE(1, 1) SEIP_CASE(1, 2) SEIP_CASE(1, 3) SEIP_CASE(1, 4)
   SEIP_CASE(2, 1) SEIP_CASE(2, 2) SEIP_CASE(2, 3) SEIP_CASE(2, 4)
   SEIP_CASE(3, 1) SEIP_CASE(3, 2) SEIP_CASE(3, 3) SEIP_CASE(3, 4)
