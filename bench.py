@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (case name in tests/cases.py, draws per GPU, description)
+    # name: (case name in dynode_b200/synthetic.py, draws per GPU, description)
     "c4": ("seirs_multi_a2s3", 100_000,
            "C4 multi-strain age-stratified SEIRS+C (A=2,S=3,n=26), 365 d, daily SaveAt T=366"),
     "c3": ("seirs_seasonal", 1_000_000, "C3 seasonally forced SEIRS (n=4), 365 d, daily SaveAt T=366"),
@@ -122,7 +122,7 @@ class ClockSampler:
 
 
 def make_inputs(workload: str, B: int, seed: int):
-    from tests.cases import make_case
+    from dynode_b200.synthetic import make_case
     return make_case(WORKLOADS[workload][0], B, seed=seed)
 
 
@@ -193,7 +193,7 @@ def run_reference_c5(args):
     forward tangents (r0 and infectious period of three strains -> beta, gamma) plus the Poisson log-likelihood and
     its gradient, on all host threads, for `chunk` chains per step.  (numpyro itself is not installable here.)"""
     from oracle import oracle as orc
-    from tests.cases import make_case
+    from dynode_b200.synthetic import make_case
     chunk = 1024
     case = make_case("seirs_multi_g6s3", chunk, seed=20260105)
     fam, dims, theta, shared = case["oracle"]
@@ -252,7 +252,7 @@ def nuts_leg(args, dev, world, barrier, fp64_peak_tf=None):
     cons = md.constrain(Z)
     r0, inf = cons["strains_0_r0"], cons["strains_0_infectious_period"]
     from dynode_b200 import _lib, engine
-    from tests.cases import make_case
+    from dynode_b200.synthetic import make_case
     case = make_case("sir_age2", 1)
     prm = {"beta": (r0 / inf).reshape(-1, 1).contiguous(), "gamma": (1.0 / inf).reshape(-1, 1).contiguous()}
     y0 = torch.as_tensor(case["y0"], dtype=torch.float64, device=dev)

@@ -44,7 +44,7 @@ struct SeipArgs {
 };
 
 struct Smem {
-  double *y, *ys, *f[7];
+  double *ys, *dx;
   double *itot, *foi, *beta, *sigma, *gamma, *omega, *contact, *pop, *imm, *red;
   double *rate, *vbase, *vknot, *vcoef, *iages, *itime, *iscale, *ipct;
 };
@@ -203,16 +203,20 @@ __device__ __forceinline__ void seip_rhs(const SeipArgs& a, const Smem& sm, doub
   __syncthreads();
 }
 
-template <int KT, int WT, bool EXT>
+// One thread block per trajectory.  Each thread owns the elements e = tid + 128 i (i < EPT) and keeps THEIR y, the
+// stage state and the 7 stage derivatives in registers (9 EPT doubles); shared memory holds only what the block
+// exchanges: the stage state the right-hand side reads (n doubles), its output (n doubles) and the tables.  With
+// 2 n instead of 9 n doubles per trajectory an SM keeps 16 trajectories in flight instead of 7 (n = 416), the stage
+// sums / error estimate / dense output run out of registers, and saves are coalesced straight from them.
+template <int KT, int WT, bool EXT, int EPT>
 __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArgs a) {
   using namespace tsit5;
   extern __shared__ double smem_raw[];
   const int A = a.A, K = KT ? KT : a.K, W = WT ? WT : a.W, H = KT ? (1 << KT) : a.H, n = a.n;
   Smem sm;
   double* p = smem_raw;
-  sm.y = p; p += n;
-  sm.ys = p; p += n;
-  for (int i = 0; i < 7; ++i) { sm.f[i] = p; p += n; }
+  sm.ys = p; p += n;   // stage state, read by the right-hand side
+  sm.dx = p; p += n;   // its output
   sm.itot = p; p += A * K;
   sm.foi = p; p += A * K;
   sm.beta = p; p += K;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 
   const int64_t traj = blockIdx.x;
   const int tid = threadIdx.x;
-  // ---- stage the shared tables, this trajectory's rates and initial state, and the element map
+  // ---- stage the shared tables and this trajectory's rates
   for (int q = tid; q < K; q += blockDim.x) {
     sm.beta[q] = a.beta.ptr[traj * a.beta.batch_stride + q];
     sm.sigma[q] = a.sigma.ptr[traj * a.sigma.batch_stride + q];
@@ -256,8 +260,28 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     }
     for (int q = tid; q < K * A; q += blockDim.x) sm.iages[q] = a.iages[q];
   }
-  for (int e = tid; e < n; e += blockDim.x) sm.y[e] = a.y0.ptr[traj * a.y0.batch_stride + e];
-  __syncthreads();
+  // ---- my elements: y, stage state, stage derivatives (registers)
+  double y[EPT], yst[EPT], f[7][EPT];
+  bool own[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = tid + i * kSeipThreads;
+    own[i] = e < n;
+    y[i] = own[i] ? a.y0.ptr[traj * a.y0.batch_stride + e] : 0.0;
+    yst[i] = y[i];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) f[j][i] = 0.0;
+  }
+  // right-hand side of the block's stage state `yst` at time t into f[slot]
+  auto eval = [&](double t, double (&out)[EPT]) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (own[i]) sm.ys[tid + i * kSeipThreads] = yst[i];
+    __syncthreads();
+    seip_rhs<KT, WT, EXT>(a, sm, t, sm.ys, sm.dx);  // ends with a barrier: dx is complete, ys free to overwrite
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) out[i] = own[i] ? sm.dx[tid + i * kSeipThreads] : 0.0;
+  };
 
   const double t1 = a.t1, rtol = a.rtol, atol = a.atol;
   const double inv_n = 1.0 / (double)n;
@@ -268,30 +292,36 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   };
 
   // ---- FSAL f0 and the initial step (Hairer-Wanner, PIDController._select_initial_step)
-  seip_rhs<KT, WT, EXT>(a, sm, a.t0, sm.y, sm.f[0]);
+  eval(a.t0, f[0]);
   double tprev = a.t0, tnext;
   if (a.const_dt > 0.0) {
     tnext = a.t0 + a.const_dt;
   } else {
     double p0 = 0.0, p1 = 0.0;
-    for (int e = tid; e < n; e += blockDim.x) {
-      const double sc = atol + fabs(sm.y[e]) * rtol;
-      const double u = sm.y[e] / sc, v = sm.f[0][e] / sc;
-      p0 += u * u;
-      p1 += v * v;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      if (own[i]) {
+        const double sc = atol + fabs(y[i]) * rtol;
+        const double u = y[i] / sc, v = f[0][i] / sc;
+        p0 += u * u;
+        p1 += v * v;
+      }
     }
     const double d0 = sqrt(block_sum(p0, sm.red) * inv_n);
     const double d1 = sqrt(block_sum(p1, sm.red) * inv_n);
     const bool small = (d0 < 1e-5) || (d1 < 1e-5);
     const double h0 = small ? 1e-6 : 0.01 * (d0 / d1);
-    for (int e = tid; e < n; e += blockDim.x) sm.ys[e] = sm.y[e] + h0 * sm.f[0][e];
-    __syncthreads();
-    seip_rhs<KT, WT, EXT>(a, sm, a.t0 + h0, sm.ys, sm.f[1]);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) yst[i] = y[i] + h0 * f[0][i];
+    eval(a.t0 + h0, f[1]);
     double p2 = 0.0;
-    for (int e = tid; e < n; e += blockDim.x) {
-      const double sc = atol + fabs(sm.y[e]) * rtol;
-      const double u = (sm.f[1][e] - sm.f[0][e]) / sc;
-      p2 += u * u;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      if (own[i]) {
+        const double sc = atol + fabs(y[i]) * rtol;
+        const double u = (f[1][i] - f[0][i]) / sc;
+        p2 += u * u;
+      }
     }
     const double d2 = sqrt(block_sum(p2, sm.red) * inv_n) / h0;
     const double md = fmax(d1, d2);
@@ -305,20 +335,20 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 
   while (tprev < t1 && n_steps < a.max_steps) {
     const double h = tnext - tprev;
-    // ---- Tsit5 stages 2..7 (stage index at compile time: the tableau row and the f_j pointers are static)
+    // ---- Tsit5 stages 2..7 (stage index at compile time: the tableau row is static, the f_j are registers)
     auto stage = [&](auto sc) {
       constexpr int s = decltype(sc)::value;
       constexpr int base = s == 1 ? I_a21 : s == 2 ? I_a31 : s == 3 ? I_a41 : s == 4 ? I_a51 : s == 5 ? I_a61 : I_a71;
-      for (int e = tid; e < n; e += blockDim.x) {
-        double acc = kTab[base] * sm.f[0][e];
 #pragma unroll
-        for (int j = 1; j < s; ++j) acc = fma(kTab[base + j], sm.f[j][e], acc);
-        sm.ys[e] = fma(h, acc, sm.y[e]);
+      for (int i = 0; i < EPT; ++i) {
+        double acc = kTab[base] * f[0][i];
+#pragma unroll
+        for (int j = 1; j < s; ++j) acc = fma(kTab[base + j], f[j][i], acc);
+        yst[i] = fma(h, acc, y[i]);
       }
-      __syncthreads();
       // stage times tprev + c_s h; the two c = 1 stages use tnext itself
       const double ts = s >= 5 ? tnext : fma(kTab[I_c2 + (s - 1)], h, tprev);
-      seip_rhs<KT, WT, EXT>(a, sm, ts, sm.ys, sm.f[s]);
+      eval(ts, f[s]);
     };
     stage(std::integral_constant<int, 1>{});
     stage(std::integral_constant<int, 2>{});
@@ -334,14 +364,17 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
       dt_next = a.const_dt;
     } else {
       double part = 0.0;
-      for (int e = tid; e < n; e += blockDim.x) {
-        double er = kTab[I_e1] * sm.f[0][e];
 #pragma unroll
-        for (int i = 1; i < 7; ++i) er = fma(kTab[I_e1 + i], sm.f[i][e], er);
-        er *= h;
-        const double sc = fma(fmax(fabs(sm.y[e]), fabs(sm.ys[e])), rtol, atol);
-        const double r = er / sc;
-        part = fma(r, r, part);
+      for (int i = 0; i < EPT; ++i) {
+        if (own[i]) {
+          double er = kTab[I_e1] * f[0][i];
+#pragma unroll
+          for (int j = 1; j < 7; ++j) er = fma(kTab[I_e1 + j], f[j][i], er);
+          er *= h;
+          const double sc = fma(fmax(fabs(y[i]), fabs(yst[i])), rtol, atol);
+          const double r = er / sc;
+          part = fma(r, r, part);
+        }
       }
       const double err2 = block_sum(part, sm.red) * inv_n;
       keep = err2 < 1.0;
@@ -354,29 +387,32 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     ++n_steps;
     if (keep) {
       ++n_acc;
-      // ---- SaveAt(ts): dense output for every ts[k] <= tnext; consecutive threads write consecutive elements
+      // ---- SaveAt(ts): dense output for every ts[k] <= tnext, straight from the registers; consecutive threads
+      // write consecutive elements
       const double inv_h = 1.0 / ((tnext == tprev) ? 1.0 : h);
       while (save_i < a.T && save_time(save_i) <= tnext) {
         const double th = (save_time(save_i) - tprev) * inv_h;
         double b[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
-          b[i] = th * fma(th, fma(th, fma(th, kDense[i][3], kDense[i][2]), kDense[i][1]), kDense[i][0]);
+        for (int j = 0; j < 7; ++j)
+          b[j] = th * fma(th, fma(th, fma(th, kDense[j][3], kDense[j][2]), kDense[j][1]), kDense[j][0]);
         double* row = out + (int64_t)save_i * n;
-        for (int e = tid; e < n; e += blockDim.x) {
-          double acc = b[0] * sm.f[0][e];
 #pragma unroll
-          for (int i = 1; i < 7; ++i) acc = fma(b[i], sm.f[i][e], acc);
-          row[e] = fma(h, acc, sm.y[e]);
+        for (int i = 0; i < EPT; ++i) {
+          if (own[i]) {
+            double acc = b[0] * f[0][i];
+#pragma unroll
+            for (int j = 1; j < 7; ++j) acc = fma(b[j], f[j][i], acc);
+            row[tid + i * kSeipThreads] = fma(h, acc, y[i]);
+          }
         }
         ++save_i;
       }
-      __syncthreads();
-      for (int e = tid; e < n; e += blockDim.x) {
-        sm.y[e] = sm.ys[e];
-        sm.f[0][e] = sm.f[6][e];
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        y[i] = yst[i];
+        f[0][i] = f[6][i];
       }
-      __syncthreads();
     } else {
       ++n_rej;
     }
@@ -396,14 +432,55 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 }
 
 size_t seip_smem_bytes(int A, int K, int W, int H, int V, int NK, int n) {
-  const size_t doubles = (size_t)9 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * V * W * K + 8 +
+  const size_t doubles = (size_t)2 * n + 2 * A * K + 3 * K + W + (size_t)A * A + A + (size_t)H * V * W * K + 8 +
                          (size_t)A * V * (5 + 2 * NK) + (size_t)K * A + 3 * K;
   return doubles * sizeof(double);
 }
 
 }  // namespace
+
+// This file is compiled twice (dynode_b200/_build.py): SEIP_EXT_UNIT = 0 holds the plain kernels and the C ABI,
+// SEIP_EXT_UNIT = 1 the kernels with the vaccination / introduction / seasonal-reset terms -- two translation units
+// so that the instantiations build in parallel.
+#ifndef SEIP_EXT_UNIT
+#define SEIP_EXT_UNIT 0
+#endif
+cudaError_t seip_launch_plain(const void* args, size_t smem, int n, cudaStream_t stream);
+cudaError_t seip_launch_ext(const void* args, size_t smem, int n, cudaStream_t stream);
+
+#if SEIP_EXT_UNIT
+cudaError_t seip_launch_ext(const void* args, size_t smem, int n, cudaStream_t stream) {
+  constexpr bool ext = true;
+#else
+cudaError_t seip_launch_plain(const void* args, size_t smem, int n, cudaStream_t stream) {
+  constexpr bool ext = false;
+#endif
+  const SeipArgs& a = *static_cast<const SeipArgs*>(args);
+  const int ept = (n + kSeipThreads - 1) / kSeipThreads;  // elements per thread, rounded up to a compiled width
+  void (*kern)(const SeipArgs) = nullptr;
+#define SEIP_PICK(KK, WW)                                                                                 \
+  {                                                                                                       \
+    if (ept <= 4) kern = seip_solver_kernel<KK, WW, ext, 4>;                                               \
+    else if (ept <= 8) kern = seip_solver_kernel<KK, WW, ext, 8>;                                          \
+    else kern = seip_solver_kernel<KK, WW, ext, 12>;                                                       \
+  }
+  SEIP_PICK(0, 0)
+  // kernels specialised for the common (strains, waning stages) pairs (loops unrolled, index arithmetic folded);
+  // any other shape runs the generic one
+#define SEIP_CASE(KK, WW) if (a.K == KK && a.W == WW) SEIP_PICK(KK, WW)
+  SEIP_CASE(2, 3) SEIP_CASE(2, 4) SEIP_CASE(3, 3) SEIP_CASE(3, 4)
+#undef SEIP_CASE
+#undef SEIP_PICK
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)a.B, kSeipThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace dynode
 
+#if !SEIP_EXT_UNIT
 using namespace dynode;
 
 extern "C" {
@@ -457,20 +534,10 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, a.V, a.NK, n);
   // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
   const bool ext = a.V > 1 || a.vbase || a.ipct.ptr || a.season_on != 0.0;
-  void (*kern)(const SeipArgs) = ext ? seip_solver_kernel<0, 0, true> : seip_solver_kernel<0, 0, false>;
-#define SEIP_CASE(KK, WW) \
-  if (a.K == KK && a.W == WW) kern = ext ? seip_solver_kernel<KK, WW, true> : seip_solver_kernel<KK, WW, false>;
-  SEIP_CASE(1, 1) SEIP_CASE(1, 2) SEIP_CASE(1, 3) SEIP_CASE(1, 4)
-  SEIP_CASE(2, 1) SEIP_CASE(2, 2) SEIP_CASE(2, 3) SEIP_CASE(2, 4)
-  SEIP_CASE(3, 1) SEIP_CASE(3, 2) SEIP_CASE(3, 3) SEIP_CASE(3, 4)
-  SEIP_CASE(4, 1) SEIP_CASE(4, 2) SEIP_CASE(4, 3) SEIP_CASE(4, 4)
-#undef SEIP_CASE
-  cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail_msg("shared memory request of %zu bytes refused: %s", smem, cudaGetErrorString(e));
-  kern<<<(unsigned)B, kSeipThreads, smem, (cudaStream_t)stream>>>(a);
-  e = cudaGetLastError();
+  const cudaError_t e = ext ? seip_launch_ext(&a, smem, n, (cudaStream_t)stream)
+                            : seip_launch_plain(&a, smem, n, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail_msg("kernel launch failed: %s", cudaGetErrorString(e));
 }
 
 }  // extern "C"
+#endif  // !SEIP_EXT_UNIT

@@ -78,7 +78,28 @@ class SolverOptions:
 _JUMP_CACHE: Dict[tuple, object] = {}
 
 # ---- row mask (DynodeSolverDesc.only) -----------------------------------------------------------------
-_ONLY = [None]
+# per host thread: two samplers driven from two threads of one process must not see each other's masks
+import threading
+
+
+class _OnlyState(threading.local):
+    mask = None
+
+
+_ONLY_TLS = _OnlyState()
+
+
+class _OnlyProxy:
+    """`_ONLY[0]` as the code below uses it, backed by thread-local storage."""
+
+    def __getitem__(self, i):
+        return _ONLY_TLS.mask
+
+    def __setitem__(self, i, v):
+        _ONLY_TLS.mask = v
+
+
+_ONLY = _OnlyProxy()
 
 
 class only_rows:
