@@ -83,7 +83,7 @@ class Params(ctypes.Structure):
 
 class SeipDesc(ctypes.Structure):
     _fields_ = [("n_ages", ctypes.c_int32), ("n_strains", ctypes.c_int32), ("n_wane", ctypes.c_int32),
-                ("n_vax", ctypes.c_int32), ("n_knots", ctypes.c_int32)]
+                ("n_vax", ctypes.c_int32), ("n_knots", ctypes.c_int32), ("save_mask", ctypes.c_uint32)]
 
 
 class SeipParams(ctypes.Structure):

@@ -41,7 +41,24 @@ struct SeipArgs {
   int max_steps;
   double* ys;
   int32_t* stats;
+  const double* jump_ts;  // SolverParams.discontinuity_points, sorted, device memory (NULL / 0 = none)
+  int n_jump;
+  uint32_t save_mask;  // bit c = compartment c (S, E, I, C) is saved (sub_save_indices, reference odes.py:182-193)
+  int n_saved;         // doubles per saved row
 };
+
+// ClipStepSizeController(jump_ts), as lane_solver.cuh: a step [t0, t1] that would contain a
+// discontinuity point ends just before it; the next one restarts exactly at it with a fresh f0.
+__device__ __forceinline__ double seip_clip_to_jumps(const SeipArgs& a, double t0, double t1, bool& made_jump) {
+  int i0 = 0, i1 = 0;
+  for (int k = 0; k < a.n_jump; ++k) {
+    const double j = a.jump_ts[k];
+    i0 += (j <= t0);
+    i1 += (j <= t1);
+  }
+  made_jump = i0 < i1;
+  return made_jump ? nextafter(a.jump_ts[i0 < a.n_jump ? i0 : a.n_jump - 1], -CUDART_INF) : t1;
+}
 
 struct Smem {
   double *ys, *dx;
@@ -263,9 +280,19 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   // ---- my elements: y, stage state, stage derivatives (registers)
   double y[EPT], yst[EPT], f[7][EPT];
   bool own[EPT];
+  int soff[EPT];  // my element's offset inside a saved row, -1 when its compartment is not saved
+  const int nS_ = A * H * a.V * W, nX_ = A * H * a.V * K;
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const int e = tid + i * kSeipThreads;
+    {
+      const int comp = e < nS_ ? 0 : 1 + (e - nS_) / nX_;
+      int skipped = 0;  // doubles of the unsaved compartments in front of mine
+      if (comp > 0 && !(a.save_mask & 1u)) skipped += nS_;
+      for (int c = 1; c < comp; ++c)
+        if (!((a.save_mask >> c) & 1u)) skipped += nX_;
+      soff[i] = (e < n && ((a.save_mask >> comp) & 1u)) ? e - skipped : -1;
+    }
     own[i] = e < n;
     y[i] = own[i] ? a.y0.ptr[traj * a.y0.batch_stride + e] : 0.0;
     yst[i] = y[i];
@@ -328,10 +355,13 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
     tnext = a.t0 + fmin(100.0 * h0, h1);
   }
+  bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
+  if (a.n_jump > 0 && !(a.const_dt > 0.0)) tnext = seip_clip_to_jumps(a, a.t0, tnext, made_jump);
   tnext = fmin(tnext, t1);
 
   int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
-  double* const out = a.ys + traj * (int64_t)a.T * n;
+  const int ns = a.n_saved;
+  double* const out = a.ys + traj * (int64_t)a.T * ns;
 
   while (tprev < t1 && n_steps < a.max_steps) {
     const double h = tnext - tprev;
@@ -381,7 +411,11 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
       dt_next = h * controller_factor_sq(err2, keep);
     }
     double ntprev = keep ? tnext : tprev;
+    bool next_made_jump = false;
+    const bool jumps = a.n_jump > 0 && !(a.const_dt > 0.0);
+    if (jumps && keep && made_jump) ntprev = nextafter(tnext, CUDART_INF);  // restart exactly at the jump
     double ntnext = ntprev + dt_next;
+    if (jumps) ntnext = seip_clip_to_jumps(a, ntprev, ntnext, next_made_jump);
     ntprev = fmin(ntprev, t1);
     if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);
     ++n_steps;
@@ -396,14 +430,14 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 #pragma unroll
         for (int j = 0; j < 7; ++j)
           b[j] = th * fma(th, fma(th, fma(th, kDense[j][3], kDense[j][2]), kDense[j][1]), kDense[j][0]);
-        double* row = out + (int64_t)save_i * n;
+        double* row = out + (int64_t)save_i * ns;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-          if (own[i]) {
+          if (soff[i] >= 0) {
             double acc = b[0] * f[0][i];
 #pragma unroll
             for (int j = 1; j < 7; ++j) acc = fma(b[j], f[j][i], acc);
-            row[tid + i * kSeipThreads] = fma(h, acc, y[i]);
+            row[soff[i]] = fma(h, acc, y[i]);
           }
         }
         ++save_i;
@@ -413,15 +447,22 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
         y[i] = yst[i];
         f[0][i] = f[6][i];
       }
+      if (jumps && made_jump) {  // no FSAL across a discontinuity: f0 is re-evaluated at (jump, y1)
+        tprev = ntprev;
+        eval(tprev, f[0]);
+      }
     } else {
       ++n_rej;
     }
+    if (jumps) made_jump = next_made_jump;
     tprev = ntprev;
     tnext = ntnext;
   }
   // slots never reached keep diffrax's +inf fill
   for (int k = save_i; k < a.T; ++k)
-    for (int e = tid; e < n; e += blockDim.x) out[(int64_t)k * n + e] = CUDART_INF;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (soff[i] >= 0) out[(int64_t)k * ns + soff[i]] = CUDART_INF;
   if (tid == 0) {
     int32_t* st = a.stats + traj * 4;
     st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
@@ -511,7 +552,9 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   if (!(sv->t1 >= sv->t0)) return fail_msg("t1 must be >= t0");
   if (!(sv->const_dt > 0.0) && !(sv->rtol > 0.0 && sv->atol > 0.0)) return fail_msg("rtol/atol must be positive");
   if (sv->max_steps <= 0) return fail_msg("max_steps must be positive");
-  if (sv->n_jump > 0) return fail_msg("unsupported: discontinuity points in the SEIP kernel");
+  if (sv->n_jump < 0 || sv->n_jump > 32) return fail_msg("n_jump must be in [0, 32]");
+  if (sv->n_jump > 0 && !sv->jump_ts) return fail_msg("jump_ts is null");
+  if (model->save_mask > 15u) return fail_msg("save_mask has bits beyond the four compartments (S, E, I, C)");
   if (B == 0) return 0;
   SeipArgs a;
   a.A = model->n_ages; a.K = model->n_strains; a.W = model->n_wane; a.H = 1 << a.K; a.n = n;
@@ -531,6 +574,15 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   a.save_ts = save_ts; a.T = T;
   a.max_steps = (int)(sv->max_steps > 0x7fffffff ? 0x7fffffff : sv->max_steps);
   a.ys = ys; a.stats = stats;
+  // the reference ignores discontinuity points in constant-step mode (odes.py:113-131)
+  a.jump_ts = (sv->n_jump > 0 && !(sv->const_dt > 0.0)) ? sv->jump_ts : nullptr;
+  a.n_jump = a.jump_ts ? sv->n_jump : 0;
+  a.save_mask = model->save_mask ? model->save_mask : 15u;
+  {
+    const int nS = a.A * a.H * a.V * a.W, nX = a.A * a.H * a.V * a.K;
+    a.n_saved = ((a.save_mask & 1u) ? nS : 0) + nX * (((a.save_mask >> 1) & 1u) + ((a.save_mask >> 2) & 1u) +
+                                                       ((a.save_mask >> 3) & 1u));
+  }
   const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, a.V, a.NK, n);
   // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
   const bool ext = a.V > 1 || a.vbase || a.ipct.ptr || a.season_on != 0.0;

@@ -38,8 +38,17 @@ class SeipModel:
             return ((A, H, W), (A, H, K), (A, H, K), (A, H, K))
         return ((A, H, V, W), (A, H, V, K), (A, H, V, K), (A, H, V, K))
 
-    def desc(self) -> _lib.SeipDesc:
-        return _lib.SeipDesc(self.n_ages, self.n_strains, self.n_wane, self.n_vax, self.n_knots)
+    def desc(self, save_mask: int = 0) -> _lib.SeipDesc:
+        return _lib.SeipDesc(self.n_ages, self.n_strains, self.n_wane, self.n_vax, self.n_knots, int(save_mask))
+
+    def compartment_sizes(self) -> Tuple[int, ...]:
+        nS = self.n_ages * self.n_hist * self.n_vax * self.n_wane
+        nX = self.n_ages * self.n_hist * self.n_vax * self.n_strains
+        return (nS, nX, nX, nX)
+
+    def saved_size(self, mask: int) -> int:
+        mask = mask or 15
+        return sum(sz for c, sz in enumerate(self.compartment_sizes()) if (mask >> c) & 1)
 
     def check_supported(self) -> None:
         d = self.desc()
@@ -79,12 +88,13 @@ def immunity_table_vax(n_strains: int, base_protection, cross_immunity, vaccine_
 
 def solve_ensemble(model: SeipModel, y0, params: Dict[str, object], contact, pop, immunity, opts: engine.SolverOptions,
                    save_ts, out=None, B: Optional[int] = None, vaccination=None, introductions=None,
-                   season_tau: Optional[float] = None):
+                   season_tau: Optional[float] = None, save_mask: int = 0):
     """One launch, one thread block per trajectory.  params: beta, sigma, gamma [B|1, K], omega [B|1, W].
     vaccination = (base [A,V,4], knots [A,V,NK], coef [A,V,NK]) shared spline tables (reference utils/splines.py);
     introductions = dict(time, scale, pct [B|1, K], ages [K, A]) (reference config/strains.py:59-109);
     season_tau: seasonal reset of the top tier, phi(t) = sin(2 pi (t + tau) / 730)^1000 (ode_model.md:72-75).
-    Returns (ys[B, T, n], stats[B, 4]); everything stays on the current CUDA device and stream."""
+    save_mask: bit c = compartment c of (s, e, i, c) is saved (0 = all); `opts.jump_ts` = discontinuity points.
+    Returns (ys[B, T, n_saved], stats[B, 4]); everything stays on the current CUDA device and stream."""
     torch = _lib.require_cuda()
     model.check_supported()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -111,7 +121,7 @@ def solve_ensemble(model: SeipModel, y0, params: Dict[str, object], contact, pop
     save_dt = engine.uniform_save_dt(save_ts, float(opts.t0), float(opts.t1)) if isinstance(save_ts, np.ndarray) else 0.0
     ts_t = f64(save_ts)
     T = int(ts_t.numel())
-    ys = out if out is not None else torch.empty((B, T, n), dtype=torch.float64, device=dev)
+    ys = out if out is not None else torch.empty((B, T, model.saved_size(save_mask)), dtype=torch.float64, device=dev)
     stats = torch.empty((B, 4), dtype=torch.int32, device=dev)
     cp = _lib.SeipParams()
     cp.beta, cp.sigma, cp.gamma = arr(p["beta"], K, "beta"), arr(p["sigma"], K, "sigma"), arr(p["gamma"], K, "gamma")
@@ -132,7 +142,7 @@ def solve_ensemble(model: SeipModel, y0, params: Dict[str, object], contact, pop
         cp.intro_ages = intro["ages"].data_ptr()
     if season_tau is not None:
         cp.season_tau, cp.season_on = float(season_tau), 1.0
-    md, sd = model.desc(), opts.desc(save_dt)
+    md, sd = model.desc(save_mask), opts.desc(save_dt)
     _lib.check(_lib.load().dynode_seip_solve_f64(
         ctypes.byref(md), ctypes.byref(sd), B, arr(y0_t, n, "y0"), ctypes.byref(cp), ts_t.data_ptr(), T,
         ys.data_ptr(), stats.data_ptr(), ctypes.c_void_p(_lib.current_stream_ptr())))

@@ -447,10 +447,7 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
     except _lib.DynodeError as e:
         raise UnsupportedODEError(str(e)) from None
     opts = _solver_options(solver_parameters, duration_days)
-    if len(opts.jump_ts) > 0:
-        raise UnsupportedODEError("discontinuity_points are not implemented for the 'seip' kernel")
-    if sub_save_indices is not None:
-        raise UnsupportedODEError("sub_save_indices are not implemented for the 'seip' kernel")
+    mask = _mask_from(sub_save_indices, 4)
     _lib.require_cuda()
     B = 1 if batch_size is None else batch_size
     ensemble = batch_size is not None
@@ -472,7 +469,7 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
                              ages=opt("intro_ages"))
     ys, stats = seip.solve_ensemble(model, y0, params, get_path(ode_parameters, spec.contact), get("population"),
                                     get("immunity"), opts, saveat.times, B=B, vaccination=vaccination,
-                                    introductions=introductions, season_tau=opt("season_tau"))
+                                    introductions=introductions, season_tau=opt("season_tau"), save_mask=mask)
     out_dev = initial_state[0].device
     st = stats if out_dev.type == "cuda" else stats.cpu()
     if throw and bool((stats[:, _lib.STAT_RESULT] != 0).any()):
@@ -483,7 +480,10 @@ def _run_seip(ode, duration_days, initial_state, ode_parameters, solver_paramete
     lead = (B, T) if ensemble else (T,)
     flat = ys if ensemble else ys[0]
     outs, off = [], 0
-    for shp in shapes:
+    for c, shp in enumerate(shapes):
+        if not (mask >> c) & 1:  # unsaved compartments come back as (T, 0), reference odes.py:182-193
+            outs.append(flat.new_empty((*lead, 0)))
+            continue
         sz = int(np.prod(shp))
         outs.append(flat[..., off:off + sz].reshape(*lead, *shp))
         off += sz

@@ -44,6 +44,8 @@ typedef struct {
   int32_t n_wane;    /* W */
   int32_t n_vax;     /* V vaccination tiers (0 or 1 = none); the top tier V-1 is the prose model's K */
   int32_t n_knots;   /* knots of the vaccination-rate splines */
+  uint32_t save_mask; /* bit c set = compartment c of (S, E, I, C) is saved (sub_save_indices, odes.py:182-193);
+                         0 = all four.  ys rows then hold the saved compartments only, concatenated */
 } DynodeSeipDesc;
 
 typedef struct {
@@ -69,7 +71,8 @@ typedef struct {
 
 int dynode_seip_state_size(const DynodeSeipDesc* model);
 
-/* y0 [B][n] (batch_stride 0 = shared), save_ts [T], ys [B][T][n] (unreached slots +inf), stats [B][4]. */
+/* y0 [B][n] (batch_stride 0 = shared), save_ts [T], ys [B][T][n_saved] (unreached slots +inf), stats [B][4].
+ * DynodeSolverDesc.jump_ts (SolverParams.discontinuity_points) is honoured as in dynode_solve_f64. */
 int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* solver, int64_t B, DynodeArray y0,
                           const DynodeSeipParams* params, const double* save_ts, int32_t T, double* ys,
                           int32_t* stats, void* stream);

@@ -610,3 +610,66 @@ def test_seip_vaccination_kernel_matches_oracle(A, K, W, V, NK, kw):
     got = torch.cat([c.reshape(B, t1 + 1, -1) for c in sol.ys], dim=2).cpu().numpy()
     assert np.array_equal(got, ys.cpu().numpy())
     assert sol.ys[0].shape == (B, t1 + 1) + shp_s
+
+
+def test_seip_discontinuity_points_and_sub_save():
+    """SolverParams.discontinuity_points and sub_save_indices on the CTA-per-trajectory kernel: steps end at
+    prevbefore(jump) and restart at the jump with a fresh f0 (same accepted / rejected counts as the oracle, which
+    differ from the unclipped solve); unsaved compartments are neither computed at the save times nor written, and come
+    back as (T, 0) through `simulate_ensemble`."""
+    import torch
+    from dynode_b200 import seip
+    from dynode_b200.config import SolverParams
+    from dynode_b200.engine import SolverOptions
+    from dynode_b200.examples import rhs as ex
+    from dynode_b200.simulation import simulate_ensemble
+    from tests.cases import make_seipv_case
+    B, t1 = 23, 150
+    A, K, W, V, NK = 3, 2, 3, 2, 1
+    H = 1 << K
+    case = make_seipv_case(B, A=A, K=K, W=W, V=V, NK=NK, t1=t1)
+    ts = np.linspace(0.0, t1, t1 + 1)
+    jumps = (30.0, 75.5, 120.0)
+    kw = dict(vaccination=case["vaccination"], introductions=case["introductions"], season_tau=case["season_tau"])
+    ys, st = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                 case["immunity"], SolverOptions(t1=float(t1), jump_ts=jumps), ts, **kw)
+    ys0, st0 = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                   case["immunity"], SolverOptions(t1=float(t1)), ts, **kw)
+    torch.cuda.synchronize()
+    ref, _, rst = _run_oracle(case, t1, jump_ts=jumps)
+    assert np.array_equal(st.cpu().numpy(), rst) and not np.array_equal(st.cpu().numpy(), st0.cpu().numpy())
+    _assert_close(ys.cpu().numpy(), ref)
+    # constant-step mode ignores the list (reference odes.py:113-131)
+    yc, stc = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                  case["immunity"], SolverOptions(t1=float(t1), const_dt=0.5, jump_ts=jumps), ts, **kw)
+    refc, _, rstc = _run_oracle(case, t1, const_dt=0.5)
+    assert np.array_equal(stc.cpu().numpy(), rstc)
+    _assert_close(yc.cpu().numpy(), refc)
+    # sub-save: S and C only (mask 0b1001), on a coarse grid
+    nS, nX = A * H * V * W, A * H * V * K
+    ts7 = np.linspace(0.0, t1, int(t1 // 7) + 1)
+    ym, stm = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
+                                  case["immunity"], SolverOptions(t1=float(t1)), ts7, save_mask=0b1001, **kw)
+    idx = list(range(nS)) + list(range(nS + 2 * nX, nS + 3 * nX))
+    refm, _, rstm = _run_oracle(case, t1, save_ts=ts7, save_idx=idx)
+    assert ym.shape == (B, len(ts7), nS + nX) and np.array_equal(stm.cpu().numpy(), rstm)
+    _assert_close(ym.cpu().numpy(), refm)
+    # ... and through the public API
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    y0 = case["y0"]
+    state = (t(y0[:nS]).reshape(A, H, V, W), t(y0[nS:nS + nX]).reshape(A, H, V, K),
+             t(y0[nS + nX:nS + 2 * nX]).reshape(A, H, V, K), t(y0[nS + 2 * nX:]).reshape(A, H, V, K))
+    prm, intro, vac = case["params"], case["introductions"], case["vaccination"]
+    p = ex.SEIP_ODEParams(beta=t(prm["beta"]), sigma=t(prm["sigma"]), gamma=t(prm["gamma"]), omega=t(prm["omega"]),
+                          contact_matrix=t(case["contact"]), population=t(case["pop"]), immunity=t(case["immunity"]),
+                          vax_base=t(vac[0]), vax_knots=t(vac[1]), vax_coef=t(vac[2]), intro_time=t(intro["time"]),
+                          intro_scale=t(intro["scale"]), intro_pct=t(intro["pct"]), intro_ages=t(intro["ages"]),
+                          season_tau=case["season_tau"])
+    sol = simulate_ensemble(ex.seip_ode, t1, state, p, SolverParams(discontinuity_points=list(jumps)),
+                            sub_save_indices=(0, 3), save_step=7, batch_size=B, state_batched=False)
+    assert sol.ys[1].shape == (B, len(ts7), 0) and sol.ys[2].shape == (B, len(ts7), 0)
+    refj, _, rstj = _run_oracle(case, t1, save_ts=ts7, save_idx=idx, jump_ts=jumps)
+    got = torch.cat([sol.ys[0].reshape(B, len(ts7), -1), sol.ys[3].reshape(B, len(ts7), -1)], dim=2).cpu().numpy()
+    _assert_close(got, refj)
+    assert np.array_equal(sol.stats["num_accepted_steps"].cpu().numpy(), rstj[:, 1])
