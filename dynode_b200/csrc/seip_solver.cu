@@ -280,12 +280,12 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   // ---- my elements: y, stage state, stage derivatives (registers)
   double y[EPT], yst[EPT], f[7][EPT];
   bool own[EPT];
-  int soff[EPT];  // my element's offset inside a saved row, -1 when its compartment is not saved
+  int soff[EXT ? EPT : 1];  // general kernel: my element's offset inside a saved row, -1 when its compartment is not saved
   const int nS_ = A * H * a.V * W, nX_ = A * H * a.V * K;
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const int e = tid + i * kSeipThreads;
-    {
+    if constexpr (EXT) {  // the general kernel honours a compartment mask; the plain one saves whole rows
       const int comp = e < nS_ ? 0 : 1 + (e - nS_) / nX_;
       int skipped = 0;  // doubles of the unsaved compartments in front of mine
       if (comp > 0 && !(a.save_mask & 1u)) skipped += nS_;
@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
 #pragma unroll
     for (int j = 0; j < 7; ++j) f[j][i] = 0.0;
   }
+  auto save_off = [&](int i) -> int {
+    if constexpr (EXT) return soff[i]; else return own[i] ? tid + i * kSeipThreads : -1;
+  };
   // right-hand side of the block's stage state `yst` at time t into f[slot]
   auto eval = [&](double t, double (&out)[EPT]) {
 #pragma unroll
@@ -356,11 +359,11 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     tnext = a.t0 + fmin(100.0 * h0, h1);
   }
   bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
-  if (a.n_jump > 0 && !(a.const_dt > 0.0)) tnext = seip_clip_to_jumps(a, a.t0, tnext, made_jump);
+  if (EXT && a.n_jump > 0 && !(a.const_dt > 0.0)) tnext = seip_clip_to_jumps(a, a.t0, tnext, made_jump);
   tnext = fmin(tnext, t1);
 
   int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
-  const int ns = a.n_saved;
+  const int ns = EXT ? a.n_saved : n;
   double* const out = a.ys + traj * (int64_t)a.T * ns;
 
   while (tprev < t1 && n_steps < a.max_steps) {
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
     }
     double ntprev = keep ? tnext : tprev;
     bool next_made_jump = false;
-    const bool jumps = a.n_jump > 0 && !(a.const_dt > 0.0);
+    const bool jumps = EXT && a.n_jump > 0 && !(a.const_dt > 0.0);
     if (jumps && keep && made_jump) ntprev = nextafter(tnext, CUDART_INF);  // restart exactly at the jump
     double ntnext = ntprev + dt_next;
     if (jumps) ntnext = seip_clip_to_jumps(a, ntprev, ntnext, next_made_jump);
@@ -433,11 +436,12 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
         double* row = out + (int64_t)save_i * ns;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-          if (soff[i] >= 0) {
+          const int so = save_off(i);
+          if (so >= 0) {
             double acc = b[0] * f[0][i];
 #pragma unroll
             for (int j = 1; j < 7; ++j) acc = fma(b[j], f[j][i], acc);
-            row[soff[i]] = fma(h, acc, y[i]);
+            row[so] = fma(h, acc, y[i]);
           }
         }
         ++save_i;
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(kSeipThreads) seip_solver_kernel(const SeipArg
   for (int k = save_i; k < a.T; ++k)
 #pragma unroll
     for (int i = 0; i < EPT; ++i)
-      if (soff[i] >= 0) out[(int64_t)k * ns + soff[i]] = CUDART_INF;
+      if (save_off(i) >= 0) out[(int64_t)k * ns + save_off(i)] = CUDART_INF;
   if (tid == 0) {
     int32_t* st = a.stats + traj * 4;
     st[DYNODE_STAT_RESULT] = (tprev < t1) ? DYNODE_RESULT_MAX_STEPS : DYNODE_RESULT_OK;
@@ -585,7 +589,8 @@ int dynode_seip_solve_f64(const DynodeSeipDesc* model, const DynodeSolverDesc* s
   }
   const size_t smem = seip_smem_bytes(a.A, a.K, a.W, a.H, a.V, a.NK, n);
   // kernels specialised for the common (strains, waning stages) pairs; any other shape runs the generic one
-  const bool ext = a.V > 1 || a.vbase || a.ipct.ptr || a.season_on != 0.0;
+  // the general kernels also carry the solver options the plain ones leave out (discontinuity points, sub-save)
+  const bool ext = a.V > 1 || a.vbase || a.ipct.ptr || a.season_on != 0.0 || a.n_jump > 0 || a.save_mask != 15u;
   const cudaError_t e = ext ? seip_launch_ext(&a, smem, n, (cudaStream_t)stream)
                             : seip_launch_plain(&a, smem, n, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail_msg("kernel launch failed: %s", cudaGetErrorString(e));
