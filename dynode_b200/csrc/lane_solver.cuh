@@ -772,10 +772,19 @@ struct LaneSolver {
                 ts_next = next_time(save_i + 1);
                 const double hthw = hw * th, hth2 = (h * th) * th;
                 const D v0 = dense(0, th, hthw, hth2);
-                if (lead) *row_ptr(out_s, save_i) = v0.v;
-                double* const pc = row_ptr(out_c, save_i);
+                if constexpr (L == 1 && NE == 4) {
+                  // one lane owns the whole 32-byte row (s, e, i, r): two 16-byte stores instead of four 8-byte ones
+                  // halve the store wavefronts of a pass whose 32 lanes hit 32 different sectors (ncu r2: the pass's
+                  // entry branch waited on the previous pass's stores for 9 % of all stall samples)
+                  double2* const pr = reinterpret_cast<double2*>(row_ptr(out_s, save_i));
+                  pr[0] = make_double2(v0.v, dense(1, th, hthw, hth2).v);
+                  pr[1] = make_double2(dense(2, th, hthw, hth2).v, dense(3, th, hthw, hth2).v);
+                } else {
+                  if (lead) *row_ptr(out_s, save_i) = v0.v;
+                  double* const pc = row_ptr(out_c, save_i);
 #pragma unroll
-                for (int e = 1; e < NE; ++e) pc[(e - 1) * G * S] = dense(e, th, hthw, hth2).v;
+                  for (int e = 1; e < NE; ++e) pc[(e - 1) * G * S] = dense(e, th, hthw, hth2).v;
+                }
                 ++save_i;
               }
               pend = ts_next <= tnext;
