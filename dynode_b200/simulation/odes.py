@@ -199,6 +199,11 @@ def simulate(
     """
     _validate_call(ode, initial_state, ode_parameters, duration_days)
     if _wants_autograd(ode, initial_state, ode_parameters):
+        if flow_spec_of(ode).flow == "seip":
+            raise UnsupportedODEError(
+                "the immune-history ('seip') kernel integrates plain solves only: it carries no sensitivities, so "
+                "`simulate` cannot be differentiated or vmapped for this flow (detach the inputs, or use "
+                "`simulate_ensemble` for batches); there is no CPU fallback")
         return _run_differentiable(ode, duration_days, initial_state, ode_parameters, solver_parameters,
                                    sub_save_indices, save_step)
     sol = _run(ode, duration_days, initial_state, ode_parameters, solver_parameters, sub_save_indices,

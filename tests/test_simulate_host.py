@@ -202,3 +202,14 @@ def test_registered_bodies_are_checked_against_the_compiled_flow():
     ]
     for ode, prm, shapes, g, s_, cshape in cases:
         verify_flow_body(ode, flow_spec_of(ode), shapes, prm, g, s_, cshape)
+
+
+def test_differentiating_the_immune_history_flow_fails_with_a_clear_message():
+    A, K, W, H = 2, 2, 2, 4
+    one = lambda *sh: torch.ones(sh, dtype=torch.float64)
+    beta = torch.tensor([0.3, 0.4], dtype=torch.float64, requires_grad=True)
+    p = ex.SEIP_ODEParams(beta=beta, sigma=one(K), gamma=one(K), omega=one(W), contact_matrix=torch.eye(A, dtype=torch.float64),
+                          population=8 * one(A), immunity=torch.zeros(H, W, K, dtype=torch.float64))
+    e = torch.zeros(A, H, K, dtype=torch.float64)
+    with pytest.raises(UnsupportedODEError, match="no sensitivities"):
+        simulate(ex.seip_ode, 10, (one(A, H, W), e, e.clone(), e.clone()), p, SolverParams())
