@@ -138,18 +138,25 @@ ffi::Error LoglikAdjointImpl(cudaStream_t stream, F64 y0, F64 beta, F64 gamma, F
       vsave->typed_data(), stream));
 }
 
+// zero-element buffers = absent (no vaccination tables / no introductions / no discontinuity points / no row mask)
 ffi::Error SeipSolveImpl(cudaStream_t stream, F64 y0, F64 beta, F64 sigma, F64 gamma, F64 omega, F64 contact, F64 pop,
-                         F64 immunity, F64 save_ts, U8 only, int32_t n_ages, int32_t n_strains, int32_t n_wane,
-                         DYN_SOLVER_PARAMS, F64Out ys, S32Out stats) {
-  const DynodeSeipDesc model{n_ages, n_strains, n_wane};
-  DynodeSolverDesc solver{};
-  solver.t0 = t0; solver.t1 = t1; solver.rtol = rtol; solver.atol = atol; solver.const_dt = const_dt;
-  solver.max_steps = max_steps; solver.save_dt = save_dt;
-  solver.only = only.element_count() > 0 ? only.typed_data() : nullptr;
+                         F64 immunity, F64 vax_base, F64 vax_knots, F64 vax_coef, F64 intro_time, F64 intro_scale,
+                         F64 intro_pct, F64 intro_ages, F64 save_ts, F64 jump_ts, U8 only, int32_t n_ages,
+                         int32_t n_strains, int32_t n_wane, int32_t n_vax, int32_t n_knots, int64_t save_mask,
+                         double season_tau, double season_on, DYN_SOLVER_PARAMS, F64Out ys, S32Out stats) {
+  DynodeSeipDesc model{};
+  model.n_ages = n_ages; model.n_strains = n_strains; model.n_wane = n_wane; model.n_vax = n_vax;
+  model.n_knots = n_knots; model.save_mask = (uint32_t)save_mask;
+  const DynodeSolverDesc solver = solver_desc(DYN_SOLVER_ARGS, jump_ts, only);
   const int64_t B = stats->dimensions()[0];
+  auto opt = [](const F64& b) -> const double* { return b.element_count() > 0 ? b.typed_data() : nullptr; };
   DynodeSeipParams p{};
   p.beta = as_array(beta, B); p.sigma = as_array(sigma, B); p.gamma = as_array(gamma, B); p.omega = as_array(omega, B);
   p.contact = contact.typed_data(); p.pop = pop.typed_data(); p.immunity = immunity.typed_data();
+  p.vax_base = opt(vax_base); p.vax_knots = opt(vax_knots); p.vax_coef = opt(vax_coef);
+  p.intro_time = as_array(intro_time, B); p.intro_scale = as_array(intro_scale, B);
+  p.intro_pct = as_array(intro_pct, B); p.intro_ages = opt(intro_ages);
+  p.season_tau = season_tau; p.season_on = season_on;
   return status(dynode_seip_solve_f64(&model, &solver, B, as_array(y0, B), &p, save_ts.typed_data(),
                                       (int32_t)save_ts.element_count(), ys->typed_data(), stats->typed_data(),
                                       stream));
@@ -210,8 +217,11 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodePoissonLoglikAdjoint, LoglikAdjointImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSeipSolve, SeipSolveImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>().Arg<F64>()
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
-                                  .Arg<U8>().Attr<int32_t>("n_ages").Attr<int32_t>("n_strains")
-                                  .Attr<int32_t>("n_wane") DYN_SOLVER_ATTRS.Ret<F64>().Ret<S32>());
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Arg<F64>().Arg<U8>().Attr<int32_t>("n_ages").Attr<int32_t>("n_strains")
+                                  .Attr<int32_t>("n_wane").Attr<int32_t>("n_vax").Attr<int32_t>("n_knots")
+                                  .Attr<int64_t>("save_mask").Attr<double>("season_tau").Attr<double>("season_on")
+                                  DYN_SOLVER_ATTRS.Ret<F64>().Ret<S32>());
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(DynodeSiteLogdensity, SiteImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F64>()
