@@ -373,6 +373,21 @@ def nuts_leg(args, dev, world, barrier, fp64_peak_tf=None):
     out["sampler"] = sampler(args.nuts_chains)
     if args.nuts_chains != 4096:
         out["sampler_4096_chains"] = sampler(4096)
+    # BASELINE.json configs[1] literally: 4 chains, 500 warm-up + 100 samples, max_tree_depth 10
+    # (examples/sir_infer_parameters.py:92-98 with num_chains=4): pure latency -- four trajectories per launch
+    mc4 = MCMC(NUTS(m.model_fused, max_tree_depth=10), num_warmup=500, num_samples=100, num_chains=4,
+               progress_bar=False)
+    barrier()
+    t0 = time.perf_counter()
+    mc4.run(PRNGKey(8675314 + rank), config=cfg, tf=100, obs_data=obs)
+    torch.cuda.synchronize()
+    dt4 = time.perf_counter() - t0
+    s4 = mc4.get_samples()
+    out["sampler_config2_4_chains"] = {
+        "value": float(mc4.engine.grad_evals) / dt4, "chains_per_gpu": 4, "num_warmup": 500, "num_samples": 100,
+        "wall_s": dt4, "rounds": mc4.engine.rounds, "us_per_round": 1e6 * dt4 / max(1, mc4.engine.rounds),
+        "posterior_mean_r0": float(s4["strains_0_r0"].mean()),
+        "posterior_mean_infectious_period": float(s4["strains_0_infectious_period"].mean())}
     out["value"] = out["sampler"]["value"]
     return out
 
