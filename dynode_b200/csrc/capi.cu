@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/dynode_b200.h"
@@ -38,6 +39,7 @@ struct Instance {
   int flow, flags, g, s, chunk;
   LaunchFn save0, saveP, lik0, likP, saveJ, saveJP, likJ0, likJP;
   AdjointFn adjoint;
+  LaunchFn lik1;  // fused log-likelihood with one direction per work item (latency regime of chunk-2 flows)
 };
 
 #define X(IDX, FLOW, FLAGS, G, S)                                                        \
@@ -50,7 +52,8 @@ struct Instance {
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_SAVE_JUMPS>,         \
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK_JUMPS>,                         \
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK_JUMPS>,       \
-   &launch_adjoint_solver<FLOW, FLAGS, G, S>},
+   &launch_adjoint_solver<FLOW, FLAGS, G, S>,                                            \
+   &launch_loglik_single_direction<FLOW, FLAGS, G, S>},
 static const Instance kInstances[] = {
 #include "instances.def"
 };
@@ -148,6 +151,19 @@ static int run_passes(const Instance* inst, SolveArgs& a, int32_t n_wrt, const i
   a.n_pass = (n_wrt + inst->chunk - 1) / inst->chunk;
   for (int k = 0; k < kMaxWrt; ++k) a.wrt[k] = k < n_wrt ? wrt[k] : -1;
   a.write_primal = 1;
+  if (loglik && !jumps && inst->chunk > 1 && n_wrt > 1) {
+    // Few chains: the launch lasts as long as one warp's instruction stream (measured: a lone warp of the config-2
+    // kernel issues 0.28 instructions per cycle, 98 us for 34 steps).  One direction per work item shortens that
+    // stream by a third; the repeated primal is free while the work items do not fill the GPU's resident warps.
+    static const int64_t few = [] { const char* v = getenv("DYNODE_B200_SINGLE_DIRECTION_BELOW"); return v ? atoll(v) : 1184 * 16; }();
+    if (a.B * n_wrt <= few) {
+      SolveArgs a1 = a;
+      a1.n_pass = n_wrt;
+      e = inst->lik1(a1, stream);
+      if (e == cudaSuccess) return 0;
+      if (e != cudaErrorNotSupported) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+    }
+  }
   e = (loglik ? (jumps ? inst->likJP : inst->likP) : (jumps ? inst->saveJP : inst->saveP))(a, stream);
   if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   return 0;

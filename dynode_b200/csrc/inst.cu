@@ -25,4 +25,14 @@ template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_c
 
 template cudaError_t launch_adjoint_solver<I::flow, I::flags, I::g, I::s>(const AdjointArgs&, cudaStream_t);
 
+template <int FLOW, int FLAGS, int G, int S>
+cudaError_t launch_loglik_single_direction(const SolveArgs& a, cudaStream_t stream) {
+  if constexpr (tangent_chunk(FLOW) > 1) {
+    return launch_lane_solver<FLOW, FLAGS, G, S, 1, MODE_LOGLIK>(a, stream);
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+template cudaError_t launch_loglik_single_direction<I::flow, I::flags, I::g, I::s>(const SolveArgs&, cudaStream_t);
+
 }  // namespace dynode

@@ -77,6 +77,13 @@ struct AdjointArgs {
 template <int FLOW, int FLAGS, int G, int S>
 cudaError_t launch_adjoint_solver(const AdjointArgs& a, cudaStream_t stream);
 
+// The fused log-likelihood carrying ONE direction per work item, for the flows whose production chunk is two
+// (FLOW_SIR): at a few chains a launch is as long as one warp's instruction stream, and a work item with one tangent
+// executes two thirds of the instructions of one with two -- the primal is repeated, which costs nothing while the
+// GPU is empty.  cudaErrorNotSupported for flows whose chunk is already one.
+template <int FLOW, int FLAGS, int G, int S>
+cudaError_t launch_loglik_single_direction(const SolveArgs& a, cudaStream_t stream);
+
 // Defined in lane_solver.cuh, explicitly instantiated per model in inst.cu (see instances.def).
 template <int FLOW, int FLAGS, int G, int S, int P, int MODE>
 cudaError_t launch_lane_solver(const SolveArgs& a, cudaStream_t stream);

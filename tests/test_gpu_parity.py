@@ -673,3 +673,25 @@ def test_seip_discontinuity_points_and_sub_save():
     got = torch.cat([sol.ys[0].reshape(B, len(ts7), -1), sol.ys[3].reshape(B, len(ts7), -1)], dim=2).cpu().numpy()
     _assert_close(got, refj)
     assert np.array_equal(sol.stats["num_accepted_steps"].cpu().numpy(), rstj[:, 1])
+
+
+def test_single_direction_work_items_equal_the_two_direction_kernel():
+    """Few chains take the fused log-likelihood with ONE tangent per work item (shorter instruction stream per warp:
+    lower latency), many chains the production kernel with two per item: same lp, same gradient, same step counts."""
+    import torch
+    from dynode_b200 import _lib
+    from dynode_b200.engine import SolverOptions, poisson_loglik_grad
+    big = make_case("sir_age2", 20000)
+    t1 = 100
+    obs = np.full((t1, 2), 3.0) + np.linspace(0, 2, t1)[:, None]
+    ts = np.linspace(0.0, t1, t1 + 1)
+    wrt = [_lib.wrt_id(_lib.P_BETA, 0), _lib.wrt_id(_lib.P_GAMMA, 0)]
+    run = lambda prm: poisson_loglik_grad(big["model"], big["y0"], prm, big["contact"], SolverOptions(t1=t1), ts, 2,
+                                          obs, 1.25, wrt=wrt)
+    lp_b, g_b, st_b = run(big["params"])                                   # 20000 x 2 work items: two per item
+    small = {k: v[:61] for k, v in big["params"].items()}
+    lp_s, g_s, st_s = run(small)                                           # 61 chains: one direction per item
+    torch.cuda.synchronize()
+    assert torch.equal(st_s, st_b[:61])
+    assert torch.allclose(lp_s, lp_b[:61], rtol=1e-13, atol=0)
+    assert torch.allclose(g_s, g_b[:61], rtol=1e-12, atol=1e-12 * float(g_b.abs().max()))
