@@ -120,7 +120,12 @@ class ModelDensity:
         if self._plan is None and not self._plan_tried and Z.is_cuda:
             self._plan_tried = True
             from .potential_plan import compile_plan
-            self._plan, self.plan_reason = compile_plan(self)
+            try:
+                self._plan, self.plan_reason = compile_plan(self)
+            except Exception as exc:  # discovery runs user code: whatever it raises, the composed path still stands
+                import warnings
+                self._plan, self.plan_reason = None, f"compiling the potential failed: {type(exc).__name__}: {exc}"
+                warnings.warn(f"dynode_b200: {self.plan_reason}; evaluating the model through torch.vmap instead")
         if self._plan is not None and Z.is_cuda:
             return self._plan.potential_and_grad(Z.detach())
         return self.potential_and_grad_composed(Z)
