@@ -564,6 +564,7 @@ def test_adjoint_capacity_overflow_falls_back_to_forward_sensitivities(monkeypat
     (4, 1, 2, 4, 3, dict(intro=False)),        # one strain, four tiers
     (2, 3, 3, 2, 1, dict(vaccinate=False)),    # tiers present but nobody is vaccinated; reset + introductions only
     (3, 2, 3, 1, 0, dict(season=False)),       # V = 1: boosters within the single tier
+    (4, 3, 4, 3, 2, {}),                       # n = 1248 (age 4 x hist 8 x vax 3 x wane 4): 10 elements per thread
 ])
 def test_seip_vaccination_kernel_matches_oracle(A, K, W, V, NK, kw):
     """The vaccination extension of the CTA-per-trajectory kernel (tiers, spline rates with the min(.,1) cap, the
@@ -576,7 +577,7 @@ def test_seip_vaccination_kernel_matches_oracle(A, K, W, V, NK, kw):
     from dynode_b200.examples import rhs as ex
     from dynode_b200.simulation import simulate_ensemble
     from tests.cases import make_seipv_case
-    B, t1 = 29, 180
+    B, t1 = (29, 180) if A * (1 << K) * V * (W + 3 * K) < 1000 else (7, 120)
     case = make_seipv_case(B, A=A, K=K, W=W, V=V, NK=NK, t1=t1, **kw)
     ts = np.linspace(0.0, t1, t1 + 1)
     ys, st = seip.solve_ensemble(case["model"], case["y0"], case["params"], case["contact"], case["pop"],
