@@ -411,3 +411,39 @@ def test_cuda_nuts_rounds_reproduce_the_numpy_oracle_on_config_2():
     # step-size feedback amplifies -- so the draws are compared to 1e-3 (the discrete decisions: exactly)
     compare_with_oracle(md.potential_and_grad, pg_single, z0, 30, 15, seed=11, max_tree_depth=6, device="cuda",
                         cuda_kernels=True, atol=1e-3)
+
+
+def test_posterior_of_config_2_matches_an_independent_sampler_on_an_independent_potential():
+    """BASELINE: "posterior summaries statistically indistinguishable".  Left side: the product -- MCMCProcess on the
+    fused CUDA log-likelihood, 256 chains.  Right side: nothing of the product's numerics -- the numpy NUTS oracle
+    (oracle/nuts_np.py) on the host statement of numpyro's config-2 potential whose ODE part is the C++ oracle's
+    frozen-step tangents (tests/test_oracle.py::config2_potential_on_host).  Means agree within Monte-Carlo error."""
+    from dynode_b200.examples import sir_infer_parameters as m
+    from dynode_b200.infer import MCMC, NUTS, PRNGKey
+    from oracle.nuts_np import NutsChain, Tape
+    from tests.test_oracle import config2_potential_on_host
+    dev = torch.device("cuda", 0)
+    obs = m.synthetic_incidence(100).to(dev)
+    mc = MCMC(NUTS(m.model_fused, max_tree_depth=8), num_warmup=200, num_samples=100, num_chains=256, progress_bar=False)
+    mc.run(PRNGKey(3), config=m.get_config(), tf=100, obs_data=obs)
+    s = mc.get_samples()
+    names = list(mc.density.sites)  # column order of z
+    obs_h = obs.cpu().numpy()
+
+    def pg(z):
+        U, dU, *_ = config2_potential_on_host(z[None, :], obs_h, names)
+        return float(U[0]), dU[0]
+
+    draws = []
+    for c in range(3):
+        chain = NutsChain(pg, 2, Tape(41, c, 3, 2), max_tree_depth=8)
+        rec = chain.run(np.zeros(2), 150, 250)[150:]
+        draws.append(np.array([r["z"] for r in rec]))
+    z = torch.as_tensor(np.concatenate(draws), device=dev)
+    ref = mc.density.constrain(z)
+    for name, tol in (("strains_0_r0", 0.02), ("strains_0_infectious_period", 0.12)):
+        a, b = s[name].cpu().numpy(), ref[name].cpu().numpy()
+        # 750 correlated oracle draws: allow 4 standard errors at an effective sample size of ~150
+        se = b.std() / np.sqrt(150.0)
+        assert abs(a.mean() - b.mean()) < max(4 * se, tol), (name, a.mean(), b.mean(), se)
+        assert 0.6 < a.std() / b.std() < 1.6, (name, a.std(), b.std())
