@@ -104,7 +104,7 @@ def _cuda_include() -> str:
         if os.path.isabs(_nvcc()) else "/usr/local/cuda/include"
 
 
-def build_xla_shim(include_dir: str = None, out: str = XLA_LIB) -> str:
+def build_xla_shim(include_dir: str = None, out: str = XLA_LIB, source: str = None) -> str:
     """Compile csrc/xla_ffi_shim.cc (typed XLA-FFI handlers over the C ABI) into libdynode_b200_xla.so.
 
     `include_dir` defaults to jaxlib's FFI headers (`jax.ffi.include_dir()`): raises ImportError in images without
@@ -116,8 +116,8 @@ def build_xla_shim(include_dir: str = None, out: str = XLA_LIB) -> str:
         include_dir = jax.ffi.include_dir()
     build()
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-I", include_dir,
-           "-I", _cuda_include(), os.path.join(CSRC, "xla_ffi_shim.cc"), "-o", out, "-L", HERE, "-ldynode_b200",
-           "-Wl,-rpath,$ORIGIN"]
+           "-I", _cuda_include(), source or os.path.join(CSRC, "xla_ffi_shim.cc"), "-o", out, "-L", HERE,
+           "-ldynode_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + HERE]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"xla shim build failed:\n{r.stdout}\n{r.stderr}")

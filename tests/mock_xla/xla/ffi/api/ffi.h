@@ -50,6 +50,9 @@ template <DataType dtype>
 class Buffer {
  public:
   using T = typename internal::Native<dtype>::type;
+  Buffer() = default;
+  // mock-only: wrap caller memory (tests/mock_xla/shim_driver.cc drives the handlers' bodies with device pointers)
+  Buffer(T* data, std::vector<int64_t> dims) : data_(data), dims_(std::move(dims)) {}
   T* typed_data() const { return data_; }
   void* untyped_data() const { return data_; }
   Span<const int64_t> dimensions() const { return Span<const int64_t>(dims_.data(), dims_.size()); }
@@ -67,6 +70,8 @@ class Buffer {
 template <typename T>
 class Result {
  public:
+  Result() = default;
+  explicit Result(T v) : v_(std::move(v)) {}
   T* operator->() { return &v_; }
   T& operator*() { return v_; }
 
@@ -83,6 +88,7 @@ class Error {
   Error(ErrorCode code, std::string message) : code_(code), message_(std::move(message)) {}
   static Error Success() { return Error(); }
   bool failure() const { return code_ != ErrorCode::kOk; }
+  const std::string& message() const { return message_; }
 
  private:
   ErrorCode code_ = ErrorCode::kOk;

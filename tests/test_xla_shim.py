@@ -64,3 +64,139 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(Bad, Impl, ffi::Ffi::Bind().Ctx<ffi::PlatformStrea
             assert (r.returncode == 0) == ok, r.stderr[-1500:]
             if not ok:
                 assert "do not match its Ffi::Bind() chain" in r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The handlers' BODIES, executed: tests/mock_xla/shim_driver.cc wraps device pointers in the mock's Buffer and calls
+# SolveImpl / LoglikGradImpl.  Results must be bit-identical to the ctypes binding's (same library underneath), so
+# any difference is the shim's own plumbing: the [B][3] season convention, batch-stride detection, jump_ts / row-mask
+# trailing buffers, attribute order.
+def _driver(tmp):
+    import ctypes
+
+    from dynode_b200 import _lib
+
+    _lib.load()
+    lib = _build.build_xla_shim(include_dir=MOCK, out=os.path.join(tmp, "libshim_driver.so"),
+                                source=os.path.join(MOCK, "shim_driver.cc"))
+    L = ctypes.CDLL(lib)
+    L.shim_driver_last_error.restype = ctypes.c_char_p
+    return L
+
+
+def _dev(torch, x, B=None, row=None):
+    if x is None:
+        return None
+    t = torch.as_tensor(x, dtype=torch.float64).cuda().contiguous()
+    if B is not None and t.numel() == row:  # one shared row: the shim sees a buffer without the batch axis
+        t = t.reshape(row)
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,jumps,masked,const_dt", [
+    ("seirs_seasonal", (), False, 0.0),
+    ("seirs_multi_a2s3", (30.0, 61.5), True, 0.0),
+    ("seirs_multi_a2s3", (30.0, 61.5), False, 0.25),  # constant step: the discontinuity points must be ignored
+    ("sir_age_risk32", (), True, 0.0),
+])
+def test_handler_body_of_the_solve_matches_the_ctypes_binding(tmp_path, name, jumps, masked, const_dt):
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from dynode_b200 import _lib, engine
+    from dynode_b200.synthetic import make_case
+
+    B, t1 = 300, 120
+    case = make_case(name, B)
+    model, prm = case["model"], case["params"]
+    G, S, n = model.n_groups, model.n_strains, model.state_size
+    ts = np.linspace(0.0, t1, t1 + 1)
+    # simulate() drops the discontinuity points in constant-step mode, as the reference does (odes.py:113-131); the
+    # shim has to do the same on its own, so the ctypes arm is given none and the shim arm is given both
+    opts = engine.SolverOptions(t1=t1, jump_ts=() if const_dt > 0 else jumps, const_dt=const_dt)
+    save_mask = model.full_mask() if name != "seirs_multi_a2s3" else 0b10001
+    ns = model.saved_size(save_mask)
+    only = (torch.rand(B, device="cuda") < 0.4).view(torch.uint8) if masked else None
+    if only is not None:
+        with engine.only_rows(only):
+            ys0, _, st0 = engine.solve_ensemble(model, case["y0"], prm, case["contact"], opts, ts, save_mask, B=B)
+    else:
+        ys0, _, st0 = engine.solve_ensemble(model, case["y0"], prm, case["contact"], opts, ts, save_mask, B=B)
+
+    L = _driver(str(tmp_path))
+    y0 = _dev(torch, case["y0"])
+    rates = {k: _dev(torch, prm.get(k)) for k in ("beta", "gamma", "sigma", "omega")}
+    season = None
+    if model.flags & _lib.FLAG_SEASONAL:
+        season = _dev(torch, np.hstack([prm["season_amp"], prm["season_phase"], prm["season_period"]]))
+    contact = _dev(torch, case["contact"])
+    tsd, jd = _dev(torch, ts), (_dev(torch, np.asarray(jumps)) if jumps else None)
+    ys1 = torch.zeros((B, len(ts), ns), dtype=torch.float64, device="cuda")
+    st1 = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    assert y0.numel() in (n, B * n)  # one shared row or [B][n]: the shim tells them apart by the leading dimension
+    c = ctypes
+    L.shim_driver_solve.argtypes = ([c.c_void_p] + [c.c_int64] * 7 + [c.c_void_p] * 9 + [c.c_int64, c.c_void_p,
+                                    c.c_int32, c.c_int32, c.c_int64] + [c.c_double] * 4 + [c.c_int64, c.c_double,
+                                    c.c_void_p, c.c_void_p])
+    rc = L.shim_driver_solve(_lib.current_stream_ptr(), B, y0.numel() // n, n, S, G, len(ts), ns, _ptr(y0), _ptr(rates["beta"]),
+                             _ptr(rates["gamma"]), _ptr(rates["sigma"]), _ptr(rates["omega"]), _ptr(season),
+                             _ptr(contact), _ptr(tsd), _ptr(jd), len(jumps), _ptr(only), model.flow, model.flags,
+                             save_mask, float(t1), opts.rtol, opts.atol, const_dt, opts.max_steps,
+                             engine.uniform_save_dt(ts, 0.0, float(t1)), ys1.data_ptr(), st1.data_ptr())
+    assert rc == 0, L.shim_driver_last_error().decode()
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st0)
+    assert torch.equal(ys1, ys0)
+    assert int((st0[:, 0] != 0).sum()) == 0 and bool(ys0.abs().sum() > 0)
+
+
+@pytest.mark.gpu
+def test_handler_body_of_the_loglik_gradient_matches_the_ctypes_binding(tmp_path):
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from dynode_b200 import _lib, engine
+    from dynode_b200.synthetic import make_case
+
+    B, t1 = 257, 100
+    case = make_case("sir_age4", B)
+    model, prm = case["model"], case["params"]
+    G, S, n = model.n_groups, model.n_strains, model.state_size
+    ts = np.linspace(0.0, t1, t1 + 1)
+    obs_comp = model.n_compartments - 1
+    m = model.compartment_sizes()[obs_comp]
+    obs = torch.rand(t1, m, dtype=torch.float64, device="cuda") + 0.1
+    wrt = [_lib.wrt_id(_lib.P_BETA, 0), _lib.wrt_id(_lib.P_GAMMA, 0)]
+    opts = engine.SolverOptions(t1=t1)
+    lp0, g0, st0 = engine.poisson_loglik_grad(model, case["y0"], prm, case["contact"], opts, ts, obs_comp, obs, 2.5,
+                                              wrt=wrt, B=B)
+    L = _driver(str(tmp_path))
+    y0 = _dev(torch, case["y0"])
+    assert y0.numel() == n  # shared initial state: one row, batch stride 0
+    beta, gamma = _dev(torch, prm["beta"]), _dev(torch, prm["gamma"])
+    contact, tsd = _dev(torch, case["contact"]), _dev(torch, ts)
+    lp1 = torch.zeros(B, dtype=torch.float64, device="cuda")
+    g1 = torch.zeros((B, 2), dtype=torch.float64, device="cuda")
+    st1 = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    w = (ctypes.c_int32 * 2)(*wrt)
+    c = ctypes
+    L.shim_driver_loglik_grad.argtypes = ([c.c_void_p] + [c.c_int64] * 7 + [c.c_void_p] * 9 + [c.c_int64, c.c_int32,
+                                          c.c_int32, c.c_int32] + [c.c_double] * 4 + [c.c_int64, c.c_double] +
+                                          [c.c_void_p] * 3)
+    rc = L.shim_driver_loglik_grad(_lib.current_stream_ptr(), B, 1, n, S, G, len(ts), m, y0.data_ptr(), beta.data_ptr(),
+                                   gamma.data_ptr(), None, None, contact.data_ptr(), tsd.data_ptr(), obs.data_ptr(),
+                                   ctypes.cast(w, c.c_void_p), 2, model.flow, model.flags, obs_comp, 2.5, float(t1),
+                                   opts.rtol, opts.atol, opts.max_steps, engine.uniform_save_dt(ts, 0.0, float(t1)),
+                                   lp1.data_ptr(), g1.data_ptr(), st1.data_ptr())
+    assert rc == 0, L.shim_driver_last_error().decode()
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st0) and torch.equal(lp1, lp0) and torch.equal(g1, g0)
