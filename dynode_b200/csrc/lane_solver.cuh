@@ -900,7 +900,11 @@ constexpr int min_blocks(int flow, int p) {
 #ifdef DYN_MINBLOCKS_TANGENT
   return p > 0 ? DYN_MINBLOCKS_TANGENT : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8);
 #else
+#ifdef DYN_MINBLOCKS_P1
+  return p == 1 ? DYN_MINBLOCKS_P1 : (p > 0 ? 1 : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8));
+#else
   return p > 0 ? 1 : (flow == DYNODE_FLOW_SEIRS_C ? 6 : 8);
+#endif
 #endif
 #endif
 }
