@@ -311,6 +311,8 @@ int64_t dynode_probe_dfma(double* sink, int32_t iters, void* stream) {
 }
 
 int dynode_probe_hbm_write(double* dst, int64_t n, void* stream) {
+  if (dst == nullptr || n < 0 || (reinterpret_cast<uintptr_t>(dst) & 15u) != 0)
+    return fail("probe: dst must be a 16-byte aligned device pointer");
   probe_write_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>((double2*)dst, n / 2);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -311,7 +311,10 @@ struct LaneSolver {
       n_saved = run_off;
     }
     if (!lead) off_save[0] = -1;  // S_g is stored once, by the strain-0 lane
-    const bool full_save = a.write_primal && a.save_mask == ((1u << NE) - 1u);
+    // the one-lane-per-row instances store rows as 16-byte pairs: a caller's ys that is only 8-byte aligned takes
+    // the general path (8-byte stores) instead of faulting
+    const bool full_save = a.write_primal && a.save_mask == ((1u << NE) - 1u) &&
+                           (!(L == 1 && NE == 4) || (reinterpret_cast<uintptr_t>(a.ys) & 15u) == 0);
     // save time k: generated arithmetically for build_saveat's uniform grid, else loaded
     auto save_time = [&](int k) -> double {
       if (k >= a.T) return CUDART_INF;

@@ -120,7 +120,8 @@ int dynode_is_supported(const DynodeModelDesc* model);
  *   y0      [B][n]                 (batch_stride 0 = one shared initial state)
  *   save_ts [T]                    build_saveat's linspace grid (odes.py:177-179)
  *   save_comp_mask                 bit c set = compartment c is saved (sub_save_indices, odes.py:182-193)
- *   ys      [B][T][n_saved]        saved compartments concatenated; slots never reached stay +inf
+ *   ys      [B][T][n_saved]        saved compartments concatenated; slots never reached stay +inf.  Any 8-byte
+ *                                  aligned pointer; 16-byte alignment lets the 4-state flows store rows in pairs
  *   stats   [B][4]                 result, accepted, rejected, steps */
 int dynode_solve_f64(const DynodeModelDesc* model, const DynodeSolverDesc* solver, int64_t B,
                      DynodeArray y0, const DynodeParams* params, const double* save_ts, int32_t T,

@@ -696,3 +696,27 @@ def test_single_direction_work_items_equal_the_two_direction_kernel():
     assert torch.equal(st_s, st_b[:61])
     assert torch.allclose(lp_s, lp_b[:61], rtol=1e-13, atol=0)
     assert torch.allclose(g_s, g_b[:61], rtol=1e-12, atol=1e-12 * float(g_b.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["seirs_1bin", "seirs_seasonal", "seirs_multi_a2s3"])
+def test_output_buffer_that_is_only_8_byte_aligned(name):
+    """The C ABI takes any double* for ys.  The one-lane-per-row instances store 16-byte pairs when they can; a
+    buffer offset by one double must give the same bits through 8-byte stores, and nothing outside it is written."""
+    import torch
+    from dynode_b200.engine import SolverOptions, solve_ensemble
+    B, t1 = 515, 90
+    case = make_case(name, B)
+    model = case["model"]
+    ts = np.linspace(0.0, t1, t1 + 1)
+    numel = B * len(ts) * model.state_size
+    opts = SolverOptions(t1=t1)
+    ys0, _, st0 = solve_ensemble(model, case["y0"], case["params"], case["contact"], opts, ts, B=B)
+    buf = torch.full((numel + 4,), -7.25, dtype=torch.float64, device="cuda")
+    assert buf.data_ptr() % 16 == 0
+    out = buf[1:1 + numel]
+    ys1, _, st1 = solve_ensemble(model, case["y0"], case["params"], case["contact"], opts, ts, out=out, B=B)
+    torch.cuda.synchronize()
+    assert ys1.data_ptr() % 16 == 8
+    assert torch.equal(ys1.reshape(-1), ys0.reshape(-1)) and torch.equal(st1, st0)
+    assert float(buf[0]) == -7.25 and bool((buf[1 + numel:] == -7.25).all())
