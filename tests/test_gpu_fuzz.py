@@ -1,0 +1,153 @@
+"""Randomised differential test: option combinations no hand-written case pairs up (compartment mask x grid kind x
+controller x discontinuity points x tangent directions x row mask x ensemble sizes around the warp geometry), the CUDA
+path through the C ABI against the CPU oracle on the same seeded inputs.  Same bar as test_gpu_parity.py: identical
+accepted / rejected / attempted counts, values to 1e-9."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.cases import ALL_CASES, EXTRA_CASES, make_case
+from tests.test_gpu_parity import _assert_close
+
+pytestmark = pytest.mark.gpu
+
+SIZES = (1, 2, 5, 6, 16, 31, 32, 33, 64, 97, 161, 230)
+N_SEEDS = int(os.environ.get("DYNODE_FUZZ_SEEDS", "64"))  # a few thousand have been run; 64 are kept in the suite
+
+
+def _draw(seed):
+    rng = np.random.default_rng(987_000 + seed)
+    name = (ALL_CASES + EXTRA_CASES)[int(rng.integers(len(ALL_CASES + EXTRA_CASES)))]
+    B = int(SIZES[int(rng.integers(len(SIZES)))])
+    t1 = float(rng.choice([7.5, 30.0, 61.0, 100.0]))
+    grid = str(rng.choice(["daily", "step3", "ragged", "inner"]))
+    if grid == "daily":
+        ts = np.linspace(0.0, t1, int(t1 // 1) + 1)
+    elif grid == "step3":
+        ts = np.linspace(0.0, t1, int(t1 // 3) + 1)
+    elif grid == "ragged":  # t0 and t1 included, irregular in between, two points closer than any step
+        inner = np.sort(rng.uniform(0.0, t1, size=int(rng.integers(1, 40))))
+        ts = np.concatenate([[0.0], inner, [inner[-1] + 1e-9 * (t1 - inner[-1])], [t1]])
+    else:  # neither end point saved
+        ts = np.sort(rng.uniform(0.05 * t1, 0.95 * t1, size=int(rng.integers(1, 25))))
+    const_dt = float(rng.choice([0.0, 0.0, 0.0, 0.3, 1.7]))
+    jumps = ()
+    if const_dt == 0.0 and rng.random() < 0.4:
+        jumps = tuple(float(x) for x in np.sort(rng.uniform(0.0, t1, size=int(rng.integers(1, 4)))))
+    tol = [(1e-5, 1e-6), (1e-5, 1e-6), (1e-7, 1e-9), (1e-3, 1e-4)][int(rng.integers(4))]
+    return rng, name, B, t1, ts, const_dt, jumps, tol
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS))
+def test_random_option_combinations_match_the_oracle(seed):
+    import torch
+
+    from dynode_b200 import _lib, engine
+    from oracle import oracle as orc
+
+    rng, name, B, t1, ts, const_dt, jumps, (rtol, atol) = _draw(seed)
+    case = make_case(name, B)
+    model = case["model"]
+    fam, dims, theta, shared = case["oracle"]
+    S = model.n_strains
+    sizes = model.compartment_sizes()
+    ncomp = len(sizes)
+    mask = int(rng.integers(1, 1 << ncomp)) if rng.random() < 0.6 else (1 << ncomp) - 1
+    idx, lo = [], 0
+    for c, m in enumerate(sizes):
+        if mask >> c & 1:
+            idx += list(range(lo, lo + m))
+        lo += m
+    kinds = 2 if model.flow == _lib.FLOW_SIR else 4
+    cand = [(k * 16 + s, k * S + s) for k in range(kinds) for s in range(S)]
+    if model.flags & _lib.FLAG_SEASONAL:
+        cand += [(4 * 16, 4 * S), (5 * 16, 4 * S + 1)]
+    n_wrt = int(rng.choice([0, 0, 1, 2, 3]))
+    pick = [cand[i] for i in rng.choice(len(cand), size=min(n_wrt, len(cand)), replace=False)] if n_wrt else []
+    wrt_e, wrt_o = [p[0] for p in pick], [p[1] for p in pick]
+    only = None
+    if rng.random() < 0.3:
+        only = torch.as_tensor((rng.random(B) < 0.6).astype(np.uint8)).cuda()
+    opts = engine.SolverOptions(t1=t1, rtol=rtol, atol=atol, const_dt=const_dt, jump_ts=jumps)
+    what = f"{name} B={B} t1={t1} T={len(ts)} mask={mask:b} const_dt={const_dt} jumps={jumps} tol={rtol} wrt={wrt_e} only={only is not None}"
+
+    def run():
+        return engine.solve_ensemble(model, case["y0"], case["params"], case["contact"], opts, ts, save_mask=mask,
+                                     wrt=wrt_e, B=B)
+    if only is not None:
+        with engine.only_rows(only):
+            ys, dys, st = run()
+    else:
+        ys, dys, st = run()
+    torch.cuda.synchronize()
+    ref, dref, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, rtol=rtol, atol=atol, const_dt=const_dt,
+                               save_ts=ts, save_idx=idx, wrt=wrt_o, jump_ts=jumps)
+    ys, st = ys.cpu().numpy(), st.cpu().numpy()
+    rows = np.ones(B, bool) if only is None else only.cpu().numpy().astype(bool)
+    assert ys.shape == ref.shape, what
+    assert np.array_equal(st[rows], rst[rows]), what
+    assert not st[~rows].any() and not ys[~rows].any(), what
+    if rows.any():
+        # tight tolerances and coarse ones alike: the two sides run the same arithmetic, so the bar does not move
+        _assert_close(ys[rows], ref[rows])
+        if wrt_e:
+            d = dys.cpu().numpy()
+            assert d.shape == dref.shape, what
+            for p in range(len(wrt_e)):
+                _assert_close(d[rows][..., p], dref[rows][..., p], rtol=1e-8, atol_scale=1e-11)
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS // 2))
+def test_random_fused_loglik_gradients_match_the_oracle(seed):
+    """Forward-sensitivity and discrete-adjoint gradients of the fused Poisson log-likelihood on random models, grids,
+    observed compartments and direction sets."""
+    import torch
+    from scipy.special import gammaln
+
+    from dynode_b200 import _lib, engine
+    from oracle import oracle as orc
+
+    rng, name, B, t1, ts, const_dt, jumps, (rtol, atol) = _draw(10_000 + seed)
+    if len(ts) < 2:
+        ts = np.array([0.0, 0.5 * t1, t1])
+    case = make_case(name, B)
+    model = case["model"]
+    fam, dims, theta, shared = case["oracle"]
+    S = model.n_strains
+    sizes = model.compartment_sizes()
+    obs_comp = int(rng.integers(len(sizes)))
+    lo = sum(sizes[:obs_comp])
+    idx = list(range(lo, lo + sizes[obs_comp]))
+    obs = rng.uniform(0.05, 3.0, size=(len(ts) - 1, sizes[obs_comp]))
+    kinds = 2 if model.flow == _lib.FLOW_SIR else 4
+    cand = [(k * 16 + s, k * S + s) for k in range(kinds) for s in range(S)]
+    if model.flags & _lib.FLAG_SEASONAL:
+        cand += [(4 * 16, 4 * S), (5 * 16, 4 * S + 1)]
+    opts = engine.SolverOptions(t1=t1, rtol=rtol, atol=atol, const_dt=const_dt, jump_ts=jumps)
+    what = f"{name} B={B} t1={t1} T={len(ts)} obs_comp={obs_comp} const_dt={const_dt} jumps={jumps} tol={rtol}"
+    ys, dys, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, rtol=rtol, atol=atol, const_dt=const_dt,
+                             save_ts=ts, save_idx=idx, wrt=[c[1] for c in cand], jump_ts=jumps)
+    lp_ref, g_ref = orc.poisson_incidence(ys, dys, obs)  # includes -lgamma(obs + 1): lp_const on the CUDA side
+    lp_const = float(-gammaln(obs + 1).sum())
+    n_wrt = int(rng.integers(0, len(cand) + 1))
+    pick = sorted(rng.choice(len(cand), size=n_wrt, replace=False).tolist())
+    lp, g, st = engine.poisson_loglik_grad(model, case["y0"], case["params"], case["contact"], opts, ts, obs_comp, obs,
+                                           lp_const, wrt=[cand[i][0] for i in pick], B=B)
+    torch.cuda.synchronize()
+    assert np.array_equal(st.cpu().numpy(), rst), what
+    assert np.allclose(lp.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-9), what
+    if pick:
+        scale = np.abs(g_ref).max() + 1e-300
+        assert np.allclose(g.cpu().numpy(), g_ref[:, pick], rtol=1e-7, atol=1e-10 * scale), what
+    if not jumps:  # the adjoint kernel takes no discontinuity points (the host routes those to forward mode)
+        la, ga, _, sa = engine.poisson_loglik_adjoint(model, case["y0"], case["params"], case["contact"], opts, ts,
+                                                      obs_comp, obs, lp_const, B=B)
+        torch.cuda.synchronize()
+        assert np.array_equal(sa.cpu().numpy(), rst), what
+        assert np.allclose(la.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-9), what
+        acols = [k * S + s for k in range(kinds) for s in range(S)]
+        if model.flags & _lib.FLAG_SEASONAL:
+            acols += [4 * S, 4 * S + 1]
+        scale = np.abs(g_ref).max() + 1e-300
+        assert np.allclose(ga.cpu().numpy()[:, acols], g_ref, rtol=1e-6, atol=1e-9 * scale), what
