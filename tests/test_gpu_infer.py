@@ -447,3 +447,42 @@ def test_posterior_of_config_2_matches_an_independent_sampler_on_an_independent_
         se = b.std() / np.sqrt(150.0)
         assert abs(a.mean() - b.mean()) < max(4 * se, tol), (name, a.mean(), b.mean(), se)
         assert 0.6 < a.std() / b.std() < 1.6, (name, a.std(), b.std())
+
+
+def test_compiled_potential_over_prior_families():
+    """Every pair of prior families on (r0, infectious period) of the config-2 model -- bounded, half-bounded, affine
+    transformed, truncated on one side or both -- compiles into the three-launch evaluation and equals the composed
+    one (bijector + log|J| + log_prob + get_odeparams + fused likelihood + autograd)."""
+    from dynode_b200.config import Strain
+    from dynode_b200.examples import sir_infer_parameters as m
+    from dynode_b200.infer import ModelDensity
+    from dynode_b200.infer import distributions as D
+    dev = torch.device("cuda", 0)
+    aff = lambda base, loc, sc: D.TransformedDistribution(base, D.transforms.AffineTransform(loc, sc))
+    r0_priors = [aff(D.Beta(0.5, 0.5), 1.5, 1), D.Uniform(1.2, 3.0), D.LogNormal(0.7, 0.2), D.Gamma(20.0, 10.0),
+                 D.TruncatedNormal(2.0, 0.5, low=1.1, high=4.0), aff(D.HalfNormal(0.8), 1.1, 1.0),
+                 aff(D.Exponential(1.5), 1.2, 1.0), D.TruncatedNormal(2.0, 0.4, low=1.05)]
+    ip_priors = [D.TruncatedNormal(loc=8, scale=2, low=2, high=15), D.Uniform(3.0, 12.0), D.LogNormal(2.0, 0.2),
+                 D.Gamma(16.0, 2.0), aff(D.Exponential(0.25), 2.5, 1.0), aff(D.Beta(2.0, 3.0), 3.0, 9.0),
+                 D.Normal(7.5, 0.4)]
+    obs = m.synthetic_incidence(100).to(dev)
+    g = torch.Generator(device=dev).manual_seed(23)
+    n = 0
+    for i, pr in enumerate(r0_priors):
+        for j, pi in enumerate(ip_priors):
+            if (i + j) % 2 and i and j:  # every family meets every other side's first entry, half of the rest
+                continue
+            cfg = m.get_config()
+            cfg.parameters.transmission_params.strains = [Strain(strain_name="swo9", r0=pr, infectious_period=pi)]
+            md = ModelDensity(m.model_fused, (), dict(config=cfg, tf=100, obs_data=obs), device=dev)
+            Z = md.init_to_median(1) + 0.3 * torch.randn(65, md.dim, dtype=torch.float64, device=dev, generator=g)
+            U, dU = md.potential_and_grad(Z)
+            assert md._plan is not None, (type(pr).__name__, type(pi).__name__, md.plan_reason)
+            U_c, dU_c = md.potential_and_grad_composed(Z)
+            ok = torch.isfinite(U_c)
+            assert ok.double().mean() > 0.9
+            assert torch.equal(torch.isfinite(U), ok)
+            assert torch.allclose(U[ok], U_c[ok], rtol=1e-10), (i, j, float((U[ok] - U_c[ok]).abs().max()))
+            assert torch.allclose(dU[ok], dU_c[ok], rtol=1e-7, atol=1e-8 * float(dU_c[ok].abs().max())), (i, j)
+            n += 1
+    assert n >= 30
