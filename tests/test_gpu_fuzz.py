@@ -223,3 +223,16 @@ def test_random_immune_history_models_match_the_oracle(seed):
     assert bool((err <= bound).all()), f"max err {err.max():.3e} (scale {scale:.3g}) :: {what}"
     assert np.array_equal(st[:, 0], rst[:, 0]) and int(np.abs(st[:, 1] - rst[:, 1]).max()) <= 1, what
     assert int((st != rst).any(axis=1).sum()) <= 1, what
+
+
+@pytest.mark.parametrize("seed", range(max(8, N_SEEDS // 4)))
+def test_random_nuts_configurations_reproduce_the_numpy_oracle(seed):
+    """The CUDA NUTS round against numpyro's algorithm restated in numpy (oracle/nuts_np.py) on a shared random tape:
+    random targets (correlated Gaussians up to the kernel's 16 dimensions, a heavy-tailed product, a banana), chain
+    counts, depth limits down to 1, dense / diagonal mass, target acceptance, with and without adaptation, warm-up
+    lengths on both sides of the adaptation-window schedule.  Every transition: same depth, leapfrogs, divergence."""
+    from tests.nuts_tape import compare_with_oracle, random_nuts_case
+
+    pg_batched, pg_single, z0, warm, n_draws, atol, kw = random_nuts_case(seed)
+    compare_with_oracle(pg_batched, pg_single, z0, warm, n_draws, seed=1000 + seed, device="cuda",
+                        cuda_kernels=True, atol=atol, **kw)

@@ -72,3 +72,12 @@ def test_oracle_chain_recovers_gaussian_moments():
     assert np.allclose(z.mean(0), MU, atol=0.15)
     assert np.allclose(np.cov(z.T), A, atol=0.35)
     assert 0.6 < np.mean([r["accept_prob"] for r in rec]) < 0.95
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_on_the_torch_round(seed):
+    """tests/test_gpu_fuzz.py's random sampler configurations (targets, chain counts, depth limits, mass matrix kind,
+    adaptation on / off) through the masked-tensor torch round on the CPU."""
+    from tests.nuts_tape import compare_with_oracle, random_nuts_case
+    pg_batched, pg_single, z0, warm, n_draws, atol, kw = random_nuts_case(seed)
+    compare_with_oracle(pg_batched, pg_single, z0, warm, n_draws, seed=1000 + seed, atol=atol, **kw)
