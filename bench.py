@@ -83,13 +83,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: int = 50):
         self.gpu, self.rows, self.proc, self.thr = gpu_index, [], None, None
+        self.period_ms = int(os.environ.get("DYNODE_BENCH_CLOCK_MS", period_ms))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
@@ -434,6 +435,14 @@ def run_c5(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def all_ranks(xs):  # [world][len(xs)]
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [t.tolist()]
+        out = torch.empty((world, len(xs)), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return out.tolist()
+
     tf = 120
     total = args.c5_chains
     lo, hi = rank * total // world, (rank + 1) * total // world
@@ -443,7 +452,8 @@ def run_c5(args):
 
     def nuts_run(num_warmup, num_samples, seed):
         mc = MCMC(NUTS(m5.model_fused, max_tree_depth=args.c5_tree_depth), num_warmup=num_warmup,
-                  num_samples=num_samples, num_chains=chains, progress_bar=False)
+                  num_samples=num_samples, num_chains=chains, progress_bar=False,
+                  sync_every=int(os.environ.get("DYNODE_BENCH_SYNC_EVERY", "4")))
         mc.run(PRNGKey(seed + rank), config=cfg, tf=tf, obs_data=obs)
         return mc
 
@@ -467,12 +477,12 @@ def run_c5(args):
     # ---- untimed warm-up steps: short runs of the same program (module loading, vmap traces, graph capture, NCCL
     # channels for the gather) -- one-time costs of the process, not of a NUTS run
     for w in range(max(args.warmup, 1)):
-        mcw = nuts_run(12, 4, 1000 + 17 * w)
+        mcw = nuts_run(40, 4, 1000 + 17 * w)  # long enough to go through a mass-matrix adaptation window
         predictive_and_gather(mcw, 5 + w)
     barrier()
     sampler_clk = ClockSampler(local)
     sampler_clk.start()
-    walls, evals, rounds, e2e_walls = [], [], [], []
+    walls, evals, rounds, e2e_walls, per_rank, timings = [], [], [], [], [], []
     d2h_bytes = 0
     for k in range(args.steps):
         barrier()
@@ -494,6 +504,8 @@ def run_c5(args):
         e2e_walls.append(reduce_max(t_e2e))
         evals.append(reduce_sum(float(mc.engine.grad_evals)))
         rounds.append(mc.engine.rounds)
+        per_rank.append(all_ranks([t_dev, float(mc.engine.rounds), float(mc.engine.grad_evals)]))
+        timings.append(dict(mc.timing))
     clocks = sampler_clk.stop()
     barrier()
     mean_wall = sum(walls) / len(walls)
@@ -518,8 +530,14 @@ def run_c5(args):
                     "api": "MCMC(NUTS(model)).run + get_samples().cpu() + Predictive + gather_draws + .cpu()"},
             "nuts": {
                 "grad_evals_per_s": value, "mcmc_wall_s": mean_wall, "rounds": rounds,
+                # every rank's own run: a rank is done when its slowest chain is, the job when the slowest rank is
+                "per_rank": [{"wall_s": [r[0] for r in step], "rounds": [int(r[1]) for r in step],
+                              "us_per_round": [1e6 * r[0] / max(r[1], 1.0) for r in step],
+                              "grad_evals": [int(r[2]) for r in step]} for step in per_rank],
                 "grad_evals_per_run": evals, "mean_leapfrogs_per_transition": leap,
                 "cuda_graph": mc.engine.graph_used, "cuda_round_kernels": mc.engine.kernels_used,
+                "graph_recaptures": mc.engine.recaptures,
+                "run_anatomy_rank0": [{k: round(v, 4) for k, v in t.items()} for t in timings],
                 "posterior_mean_r0": [float(allpp[k].mean()) for k in names_r0],
                 "posterior_mean_infectious_period": [float(allpp[k].mean()) for k in names_inf],
                 "truth_r0": list(m5.TRUE_R0), "truth_infectious_period": list(m5.TRUE_INF),

@@ -84,6 +84,7 @@ import threading
 
 class _OnlyState(threading.local):
     mask = None
+    n_rows = None  # how many rows of the mask are set, when the caller knows (only_rows(mask, n_rows=...))
 
 
 _ONLY_TLS = _OnlyState()
@@ -105,20 +106,32 @@ _ONLY = _OnlyProxy()
 class only_rows:
     """Context: ensemble launches made inside it integrate only the rows b with mask[b] != 0 (uint8/bool CUDA
     tensor of the ensemble size; launches of another size ignore it).  Rows left out cost nothing and come
-    back as zeros.  The many-chain NUTS wraps the model evaluation of a round in it with its "chain still
+    back as zeros.  `n_rows` (optional) is an upper bound of the number of rows set, see `rows_to_integrate`.  The many-chain NUTS wraps the model evaluation of a round in it with its "chain still
     running" flags; inside a CUDA-graph capture the mask's address is what gets recorded, so the flags may
     change between replays."""
 
-    def __init__(self, mask):
-        self.mask, self.prev = mask, None
+    def __init__(self, mask, n_rows: Optional[int] = None):
+        self.mask, self.n_rows, self.prev = mask, n_rows, None
 
     def __enter__(self):
-        self.prev, _ONLY[0] = _ONLY[0], self.mask
+        self.prev = (_ONLY[0], _ONLY_TLS.n_rows)
+        _ONLY[0], _ONLY_TLS.n_rows = self.mask, self.n_rows
         return self
 
     def __exit__(self, *exc):
-        _ONLY[0] = self.prev
+        _ONLY[0], _ONLY_TLS.n_rows = self.prev
         return False
+
+
+def rows_to_integrate(B: int) -> int:
+    """B, or the caller's count of the rows an active `only_rows` mask leaves in.  The mask itself lives on the device;
+    this is host knowledge (the NUTS driver reads its active-chain count at its sync points), used where a launch
+    is CHOSEN -- forward sensitivities against the adjoint depends on how many warps will really run."""
+    n = _ONLY_TLS.n_rows
+    m = _ONLY[0]
+    if n is None or m is None or m.numel() != B:
+        return B
+    return max(1, min(int(n), B))
 
 
 def current_row_mask(B: int):

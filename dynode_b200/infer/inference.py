@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import Any, Callable, Dict, Optional
 
+import os
 import torch
 from pydantic import BaseModel, ConfigDict, Field, PositiveInt, PrivateAttr
 
@@ -57,11 +58,14 @@ class MCMC:
         self.engine: Optional[BatchedNUTS] = None
 
     def run(self, rng_key: Optional[ppl.PRNGKey] = None, *args, init_z: Optional[torch.Tensor] = None, **kwargs):
+        import time
         key = rng_key or ppl.PRNGKey(0)
+        t_start = time.perf_counter()
         md = ModelDensity(self.sampler.model, args, kwargs, rng_key=key.fold_in(11))
         self.density = md
         z0 = init_z if init_z is not None else self.sampler.init_strategy(md, self.num_chains)
         z0 = z0.to(md.device)
+        t_setup = time.perf_counter()
         gen = key.fold_in(12).generator(md.device)
         if md.device.type == "cuda":
             torch.cuda.manual_seed(key.fold_in(13).seed % (2**63 - 1))  # graph-replayed rounds draw from it
@@ -70,7 +74,9 @@ class MCMC:
                           target_accept_prob=s.target_accept_prob, dense_mass=s.dense_mass,
                           step_size=s.step_size, adapt_step_size=s.adapt_step_size,
                           adapt_mass_matrix=s.adapt_mass_matrix, generator=gen, cuda_graph=self.cuda_graph,
-                          sync_every=self.sync_every)
+                          sync_every=self.sync_every,
+                          # DYNODE_B200_FIXED_LAUNCH=1: keep the launches chosen for all chains running (A/B knob)
+                          launch_key=None if os.environ.get("DYNODE_B200_FIXED_LAUNCH") else md.launch_key)
         self.engine = eng
         progress = None
         if self.progress_bar:
@@ -92,12 +98,18 @@ class MCMC:
             # occurred (simulation/autograd.py); the count is kept as a diagnostic
             self.adjoint_fallbacks = _engine.adjoint_overflows(reset=True)
         self._samples_z, self._extra, self.last_state = z, extra, last
+        t_sampled = time.perf_counter()  # eng.run ends on host reads of device counters: the device is idle here
         C, N, D = z.shape
         flat = md.constrain(z.reshape(C * N, D), with_deterministic=True)
         latent = set(md.sites)
         self._states_flat = {"z": flat}
         self._states = {"z": {k: v.reshape(C, N, *v.shape[1:]) for k, v in flat.items()}}
         self._latent = latent
+        if md.device.type == "cuda":
+            torch.cuda.synchronize()
+        # where a run's wall time went (seconds): model trace + initial positions | first evaluation (compiles the
+        # potential) | graph capture | the rounds | constraining the draws
+        self.timing = {"setup_s": t_setup - t_start, **eng.timing, "constrain_s": time.perf_counter() - t_sampled}
         return self
 
     def get_samples(self, group_by_chain: bool = False) -> Dict[str, torch.Tensor]:

@@ -130,6 +130,11 @@ class ModelDensity:
             return self._plan.potential_and_grad(Z.detach())
         return self.potential_and_grad_composed(Z)
 
+    def launch_key(self, C: int, n_rows: int):
+        """Hashable description of the launches `potential_and_grad` makes for C rows of which only n_rows run under
+        an `engine.only_rows` mask (None: no choice depends on it)."""
+        return None if self._plan is None else self._plan.launch_key(C, n_rows)
+
     def potential_and_grad_composed(self, Z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """The same through the vmapped Python model and autograd (~35 launches for a DynODE model)."""
         Zr = Z.detach().requires_grad_(True)

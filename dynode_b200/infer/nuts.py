@@ -111,7 +111,8 @@ class BatchedNUTS:
                  max_tree_depth: int = 10, target_accept_prob: float = 0.8, dense_mass: bool = True,
                  step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True,
                  generator: Optional[torch.Generator] = None, cuda_graph: Optional[bool] = None,
-                 sync_every: int = 4, cuda_kernels: Optional[bool] = None):
+                 sync_every: int = 4, cuda_kernels: Optional[bool] = None,
+                 launch_key: Optional[Callable[[int, int], object]] = None):
         self.pg = potential_and_grad
         self.max_depth = int(max_tree_depth)
         self.target = float(target_accept_prob)
@@ -125,6 +126,9 @@ class BatchedNUTS:
         self.grad_evals = 0          # leapfrogs that belong to a tree (what "NUTS grad-evals" counts)
         self.launched_evals = 0      # rounds x chains (includes chains idling at a window boundary)
         self.rounds = 0
+        self._n_running = None  # chains still running, as told to the model's launches (None: all of them)
+        self.launch_key = launch_key  # (chains, chains still running) -> what the model evaluation would launch
+        self.recaptures = 0
         self.graph_used = False
         self.b: Optional[SimpleNamespace] = None
 
@@ -440,7 +444,7 @@ class BatchedNUTS:
         self._lib.check(L.dynode_nuts_round_pre(ctypes.byref(self._st), rnd_n.data_ptr(), rnd_u.data_ptr(), stream))
         # finished chains cost nothing in the model's ensemble launches (engine.only_rows -> DynodeSolverDesc.only)
         from .. import engine as _engine
-        with _engine.only_rows(b.active.view(torch.uint8)):
+        with _engine.only_rows(b.active.view(torch.uint8), n_rows=self._n_running):
             U_new, g_new = self.pg(b.z_new)
         U_new, g_new = U_new.contiguous(), g_new.contiguous()
         self._lib.check(L.dynode_nuts_round_post(ctypes.byref(self._st), U_new.data_ptr(), g_new.data_ptr(),
@@ -459,6 +463,7 @@ class BatchedNUTS:
             self._bind_cuda_state()
         round_impl = self._round_cuda if use_kernels else self._round
         self._round_fn = round_impl
+        self._launch_key_now = self.launch_key(b.C, b.C) if self.launch_key is not None else None
         self.graph_used = False
         if not want or b.dev.type != "cuda":
             return
@@ -472,12 +477,8 @@ class BatchedNUTS:
                     self.rounds += 1
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                round_impl()
-            self._graph = graph
-            self._round_fn = graph.replay
-            self.graph_used = True
+            self._round_impl = round_impl
+            self._capture()
         except Exception as e:  # the SAME round implementation runs eagerly; say that replay is off and why
             import traceback
             import warnings
@@ -490,18 +491,56 @@ class BatchedNUTS:
             warnings.warn(f"BatchedNUTS: CUDA-graph capture of the round failed ({type(e).__name__}: {e}); "
                           f"running rounds eagerly\n{where}")
 
+    def _capture(self):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._round_impl()
+        self._graph = graph
+        self._round_fn = graph.replay
+        self.graph_used = True
+
     # ------------------------------------------------------------------ driver
+    LOOK_EVERY = 64  # rounds between two looks at the number of chains still running
+
+    def _look_at_running_chains(self):
+        """Most rounds of a run belong to the few chains that are still building deep trees (config 5: the slowest of
+        1024 chains takes 4-5x the mean number of leapfrogs).  How the model's gradient is best launched depends on
+        how many rows really run (simulation.autograd.use_adjoint: below a GPU's worth of warps, independent forward
+        directions beat the adjoint's longer dependent chain), and that choice is frozen into the captured graph -- so
+        when the model says its launches would change (`launch_key`), the round is captured again."""
+        n = int(self.b.active.sum())
+        if n <= 0:
+            return
+        key = self.launch_key(self.b.C, n)
+        if key == self._launch_key_now:
+            return
+        self._launch_key_now, self._n_running = key, n
+        if self.graph_used:
+            try:
+                torch.cuda.synchronize()
+                self._round_impl()  # one eager round first: a launch path that is new must not load inside a capture
+                self.rounds += 1
+                torch.cuda.synchronize()
+                self._capture()
+                self.recaptures += 1
+            except Exception:  # keep replaying the graph that exists
+                torch.cuda.synchronize()
+
     def _run_schedule(self, progress: Optional[Callable] = None):
         """Rounds until every chain has walked the whole schedule (one host sync every `sync_every` rounds)."""
         b = self.b
         step = max(1, int(b.nwin) // 10)
         next_mark = step
+        next_look = self.LOOK_EVERY
         while True:
             for _ in range(self.sync_every):
                 self._round_fn()
                 self.rounds += 1
             if not bool(b.any_active):
                 break
+            if self.launch_key is not None and self.kernels_used and self.rounds >= next_look:
+                self._look_at_running_chains()
+                next_look = self.rounds + self.LOOK_EVERY
             if progress is not None:
                 kmin = int(b.k.min())  # the slowest chain's position in the schedule
                 if kmin >= next_mark:
@@ -510,6 +549,8 @@ class BatchedNUTS:
 
     def run(self, z0: torch.Tensor, num_warmup: int, num_samples: int, progress: Optional[Callable] = None):
         """Returns (samples z [C, num_samples, D], per-sample stats dict, final state namespace)."""
+        import time
+        t0 = time.perf_counter()
         self._allocate(z0, num_samples)
         b = self.b
         self._g = self.gen
@@ -524,12 +565,15 @@ class BatchedNUTS:
         self.set_schedule(flags, wlen, num_warmup)
         if self.adapt_ss:
             b.searching.fill_(True)  # warmup_adapter.init: find_reasonable_step_size before the first transition
+        t1 = time.perf_counter()  # the isfinite check above synchronised
         self._prepare_round_fn()
+        t2 = time.perf_counter()
         if len(flags) > 0:
             self._run_schedule(progress)
             if progress is not None:
                 progress(num_warmup + num_samples - 1, self)
         self.grad_evals = int(b.n_useful) + int(b.n_leap.sum())
+        self.timing = {"first_eval_s": t1 - t0, "capture_s": t2 - t1, "rounds_s": time.perf_counter() - t2}
         self.launched_evals = self.rounds * b.C
         stats = {k: v.clone() for k, v in b.out_stats.items()}
         return b.out_z.clone(), stats, b

@@ -77,6 +77,11 @@ class PotentialPlan:
             self._cols[use_adjoint] = m
         return m
 
+    def launch_key(self, C: int, n_rows: int):
+        """What `potential_and_grad` would launch for C rows of which n_rows run (hashable): a sampler that replays a
+        captured graph asks this to learn whether the capture is still the right one."""
+        return ag.use_adjoint(self.cfg.model, len(self.cfg.wrt_cols), self.cfg.opts(), C, n_rows=n_rows)
+
     def potential_and_grad(self, Z: torch.Tensor):
         """U [C], dU/dz [C, D]: pre -> fused log-likelihood -> post, nothing else touches the device."""
         cfg, pl = self.cfg, self.cfg.payload

@@ -207,7 +207,8 @@ class EnsembleSolve(torch.autograd.Function):
         return (ys, stats, dys), (0, 0, 0)
 
 
-def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions, B: int = 1 << 30) -> bool:
+def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions, B: int = 1 << 30,
+                n_rows: Optional[int] = None) -> bool:
     """Forward sensitivities or the discrete adjoint for the fused log-likelihood gradient?
 
     Measured on B200 (profiles/r1/adjoint_vs_forward.md), in units of one primal solve: the adjoint costs
@@ -227,7 +228,10 @@ def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions,
     chunk = 2 if model.flow == _lib.FLOW_SIR else 1
     groups = -(-n_dir // chunk)
     slots = max(1, 32 // (model.n_groups * model.n_strains))
-    warps = -(-B // slots) * groups
+    # rows a row mask leaves out retire at once: what counts is the rows that run (a NUTS run spends most of its
+    # rounds on the few chains that are still building deep trees)
+    rows = engine.rows_to_integrate(B) if n_rows is None else max(1, min(int(n_rows), B))
+    warps = -(-rows // slots) * groups
     if warps <= RESIDENT_WARPS:  # latency regime
         return groups > 8
     return groups * (1.9 if chunk == 2 else 1.45) > ADJOINT_COST
