@@ -22,7 +22,11 @@
 
 namespace dynode {
 
-template <int FLOW, int FLAGS, int G, int S>
+// JUMPS: SolverParams.discontinuity_points (ClipStepSizeController) in the forward sweep, as in
+// lane_solver.cuh: a step that would contain a point ends just before it, the next starts exactly at it with a fresh
+// f0.  The reverse sweep needs nothing for it: it rebuilds every step from its checkpoint (tprev, tnext, y_k) and
+// recomputes f0 there anyway, and y is carried unchanged across the one-ulp gap.
+template <int FLOW, int FLAGS, int G, int S, bool JUMPS = false>
 struct AdjointSolver {
   using LS = LaneSolver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK>;
   using D = typename LS::D;
@@ -206,6 +210,7 @@ struct AdjointSolver {
 
     // =============================== forward sweep ===============================
     double tprev = a.t0, tnext;
+    bool made_jump = false;  // the running step was clipped to end just before a discontinuity point
     {
       const D invN0 = LS::inv_population(y, c);
       LS::rhs(a.t0, y, f[0], c, K, prm, invN0);
@@ -238,6 +243,7 @@ struct AdjointSolver {
         const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / md, 0.2);
         tnext = a.t0 + fmin(100.0 * h0, h1);
       }
+      if constexpr (JUMPS) tnext = LS::clip_to_jumps(a, a.t0, tnext, made_jump);
       tnext = fmin(tnext, t1);
     }
     int32_t n_acc = 0, n_rej = 0, n_steps = 0, save_i = 0;
@@ -273,7 +279,12 @@ struct AdjointSolver {
         dt_next = h * controller_factor_sq(err2, keep);
       }
       double ntprev = keep ? tnext : tprev;
+      bool next_made_jump = false;
+      if constexpr (JUMPS) {
+        if (keep && made_jump) ntprev = nextafter(tnext, CUDART_INF);  // restart exactly at the jump
+      }
       double ntnext = ntprev + dt_next;
+      if constexpr (JUMPS) ntnext = LS::clip_to_jumps(a, ntprev, ntnext, next_made_jump);
       ntprev = fmin(ntprev, t1);
       if (ntnext > t1 - 1e-10) ntnext = keep ? t1 : fma(0.5, t1 - ntprev, ntprev);
       if (stepping && keep) {
@@ -317,6 +328,19 @@ struct AdjointSolver {
         }
         tprev = ntprev;
         tnext = ntnext;
+      }
+      if constexpr (JUMPS) {
+        // no FSAL across a discontinuity: f0 is re-evaluated at (jump, y1) for the trajectories that crossed one
+        const bool crossed = stepping && keep && made_jump;
+        if (__any_sync(0xffffffffu, crossed)) {
+          const D invNj = LS::inv_population(y, c);
+          LS::rhs(tprev, y, ys, c, K, prm, invNj);
+          if (crossed) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) f[0][e] = ys[e];
+          }
+        }
+        if (stepping) made_jump = next_made_jump;
       }
       active = active && (tprev < t1) && (n_steps < a.max_steps);
     }
@@ -497,19 +521,19 @@ struct AdjointSolver {
   }
 };
 
-template <int FLOW, int FLAGS, int G, int S>
+template <int FLOW, int FLAGS, int G, int S, bool JUMPS>
 __global__ void __launch_bounds__(kThreads, 1) adjoint_solver_kernel(const AdjointArgs a) {
-  AdjointSolver<FLOW, FLAGS, G, S>::run(a);
+  AdjointSolver<FLOW, FLAGS, G, S, JUMPS>::run(a);
 }
 
-template <int FLOW, int FLAGS, int G, int S>
+template <int FLOW, int FLAGS, int G, int S, bool JUMPS>
 cudaError_t launch_adjoint_solver(const AdjointArgs& a, cudaStream_t stream) {
-  using AS = AdjointSolver<FLOW, FLAGS, G, S>;
+  using AS = AdjointSolver<FLOW, FLAGS, G, S, JUMPS>;
   if (a.s.B <= 0) return cudaSuccess;
   constexpr int wpc = kThreads / 32;
   const int64_t warps = (a.s.B + AS::TPW - 1) / AS::TPW;
   const int64_t grid = (warps + wpc - 1) / wpc;
-  adjoint_solver_kernel<FLOW, FLAGS, G, S><<<(unsigned)grid, kThreads, 0, stream>>>(a);
+  adjoint_solver_kernel<FLOW, FLAGS, G, S, JUMPS><<<(unsigned)grid, kThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

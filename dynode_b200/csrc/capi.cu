@@ -38,7 +38,7 @@ typedef cudaError_t (*AdjointFn)(const AdjointArgs&, cudaStream_t);
 struct Instance {
   int flow, flags, g, s, chunk;
   LaunchFn save0, saveP, lik0, likP, saveJ, saveJP, likJ0, likJP;
-  AdjointFn adjoint;
+  AdjointFn adjoint, adjointJ;
   LaunchFn lik1;  // fused log-likelihood with one direction per work item (latency regime of chunk-2 flows)
 };
 
@@ -52,7 +52,8 @@ struct Instance {
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_SAVE_JUMPS>,         \
    &launch_lane_solver<FLOW, FLAGS, G, S, 0, MODE_LOGLIK_JUMPS>,                         \
    &launch_lane_solver<FLOW, FLAGS, G, S, tangent_chunk(FLOW), MODE_LOGLIK_JUMPS>,       \
-   &launch_adjoint_solver<FLOW, FLAGS, G, S>,                                            \
+   &launch_adjoint_solver<FLOW, FLAGS, G, S, false>,                                     \
+   &launch_adjoint_solver<FLOW, FLAGS, G, S, true>,                                      \
    &launch_loglik_single_direction<FLOW, FLAGS, G, S>},
 static const Instance kInstances[] = {
 #include "instances.def"
@@ -284,7 +285,6 @@ int dynode_poisson_loglik_adjoint_f64(const DynodeModelDesc* model, const Dynode
   if (!obs || !lp || !grad || !stats) return fail("obs/lp/grad/stats must not be null");
   if (!ckpt || !vsave || cap < 1) return fail("the adjoint needs checkpoint scratch (ckpt, vsave, cap >= 1)");
   if (T < 2) return fail("need at least two save times to form increments");
-  if (solver->n_jump > 0) return fail("unsupported: discontinuity points together with the adjoint");
   AdjointArgs a;
   fill_common(a.s, solver, B, y0, params, save_ts, T);
   a.s.stats = stats;
@@ -298,7 +298,7 @@ int dynode_poisson_loglik_adjoint_f64(const DynodeModelDesc* model, const Dynode
   a.vsave = vsave;
   a.cap = cap;
   if (B == 0) return 0;
-  const cudaError_t e = inst->adjoint(a, (cudaStream_t)stream);
+  const cudaError_t e = (a.s.n_jump > 0 ? inst->adjointJ : inst->adjoint)(a, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -23,7 +23,8 @@ template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_c
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, 0, MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
 template cudaError_t launch_lane_solver<I::flow, I::flags, I::g, I::s, tangent_chunk(I::flow), MODE_LOGLIK>(const SolveArgs&, cudaStream_t);
 
-template cudaError_t launch_adjoint_solver<I::flow, I::flags, I::g, I::s>(const AdjointArgs&, cudaStream_t);
+template cudaError_t launch_adjoint_solver<I::flow, I::flags, I::g, I::s, false>(const AdjointArgs&, cudaStream_t);
+template cudaError_t launch_adjoint_solver<I::flow, I::flags, I::g, I::s, true>(const AdjointArgs&, cudaStream_t);
 
 template <int FLOW, int FLAGS, int G, int S>
 cudaError_t launch_loglik_single_direction(const SolveArgs& a, cudaStream_t stream) {

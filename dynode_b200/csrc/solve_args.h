@@ -74,7 +74,7 @@ struct AdjointArgs {
   double* vsave;      // scratch [B][T][m]: observed compartment at the save times, then its cotangent
   int32_t cap;        // accepted steps that fit the scratch
 };
-template <int FLOW, int FLAGS, int G, int S>
+template <int FLOW, int FLAGS, int G, int S, bool JUMPS>
 cudaError_t launch_adjoint_solver(const AdjointArgs& a, cudaStream_t stream);
 
 // The fused log-likelihood carrying ONE direction per work item, for the flows whose production chunk is two

@@ -220,7 +220,7 @@ def use_adjoint(model: engine.FlowModel, n_dir: int, opts: engine.SolverOptions,
     force = os.environ.get("DYNODE_B200_ADJOINT")
     if force is not None:
         return force == "1" and n_dir > 0
-    if n_dir == 0 or len(opts.jump_ts) > 0:
+    if n_dir == 0:
         return False
     # the adjoint checkpoints every accepted step: [B][cap][n + 2] doubles of scratch
     if B * adjoint_capacity() * (model.state_size + 2) * 8 > ADJOINT_SCRATCH_LIMIT:

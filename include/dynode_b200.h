@@ -65,8 +65,9 @@ typedef struct {
   double save_dt;
   /* SolverParams.discontinuity_points (odes.py:120-131: ClipStepSizeController(jump_ts)): n_jump <= 32
    * sorted times in DEVICE memory; steps end just before a jump and restart at it.  NULL / 0 = none.
-   * Honoured by dynode_solve_f64, dynode_solve_sens_f64 and dynode_poisson_loglik_grad_f64 (tangents ride the
-   * clipped step sequence); dynode_poisson_loglik_adjoint_f64 rejects it. */
+   * Honoured by every entry point: dynode_solve_f64, dynode_solve_sens_f64 and dynode_poisson_loglik_grad_f64
+   * (tangents ride the clipped step sequence) and dynode_poisson_loglik_adjoint_f64 (its forward sweep clips, its
+   * reverse sweep rebuilds every step from its checkpoint). */
   const double* jump_ts;
   int32_t n_jump;
   /* Optional row mask: DEVICE [B] bytes.  When non-NULL, only trajectories with only[b] != 0 are integrated;

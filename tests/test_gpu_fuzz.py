@@ -140,17 +140,16 @@ def test_random_fused_loglik_gradients_match_the_oracle(seed):
     if pick:
         scale = np.abs(g_ref).max() + 1e-300
         assert np.allclose(g.cpu().numpy(), g_ref[:, pick], rtol=1e-7, atol=1e-10 * scale), what
-    if not jumps:  # the adjoint kernel takes no discontinuity points (the host routes those to forward mode)
-        la, ga, _, sa = engine.poisson_loglik_adjoint(model, case["y0"], case["params"], case["contact"], opts, ts,
-                                                      obs_comp, obs, lp_const, B=B)
-        torch.cuda.synchronize()
-        assert np.array_equal(sa.cpu().numpy(), rst), what
-        assert np.allclose(la.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-9), what
-        acols = [k * S + s for k in range(kinds) for s in range(S)]
-        if model.flags & _lib.FLAG_SEASONAL:
-            acols += [4 * S, 4 * S + 1]
-        scale = np.abs(g_ref).max() + 1e-300
-        assert np.allclose(ga.cpu().numpy()[:, acols], g_ref, rtol=1e-6, atol=1e-9 * scale), what
+    la, ga, _, sa = engine.poisson_loglik_adjoint(model, case["y0"], case["params"], case["contact"], opts, ts,
+                                                  obs_comp, obs, lp_const, B=B)
+    torch.cuda.synchronize()
+    assert np.array_equal(sa.cpu().numpy(), rst), what
+    assert np.allclose(la.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-9), what
+    acols = [k * S + s for k in range(kinds) for s in range(S)]
+    if model.flags & _lib.FLAG_SEASONAL:
+        acols += [4 * S, 4 * S + 1]
+    scale = np.abs(g_ref).max() + 1e-300
+    assert np.allclose(ga.cpu().numpy()[:, acols], g_ref, rtol=1e-6, atol=1e-9 * scale), what
 
 
 @pytest.mark.parametrize("seed", range(N_SEEDS // 2))

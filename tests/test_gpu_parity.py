@@ -385,6 +385,21 @@ def test_discontinuity_points_with_sensitivities_and_loglik(name):
         if w_e:
             g = grad.cpu().numpy()
             assert np.all(np.abs(g - g_ref) <= 1e-8 * np.abs(g_ref) + 1e-9 * np.abs(g_ref).max())
+    # the discrete adjoint over the same clipped step sequence (its forward sweep clips, its reverse sweep rebuilds
+    # every step from its checkpoint): same counts, same log-likelihood, same gradient, initial-state gradient finite
+    from dynode_b200 import _lib
+    from dynode_b200.engine import poisson_loglik_adjoint
+    lp_a, g_a, g0_a, st_a = poisson_loglik_adjoint(model, case["y0"], case["params"], case["contact"],
+                                                   SolverOptions(t1=t1, jump_ts=jumps), ts, obs_comp, obs, lp_const,
+                                                   with_y0_grad=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(st_a.cpu().numpy(), rst2)
+    assert np.allclose(lp_a.cpu().numpy(), lp_ref, rtol=1e-10, atol=0)
+    S = model.n_strains
+    cols = [(w >> 4) * S + (w & 15) if (w >> 4) < 4 else 4 * S + ((w >> 4) - 4) for w in wrt_e]
+    ga = g_a.cpu().numpy()[:, cols]
+    assert np.all(np.abs(ga - g_ref) <= 1e-6 * np.abs(g_ref) + 1e-8 * np.abs(g_ref).max())
+    assert bool(torch.isfinite(g0_a).all())
 
 
 def test_fused_loglik_on_a_nonuniform_grid():
