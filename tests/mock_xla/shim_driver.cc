@@ -61,4 +61,27 @@ int shim_driver_loglik_grad(void* stream, int64_t B, int64_t y0_rows, int64_t n,
                                obs_comp, lp_const, 0.0, t1, rtol, atol, 0.0, max_steps, save_dt, lp_r, g_r, st_r));
 }
 
+// DynodeSeipSolve's body: one shared y0 [n], per-draw rates [B][K] / [B][W] and introduction parameters [B][K], shared
+// tables; NULL pointers become zero-element buffers (= absent), which is the handler's own convention
+int shim_driver_seip(void* stream, int64_t B, int64_t n, int64_t A, int64_t K, int64_t W, int64_t V, int64_t NK,
+                     int64_t T, int64_t n_saved, const double* y0, const double* beta, const double* sigma,
+                     const double* gamma, const double* omega, const double* contact, const double* pop,
+                     const double* imm, const double* vbase, const double* vknots, const double* vcoef,
+                     const double* itime, const double* iscale, const double* ipct, const double* iages,
+                     const double* save_ts, const double* jump_ts, int64_t n_jump, int64_t save_mask,
+                     double season_tau, double season_on, double t1, double rtol, double atol, double const_dt,
+                     int64_t max_steps, double save_dt, double* ys, int32_t* stats) {
+  const int64_t H = int64_t(1) << K;
+  U8 mask(nullptr, std::vector<int64_t>{0});
+  F64Out ys_r(F64(ys, {B, T, n_saved}));
+  S32Out st_r(ffi::Buffer<ffi::S32>(stats, {B, 4}));
+  return finish(SeipSolveImpl((cudaStream_t)stream, f64(y0, n), f64(beta, B, K), f64(sigma, B, K), f64(gamma, B, K),
+                              f64(omega, B, W), f64(contact, A, A), f64(pop, A), f64(imm, H * V, W, K),
+                              f64(vbase, A, V, 4), f64(vknots, A, V, NK), f64(vcoef, A, V, NK), f64(itime, B, K),
+                              f64(iscale, B, K), f64(ipct, B, K), f64(iages, K, A), f64(save_ts, T),
+                              f64(jump_ts, n_jump), mask, (int32_t)A, (int32_t)K, (int32_t)W, (int32_t)V,
+                              (int32_t)NK, save_mask, season_tau, season_on, 0.0, t1, rtol, atol, const_dt, max_steps,
+                              save_dt, ys_r, st_r));
+}
+
 }  // extern "C"

@@ -200,3 +200,57 @@ def test_handler_body_of_the_loglik_gradient_matches_the_ctypes_binding(tmp_path
     assert rc == 0, L.shim_driver_last_error().decode()
     torch.cuda.synchronize()
     assert torch.equal(st1, st0) and torch.equal(lp1, lp0) and torch.equal(g1, g0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("A,K,W,V,NK,kw,jumps,save_mask", [
+    (3, 2, 3, 3, 2, {}, (20.0, 41.5), 0b1001),                       # every optional buffer present
+    (2, 3, 4, 2, 0, dict(intro=False), (), 0b1111),                  # no knots, no introductions
+    (4, 2, 3, 1, 0, dict(season=False, intro=False, vaccinate=False), (), 0b1111),  # the plain family
+])
+def test_handler_body_of_the_immune_history_solve_matches_the_ctypes_binding(tmp_path, A, K, W, V, NK, kw, jumps,
+                                                                             save_mask):
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from dynode_b200 import _lib, engine, seip
+    from tests.cases import make_seipv_case
+
+    B, t1 = 9, 60
+    case = make_seipv_case(B, A=A, K=K, W=W, V=V, NK=NK, t1=t1, **kw)
+    model = case["model"]
+    ts = np.linspace(0.0, t1, t1 + 1)
+    opts = engine.SolverOptions(t1=float(t1), jump_ts=jumps)
+    ys0, st0 = seip.solve_ensemble(model, case["y0"], case["params"], case["contact"], case["pop"], case["immunity"],
+                                   opts, ts, vaccination=case["vaccination"], introductions=case["introductions"],
+                                   season_tau=case["season_tau"], save_mask=save_mask)
+    L = _driver(str(tmp_path))
+    d = lambda x: None if x is None else torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+    prm, vac, intro = case["params"], case["vaccination"], case["introductions"]
+    bufs = dict(y0=d(case["y0"]), beta=d(prm["beta"]), sigma=d(prm["sigma"]), gamma=d(prm["gamma"]),
+                omega=d(prm["omega"]), contact=d(case["contact"]), pop=d(case["pop"]), imm=d(case["immunity"]),
+                vbase=d(vac[0]) if vac else None, vknots=d(vac[1]) if vac and NK else None,
+                vcoef=d(vac[2]) if vac and NK else None,
+                itime=d(intro["time"]) if intro else None, iscale=d(intro["scale"]) if intro else None,
+                ipct=d(intro["pct"]) if intro else None, iages=d(intro["ages"]) if intro else None,
+                ts=d(ts), jumps=d(np.asarray(jumps)) if jumps else None)
+    ns = ys0.shape[2]
+    ys1 = torch.zeros((B, len(ts), ns), dtype=torch.float64, device="cuda")
+    st1 = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    c = ctypes
+    L.shim_driver_seip.argtypes = ([c.c_void_p] + [c.c_int64] * 9 + [c.c_void_p] * 17 + [c.c_int64, c.c_int64] +
+                                   [c.c_double] * 6 + [c.c_int64, c.c_double, c.c_void_p, c.c_void_p])
+    tau = case["season_tau"]
+    rc = L.shim_driver_seip(_lib.current_stream_ptr(), B, model.state_size, A, K, W, V, NK, len(ts), ns,
+                            *[_ptr(bufs[k]) for k in ("y0", "beta", "sigma", "gamma", "omega", "contact", "pop", "imm",
+                                                      "vbase", "vknots", "vcoef", "itime", "iscale", "ipct", "iages",
+                                                      "ts", "jumps")],
+                            len(jumps), save_mask, 0.0 if tau is None else float(tau), 0.0 if tau is None else 1.0,
+                            float(t1), opts.rtol, opts.atol, 0.0, opts.max_steps,
+                            engine.uniform_save_dt(ts, 0.0, float(t1)), ys1.data_ptr(), st1.data_ptr())
+    assert rc == 0, L.shim_driver_last_error().decode()
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st0) and torch.equal(ys1, ys0)
+    assert int((st0[:, 0] != 0).sum()) == 0 and bool(ys0.abs().sum() > 0)
