@@ -27,28 +27,52 @@ struct Vec {
   double v[MD];
 };
 
+// The kernels below are instantiated with the dimension at compile time for the common sizes (DT > 0): D is then a
+// constant in these helpers, the loops unroll, and the Vec's live in registers instead of local memory (ncu: at 128
+// chains the run-time-D post kernel took 70 us of a 280 us round, one thread walking ~10 D x D products out of local
+// and global memory).  Same operations in the same order either way.
 __device__ __forceinline__ void load(Vec& x, const double* p, int D) {
+#pragma unroll
   for (int i = 0; i < D; ++i) x.v[i] = p[i];
 }
 __device__ __forceinline__ void store(double* p, const Vec& x, int D) {
+#pragma unroll
   for (int i = 0; i < D; ++i) p[i] = x.v[i];
 }
 __device__ __forceinline__ void copy(double* dst, const double* src, int D) {
+#pragma unroll
   for (int i = 0; i < D; ++i) dst[i] = src[i];
 }
 // y = M x, M row-major [D][D]
 __device__ __forceinline__ void matvec(Vec& y, const double* M, const Vec& x, int D) {
+#pragma unroll
   for (int i = 0; i < D; ++i) {
     double acc = 0.0;
+#pragma unroll
     for (int j = 0; j < D; ++j) acc += M[i * D + j] * x.v[j];
     y.v[i] = acc;
   }
 }
 __device__ __forceinline__ double dot(const Vec& a, const Vec& b, int D) {
   double acc = 0.0;
+#pragma unroll
   for (int i = 0; i < D; ++i) acc += a.v[i] * b.v[i];
   return acc;
 }
+// the inverse mass matrix of a chain: a register copy when the dimension is a small compile-time constant
+template <int DT>
+struct MassCache {
+  static constexpr bool CACHED = DT > 0 && DT <= 8;
+  double m[CACHED ? DT * DT : 1];
+  const double* p;
+  __device__ __forceinline__ explicit MassCache(const double* g) : p(g) {
+    if constexpr (CACHED) {
+#pragma unroll
+      for (int i = 0; i < DT * DT; ++i) m[i] = g[i];
+    }
+  }
+  __device__ __forceinline__ const double* get() const { return CACHED ? m : p; }
+};
 __device__ __forceinline__ double logaddexp(double a, double b) {
   const double m = fmax(a, b);
   if (isinf(m)) return m;  // (-inf, -inf) -> -inf ; (+inf, .) -> +inf
@@ -60,18 +84,21 @@ __device__ __forceinline__ bool is_turning(const double* imm, const Vec& r_left,
   Vec vl, vr, rc;
   matvec(vl, imm, r_left, D);
   matvec(vr, imm, r_right, D);
+#pragma unroll
   for (int i = 0; i < D; ++i) rc.v[i] = r_sum.v[i] - 0.5 * (r_left.v[i] + r_right.v[i]);
   return (dot(vl, rc, D) <= 0.0) || (dot(vr, rc, D) <= 0.0);
 }
 
+template <int DT>
 __global__ void __launch_bounds__(128) nuts_pre_kernel(const DynodeNutsState s, const double* __restrict__ rnd_n,
                                                        const double* __restrict__ rnd_u) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0) *s.any_active = 0;  // _post of this round sets it again if a chain is still running
   if (c >= s.C) return;
-  const int D = s.D;
+  const int D = DT > 0 ? DT : s.D;
   const int64_t o = (int64_t)c * D;
-  const double* imm = s.imm + o * D;
+  const MassCache<DT> mass(s.imm + o * D);
+  const double* imm = mass.get();
   const bool act = s.active[c] != 0;
   const bool probe = act && s.searching[c] != 0;
   if (probe) {
@@ -116,22 +143,26 @@ __global__ void __launch_bounds__(128) nuts_pre_kernel(const DynodeNutsState s, 
   // first half of the leapfrog (idle chains too: their result is discarded)
   const double h = s.s_right[c] ? s.eps[c] : -s.eps[c];
   Vec rh, v;
+#pragma unroll
   for (int i = 0; i < D; ++i) rh.v[i] = s.s_r[o + i] - 0.5 * h * s.s_g[o + i];
   matvec(v, imm, rh, D);
+#pragma unroll
   for (int i = 0; i < D; ++i) s.z_new[o + i] = s.s_z[o + i] + h * v.v[i];
   store(s.r_half + o, rh, D);
 }
 
+template <int DT>
 __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s, const double* __restrict__ U_in,
                                                         const double* __restrict__ g_in,
                                                         const double* __restrict__ rnd_u) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= s.C) return;
-  const int D = s.D, md = s.max_depth;
+  const int D = DT > 0 ? DT : s.D, md = s.max_depth;
   const int64_t o = (int64_t)c * D;
-  const double* imm = s.imm + o * D;
   const bool act = s.active[c] != 0;
   if (!act) return;  // nothing of an idle chain changes in a round
+  const MassCache<DT> mass(s.imm + o * D);
+  const double* imm = mass.get();
   // "some chain is still running": set by every chain that entered this round active (one round late for the last
   // chain to finish, which costs the driver at most one extra host check)
   *s.any_active = 1;
@@ -140,9 +171,11 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   double U_new = U_in[c];
   Vec g_new, r_new, v;
   bool bad = !isfinite(U_new);
+#pragma unroll
   for (int i = 0; i < D; ++i) { g_new.v[i] = g_in[o + i]; bad = bad || !isfinite(g_new.v[i]); }
   if (bad) { U_new = CUDART_INF; for (int i = 0; i < D; ++i) g_new.v[i] = 0.0; }
   const double h = s.s_right[c] ? s.eps[c] : -s.eps[c];
+#pragma unroll
   for (int i = 0; i < D; ++i) r_new.v[i] = s.r_half[o + i] - 0.5 * h * g_new.v[i];
   matvec(v, imm, r_new, D);
   double delta = U_new + 0.5 * dot(r_new, v, D) - s.energy0[c];
@@ -184,6 +217,7 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
     store(s.s_gP + o, g_new, D);
   }
   Vec rsum;
+#pragma unroll
   for (int i = 0; i < D; ++i) rsum.v[i] = first ? r_new.v[i] : s.s_rsum[o + i] + r_new.v[i];
   store(s.s_rsum + o, rsum, D);
   copy(s.s_z + o, s.z_new + o, D);
@@ -213,6 +247,7 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
       Vec rl, vl, rc;
       load(rl, rck + i * D, D);
       matvec(vl, imm, rl, D);
+#pragma unroll
       for (int j = 0; j < D; ++j)
         rc.v[j] = (rsum.v[j] - rsck[i * D + j] + rl.v[j]) - 0.5 * (rl.v[j] + r_new.v[j]);
       s_turn = s_turn || (dot(vl, rc, D) <= 0.0) || (dot(vr, rc, D) <= 0.0);
@@ -243,6 +278,7 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
   store((right ? s.gR : s.gL) + o, g_new, D);
   s.weight[c] = logaddexp(weight, new_w);
   Vec tsum, rL, rR;
+#pragma unroll
   for (int i = 0; i < D; ++i) tsum.v[i] = s.r_sum[o + i] + rsum.v[i];
   store(s.r_sum + o, tsum, D);
   load(rL, s.rL + o, D);
@@ -287,8 +323,11 @@ __global__ void __launch_bounds__(128) nuts_post_kernel(const DynodeNutsState s,
     double* mean = s.wf_mean + o;
     double* m2 = s.wf_m2 + o * D;
     Vec d1;
+#pragma unroll
     for (int i = 0; i < D; ++i) { d1.v[i] = z.v[i] - mean[i]; mean[i] += d1.v[i] / n1; }
+#pragma unroll
     for (int i = 0; i < D; ++i)
+#pragma unroll
       for (int j = 0; j < D; ++j) m2[i * D + j] += d1.v[i] * (z.v[j] - mean[j]);
     s.wf_n[c] = n1;
   }
@@ -375,7 +414,14 @@ int dynode_nuts_round_pre(const DynodeNutsState* st, const double* rnd_n, const 
   if (int rc = check(st)) return rc;
   if (!rnd_n || !rnd_u) return fail_msg("null random-number buffers");
   if (st->C == 0) return 0;
-  nuts_pre_kernel<<<(st->C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st, rnd_n, rnd_u);
+  const dim3 grid((st->C + 127) / 128);
+  switch (st->D) {
+#define DYN_NUTS_CASE(d) case d: nuts_pre_kernel<d><<<grid, 128, 0, (cudaStream_t)stream>>>(*st, rnd_n, rnd_u); break;
+    DYN_NUTS_CASE(1) DYN_NUTS_CASE(2) DYN_NUTS_CASE(3) DYN_NUTS_CASE(4) DYN_NUTS_CASE(5) DYN_NUTS_CASE(6)
+    DYN_NUTS_CASE(7) DYN_NUTS_CASE(8)
+#undef DYN_NUTS_CASE
+    default: nuts_pre_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*st, rnd_n, rnd_u);
+  }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("nuts_pre launch failed: %s", cudaGetErrorString(e));
 }
@@ -385,7 +431,15 @@ int dynode_nuts_round_post(const DynodeNutsState* st, const double* U_new, const
   if (int rc = check(st)) return rc;
   if (!U_new || !g_new || !rnd_u) return fail_msg("null potential / gradient / random-number buffers");
   if (st->C == 0) return 0;
-  nuts_post_kernel<<<(st->C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st, U_new, g_new, rnd_u);
+  const dim3 grid((st->C + 127) / 128);
+  switch (st->D) {
+#define DYN_NUTS_CASE(d) \
+  case d: nuts_post_kernel<d><<<grid, 128, 0, (cudaStream_t)stream>>>(*st, U_new, g_new, rnd_u); break;
+    DYN_NUTS_CASE(1) DYN_NUTS_CASE(2) DYN_NUTS_CASE(3) DYN_NUTS_CASE(4) DYN_NUTS_CASE(5) DYN_NUTS_CASE(6)
+    DYN_NUTS_CASE(7) DYN_NUTS_CASE(8)
+#undef DYN_NUTS_CASE
+    default: nuts_post_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*st, U_new, g_new, rnd_u);
+  }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("nuts_post launch failed: %s", cudaGetErrorString(e));
 }
