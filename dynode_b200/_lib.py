@@ -95,6 +95,7 @@ class SeipParams(ctypes.Structure):
 
 
 NUTS_ADAPT, NUTS_WELFORD, NUTS_SAMPLING, NUTS_END_SLOW, NUTS_END_WARMUP = 1, 2, 4, 8, 16  # DYNODE_NUTS_*
+NUTS_MAX_DIM, NUTS_MAX_DEPTH = 16, 12  # DYNODE_NUTS_MAX_DIM / _MAX_DEPTH of include/dynode_b200_nuts.h
 _NUTS_PTRS = (
     "z U g eps imm msqrt k nwin active need_tree searching fr_dir fr_last sched sched_n energy0 "
     "zL rL gL zR rR gR zP gP r_sum UP weight sum_acc depth nprop turning diverging "

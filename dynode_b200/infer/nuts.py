@@ -106,6 +106,11 @@ def _put(dst: torch.Tensor, mask: torch.Tensor, src) -> None:
     torch.where(m, src, dst, out=dst)
 
 
+def _lib_limits():
+    from .. import _lib
+    return _lib.NUTS_MAX_DIM, _lib.NUTS_MAX_DEPTH
+
+
 class BatchedNUTS:
     def __init__(self, potential_and_grad: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                  max_tree_depth: int = 10, target_accept_prob: float = 0.8, dense_mass: bool = True,
@@ -455,7 +460,10 @@ class BatchedNUTS:
         b = self.b
         want = self.cuda_graph if self.cuda_graph is not None else b.dev.type == "cuda"
         self._g = self.gen
-        use_kernels = self.cuda_kernels if self.cuda_kernels is not None else b.dev.type == "cuda"
+        # the one-thread-per-chain kernels hold a chain's vectors in registers: up to 16 dimensions and 12 doublings
+        # (include/dynode_b200_nuts.h); larger models run the same round as masked tensor operations on the device
+        fits = b.D <= _lib_limits()[0] and self.max_depth <= _lib_limits()[1]
+        use_kernels = self.cuda_kernels if self.cuda_kernels is not None else (b.dev.type == "cuda" and fits)
         if use_kernels and b.dev.type != "cuda":
             raise RuntimeError("the NUTS round kernels need the chains on a CUDA device")
         self.kernels_used = bool(use_kernels)

@@ -522,3 +522,29 @@ def test_sampler_recaptures_its_round_when_the_models_launch_choice_changes(monk
     for k in a:  # same chains, same random numbers; the two gradient modes agree to ~1e-9, the draws stay close
         sd = float(b[k].std())
         assert abs(float(a[k].mean()) - float(b[k].mean())) < 0.25 * sd, k
+
+
+def test_models_beyond_the_round_kernels_limits_run_the_tensor_round_on_the_device():
+    """More than 16 latent dimensions (or more than 12 doublings) do not fit the one-thread-per-chain kernels: the
+    sampler then runs the same round as masked tensor operations on the GPU and says so; forcing the kernels fails
+    loudly."""
+    from dynode_b200._lib import DynodeError
+    from dynode_b200.infer.nuts import BatchedNUTS
+    dev = torch.device("cuda", 0)
+    D = 20
+    mu = torch.linspace(-2.0, 2.0, D, dtype=torch.float64, device=dev)
+    sd = torch.linspace(0.5, 2.0, D, dtype=torch.float64, device=dev)
+
+    def pg(Z):
+        d = (Z - mu) / sd
+        return 0.5 * (d * d).sum(1), d / sd
+
+    eng = BatchedNUTS(pg, max_tree_depth=6, generator=torch.Generator(device=dev).manual_seed(3))
+    zs, stats, _ = eng.run(torch.zeros(64, D, dtype=torch.float64, device=dev), 150, 100)
+    assert not eng.kernels_used
+    flat = zs.reshape(-1, D)
+    assert float(((flat.mean(0) - mu).abs() / sd).max()) < 0.15
+    assert float((flat.std(0) / sd - 1.0).abs().max()) < 0.15
+    forced = BatchedNUTS(pg, max_tree_depth=6, cuda_kernels=True, cuda_graph=False)
+    with pytest.raises(DynodeError, match="dimension"):
+        forced.run(torch.zeros(4, D, dtype=torch.float64, device=dev), 5, 5)

@@ -272,3 +272,14 @@ def test_svi_stops_on_a_non_finite_loss_without_poisoning_the_guide():
         svi.run(PRNGKey(3), 50, progress_bar=False)
     assert calls["n"] < 20  # stopped at the first check after the bad step, not after all 50
     assert all(bool(torch.isfinite(p).all()) for p in guide.parameters())
+
+
+def test_nuts_kernel_limits_match_the_header():
+    import os
+    import re
+
+    from dynode_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                            "dynode_b200_nuts.h")).read()
+    assert int(re.search(r"#define DYNODE_NUTS_MAX_DIM (\d+)", hdr).group(1)) == _lib.NUTS_MAX_DIM
+    assert int(re.search(r"#define DYNODE_NUTS_MAX_DEPTH (\d+)", hdr).group(1)) == _lib.NUTS_MAX_DEPTH
