@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from tests.cases import ALL_CASES, EXTRA_CASES, make_case
-from tests.test_gpu_parity import _assert_close
+from tests.test_gpu_parity import ATOL_SCALE, RTOL, _assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -235,3 +235,61 @@ def test_random_nuts_configurations_reproduce_the_numpy_oracle(seed):
     pg_batched, pg_single, z0, warm, n_draws, atol, kw = random_nuts_case(seed)
     compare_with_oracle(pg_batched, pg_single, z0, warm, n_draws, seed=1000 + seed, device="cuda",
                         cuda_kernels=True, atol=atol, **kw)
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS // 2))
+def test_random_solver_params_through_the_public_api(seed):
+    """`simulate_ensemble(ode, duration, state, ODEParams, SolverParams, sub_save_indices, save_step)` on the registered
+    example right-hand sides with random `SolverParams` (tolerances, constant step, discontinuity points -- dropped in
+    constant-step mode as the reference does), save_step and sub_save_indices (negative and out-of-range indices
+    select nothing, as in the reference's `i in sub_save_indices`), against the oracle called with what the
+    reference's `simulate` would hand diffrax."""
+    from oracle import oracle as orc
+    from tests.test_gpu_parity import _public_api_solver
+
+    rng = np.random.default_rng(777_000 + seed)
+    name = ALL_CASES[int(rng.integers(len(ALL_CASES)))]
+    B = int(rng.choice([1, 3, 33, 70]))
+    case = make_case(name, B)
+    t1 = case["t1"]
+    model = case["model"]
+    ncomp = model.n_compartments
+    const_dt = float(rng.choice([0.0, 0.0, 0.4]))
+    jumps = tuple(float(x) for x in np.sort(rng.uniform(0.0, t1, size=int(rng.integers(0, 3)))))
+    rtol, atol = [(1e-5, 1e-6), (1e-7, 1e-9), (1e-4, 1e-5)][int(rng.integers(3))]
+    step = int(rng.choice([1, 1, 2, 5, 30]))
+    sub = None
+    if rng.random() < 0.5:
+        sub = tuple(int(i) for i in rng.choice(np.arange(-1, ncomp + 1), size=int(rng.integers(1, ncomp + 1)),
+                                               replace=False))
+        if not any(0 <= i < ncomp for i in sub):
+            sub = sub + (0,)
+    ys, st = _public_api_solver(name, B, jump_ts=jumps, const_dt=const_dt, save_step=step, sub_save=sub, rtol=rtol,
+                                atol=atol)
+    sizes = model.compartment_sizes()
+    idx, lo = [], 0
+    for c, m in enumerate(sizes):
+        if sub is None or c in sub:
+            idx += list(range(lo, lo + m))
+        lo += m
+    ts = np.linspace(0.0, t1, int(t1 // step) + 1)
+    fam, dims, theta, shared = case["oracle"]
+    ref, _, rst = orc.solve(fam, dims, case["y0"], theta, shared, t1=t1, rtol=rtol, atol=atol, const_dt=const_dt,
+                            save_ts=ts, save_idx=idx, jump_ts=() if const_dt > 0 else jumps)
+    what = f"{name} B={B} const_dt={const_dt} jumps={jumps} tol={rtol} save_step={step} sub={sub}"
+    assert ys.shape == ref.shape, what
+    # A draw whose error estimate is rounding noise (a SIR epidemic long over, rtol 1e-7: the steps sit on the
+    # controller's lower clip and the estimate is the last bits of 500-people compartments) has no well-defined step
+    # sequence: the kernel's 2^-46 reciprocal and butterfly sums against the oracle's division and sequential sums are
+    # enough to move it (seed 98 of 400: 65 accepted steps against 64 -- the numpy twin of the oracle sides with the
+    # kernel -- and step ends 5e-3 days apart by day 147).  Such rows must be rare and still agree to a fraction of
+    # the solver's tolerance; every other row to 1e-9 with identical counts.
+    scale = float(np.abs(ref[np.isfinite(ref)]).max()) if np.isfinite(ref).any() else 1.0
+    tight = np.abs(ys - ref) <= ATOL_SCALE * scale + RTOL * np.abs(ref)
+    tight |= ys == ref
+    good = (st == rst).all(axis=1) & tight.reshape(B, -1).all(axis=1)
+    assert int((~good).sum()) <= max(1, B // 50), what
+    if (~good).any():
+        pop = float(np.abs(case["y0"]).max())
+        assert np.abs(ys[~good] - ref[~good]).max() <= 0.05 * (atol + rtol * pop), what
+        assert np.array_equal(st[~good][:, 0], rst[~good][:, 0]) and np.abs(st[~good] - rst[~good]).max() <= 3, what

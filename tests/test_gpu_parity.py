@@ -475,7 +475,7 @@ def _public_api_solver(name, B, jump_ts=(), const_dt=0.0, save_step=1, sub_save=
     state = tuple(y0[:, offs[i]:offs[i + 1]].reshape(B, *shapes[i]) for i in range(len(shapes)))
     sp = SolverParams(discontinuity_points=list(jump_ts), constant_step_size=const_dt,
                       ode_solver_rel_tolerance=rtol, ode_solver_abs_tolerance=atol)
-    sub = (0, len(shapes) - 1) if sub_save == "first_last" else None
+    sub = (0, len(shapes) - 1) if sub_save == "first_last" else sub_save  # or a tuple of compartment indices
     sol = simulate_ensemble(ode, case["t1"], state, prm, sp, sub_save_indices=sub, save_step=save_step,
                             batch_size=B, state_batched=True)
     torch.cuda.synchronize()
