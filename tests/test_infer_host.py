@@ -283,3 +283,26 @@ def test_nuts_kernel_limits_match_the_header():
                             "dynode_b200_nuts.h")).read()
     assert int(re.search(r"#define DYNODE_NUTS_MAX_DIM (\d+)", hdr).group(1)) == _lib.NUTS_MAX_DIM
     assert int(re.search(r"#define DYNODE_NUTS_MAX_DEPTH (\d+)", hdr).group(1)) == _lib.NUTS_MAX_DEPTH
+
+
+def test_row_count_hint_reaches_the_forward_versus_adjoint_choice():
+    """engine.only_rows(mask, n_rows=) is host knowledge about a device mask; simulation.autograd.use_adjoint sizes its
+    choice by the rows that run, and ModelDensity.launch_key lets a sampler ask whether a captured round is stale."""
+    import torch
+
+    from dynode_b200 import _lib, engine
+    from dynode_b200.simulation import autograd as ag
+    model = engine.FlowModel(_lib.FLOW_SEIRS_C, 0, 6, 3)
+    opts = engine.SolverOptions(t1=120.0)
+    assert ag.use_adjoint(model, 6, opts, 1024) is True          # 6144 warps: the adjoint's ~3.2 solves win
+    assert ag.use_adjoint(model, 6, opts, 128) is False          # 768 warps: one direction per warp, latency regime
+    assert ag.use_adjoint(model, 6, opts, 1024, n_rows=40) is False
+    mask = torch.ones(1024, dtype=torch.uint8)
+    with engine.only_rows(mask, n_rows=40):
+        assert engine.rows_to_integrate(1024) == 40 and engine.rows_to_integrate(512) == 512
+        assert ag.use_adjoint(model, 6, opts, 1024) is False
+        with engine.only_rows(mask):                             # a nested mask without a count: all rows again
+            assert engine.rows_to_integrate(1024) == 1024
+        assert engine.rows_to_integrate(1024) == 40
+    assert engine.rows_to_integrate(1024) == 1024
+    assert ag.use_adjoint(model, 6, engine.SolverOptions(t1=120.0, jump_ts=(30.0,)), 1024) is True  # jumps: no longer forward-only
