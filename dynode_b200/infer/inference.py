@@ -235,12 +235,19 @@ class SVI:
         for it in range(num_steps):
             opt.zero_grad(set_to_none=True)
             z = self.guide.rsample(self.num_particles, gen)
-            loss = md.potential(z).mean() - self.guide.entropy()  # -ELBO
-            loss.backward()
+            # -ELBO = E_q[U(z)] - H[q] with z = loc + L eps.  U and dU/dz come from the model's own evaluation path
+            # (three launches for a model of the compiled form, infer/potential_plan.py -- not ~35 forward and as
+            # many backward through autograd); the guide's parameters get their gradient through the surrogate
+            # sum(z * dU/dz) / n, whose derivative is E_q[dU/dz . dz/dparams].
+            U, dU = md.potential_and_grad(z.detach())
+            entropy = self.guide.entropy()
+            loss = U.mean() - entropy.detach()
+            ((z * dU).sum() / z.shape[0] - entropy).backward()
             # A non-finite loss (a solve that ran out of max_steps reports NaN) must not reach Adam: one NaN
             # gradient poisons loc / scale for good.  Its gradients are zeroed on the device (no sync), the step is
             # recorded, and the run stops at the next check below.
-            ok = torch.isfinite(loss.detach())
+            ok = torch.isfinite(loss) & torch.isfinite(dU).all()
+            loss = torch.where(ok, loss, torch.full_like(loss, float("nan")))
             for p in self.guide.parameters():
                 if p.grad is not None:
                     p.grad = torch.where(ok, p.grad, torch.zeros_like(p.grad))
