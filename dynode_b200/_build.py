@@ -69,9 +69,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, ext
     for unit in ("capi", "nuts_round", "seip_solver", "ppl_kernels", "host_buffers"):
         obj = os.path.join(BUILD_, f"{unit}.o")
         jobs.append((obj, [nvcc, *flags, "-c", os.path.join(CSRC, f"{unit}.cu"), "-o", obj]))
-    # the immune-history kernels with the vaccination terms: same source, second translation unit (parallel build)
-    obj = os.path.join(BUILD_, "seip_solver_ext.o")
-    jobs.append((obj, [nvcc, *flags, "-DSEIP_EXT_UNIT=1", "-c", os.path.join(CSRC, "seip_solver.cu"), "-o", obj]))
+    # the immune-history kernels with the vaccination terms: same source, one more translation unit per
+    # elements-per-thread width (parallel build)
+    for ept in (4, 8, 12):
+        obj = os.path.join(BUILD_, f"seip_solver_ext{ept}.o")
+        jobs.append((obj, [nvcc, *flags, "-DSEIP_EXT_UNIT=1", f"-DSEIP_EPT={ept}", "-c",
+                           os.path.join(CSRC, "seip_solver.cu"), "-o", obj]))
     jobs.sort(key=lambda j: 0 if "seip_solver" in j[0] else 1)  # the longest units first
 
     def run(job):

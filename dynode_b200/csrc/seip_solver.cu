@@ -484,44 +484,65 @@ size_t seip_smem_bytes(int A, int K, int W, int H, int V, int NK, int n) {
 
 }  // namespace
 
-// This file is compiled twice (dynode_b200/_build.py): SEIP_EXT_UNIT = 0 holds the plain kernels and the C ABI,
-// SEIP_EXT_UNIT = 1 the kernels with the vaccination / introduction / seasonal-reset terms -- two translation units
-// so that the instantiations build in parallel.
+// This file is compiled four times (dynode_b200/_build.py): SEIP_EXT_UNIT = 0 holds the plain kernels and the C ABI;
+// SEIP_EXT_UNIT = 1 with SEIP_EPT = 4 / 8 / 12 the kernels with the vaccination / introduction / seasonal-reset terms,
+// one translation unit per elements-per-thread width -- the instantiations build in parallel (as one unit they took
+// 190 s, three quarters of the whole library's build).
 #ifndef SEIP_EXT_UNIT
 #define SEIP_EXT_UNIT 0
 #endif
 cudaError_t seip_launch_plain(const void* args, size_t smem, int n, cudaStream_t stream);
 cudaError_t seip_launch_ext(const void* args, size_t smem, int n, cudaStream_t stream);
+cudaError_t seip_launch_ext_4(const void* args, size_t smem, cudaStream_t stream);
+cudaError_t seip_launch_ext_8(const void* args, size_t smem, cudaStream_t stream);
+cudaError_t seip_launch_ext_12(const void* args, size_t smem, cudaStream_t stream);
 
-#if SEIP_EXT_UNIT
-cudaError_t seip_launch_ext(const void* args, size_t smem, int n, cudaStream_t stream) {
-  constexpr bool ext = true;
-#else
-cudaError_t seip_launch_plain(const void* args, size_t smem, int n, cudaStream_t stream) {
-  constexpr bool ext = false;
-#endif
-  const SeipArgs& a = *static_cast<const SeipArgs*>(args);
-  const int ept = (n + kSeipThreads - 1) / kSeipThreads;  // elements per thread, rounded up to a compiled width
-  void (*kern)(const SeipArgs) = nullptr;
-#define SEIP_PICK(KK, WW)                                                                                 \
-  {                                                                                                       \
-    if (ept <= 4) kern = seip_solver_kernel<KK, WW, ext, 4>;                                               \
-    else if (ept <= 8) kern = seip_solver_kernel<KK, WW, ext, 8>;                                          \
-    else kern = seip_solver_kernel<KK, WW, ext, 12>;                                                       \
-  }
-  SEIP_PICK(0, 0)
-  // kernels specialised for the common (strains, waning stages) pairs (loops unrolled, index arithmetic folded);
-  // any other shape runs the generic one
-#define SEIP_CASE(KK, WW) if (a.K == KK && a.W == WW) SEIP_PICK(KK, WW)
-  SEIP_CASE(2, 3) SEIP_CASE(2, 4) SEIP_CASE(3, 3) SEIP_CASE(3, 4)
-#undef SEIP_CASE
-#undef SEIP_PICK
+namespace {
+cudaError_t seip_launch_kernel(void (*kern)(const SeipArgs), const SeipArgs& a, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
   if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)a.B, kSeipThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
+}  // namespace
+
+// kernels specialised for the common (strains, waning stages) pairs (loops unrolled, index arithmetic folded); any
+// other shape runs the generic one
+#define SEIP_PICK_KW(EXT, EPT)                                          \
+  kern = seip_solver_kernel<0, 0, EXT, EPT>;                            \
+  if (a.K == 2 && a.W == 3) kern = seip_solver_kernel<2, 3, EXT, EPT>;  \
+  if (a.K == 2 && a.W == 4) kern = seip_solver_kernel<2, 4, EXT, EPT>;  \
+  if (a.K == 3 && a.W == 3) kern = seip_solver_kernel<3, 3, EXT, EPT>;  \
+  if (a.K == 3 && a.W == 4) kern = seip_solver_kernel<3, 4, EXT, EPT>;
+
+#if SEIP_EXT_UNIT
+#define SEIP_CAT_(a, b) a##b
+#define SEIP_CAT(a, b) SEIP_CAT_(a, b)
+cudaError_t SEIP_CAT(seip_launch_ext_, SEIP_EPT)(const void* args, size_t smem, cudaStream_t stream) {
+  const SeipArgs& a = *static_cast<const SeipArgs*>(args);
+  void (*kern)(const SeipArgs) = nullptr;
+  SEIP_PICK_KW(true, SEIP_EPT)
+  return seip_launch_kernel(kern, a, smem, stream);
+}
+#else
+// elements per thread, rounded up to a compiled width
+cudaError_t seip_launch_ext(const void* args, size_t smem, int n, cudaStream_t stream) {
+  const int ept = (n + kSeipThreads - 1) / kSeipThreads;
+  return ept <= 4 ? seip_launch_ext_4(args, smem, stream)
+                  : (ept <= 8 ? seip_launch_ext_8(args, smem, stream) : seip_launch_ext_12(args, smem, stream));
+}
+cudaError_t seip_launch_plain(const void* args, size_t smem, int n, cudaStream_t stream) {
+  const SeipArgs& a = *static_cast<const SeipArgs*>(args);
+  const int ept = (n + kSeipThreads - 1) / kSeipThreads;
+  void (*kern)(const SeipArgs) = nullptr;
+  if (ept <= 4) { SEIP_PICK_KW(false, 4) }
+  else if (ept <= 8) { SEIP_PICK_KW(false, 8) }
+  else { SEIP_PICK_KW(false, 12) }
+  return seip_launch_kernel(kern, a, smem, stream);
+}
+#endif
+#undef SEIP_PICK_KW
 
 }  // namespace dynode
 
